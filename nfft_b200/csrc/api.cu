@@ -1,0 +1,529 @@
+// api.cu -- the extern "C" boundary of libnfftcu.so (include/nfftcu.h): plan context life cycle,
+// node upload/sort, the trafo/adjoint drivers and the plumbing entry points.
+//
+// Driver structure mirrors the reference's nfft_trafo / nfft_adjoint (kernel/nfft/nfft.c:5655-5749):
+//   trafo   = D (deconv.cu) -> F forward (fft.cu)  -> B   (interp.cu)
+//   adjoint = B^T (spread.cu) -> F backward (fft.cu) -> D^T (deconv.cu)
+// with the exact NDFT (ndft.cu) when any N_t <= m or n_t <= 2m+2.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+namespace nfftcu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// I0(x) by its power series sum_k ((x/2)^2)^k/(k!)^2 in long double: all terms positive, so the
+// double result is good to ~1 ulp over the window's argument range.  Takes the role of
+// nfft_bessel_i0 (kernel/util/bessel_i0.c:300-338) inside PHI_HUT (include/infft.h:208).
+long double bessel_i0_series(long double x) {
+  const long double q = 0.25L * x * x;
+  long double term = 1.0L, sum = 1.0L;
+  for (int k = 1; k < 4000; k++) {
+    term *= q / ((long double) k * (long double) k);
+    sum += term;
+    if (term < sum * 0x1p-70L) break;
+  }
+  return sum;
+}
+
+int check_ctx(const nfftcu_ctx *c) {
+  if (!c) {
+    set_error("null context");
+    return NFFTCU_EINVAL;
+  }
+  return NFFTCU_OK;
+}
+
+int bind_device(const nfftcu_ctx *c) {
+  NFFTCU_CUDA(cudaSetDevice(c->device));
+  return NFFTCU_OK;
+}
+
+size_t cbytes(const nfftcu_ctx *c, long long count) { return 2 * real_size(c) * (size_t) count; }
+
+int ensure_staging(nfftcu_ctx *c) {
+  if (!c->fhat_dev && c->N_total > 0) NFFTCU_CUDA(cudaMalloc(&c->fhat_dev, cbytes(c, c->N_total)));
+  if (!c->f_dev && c->M > 0) NFFTCU_CUDA(cudaMalloc(&c->f_dev, cbytes(c, c->M)));
+  return NFFTCU_OK;
+}
+
+struct StageTimer {
+  nfftcu_ctx *c;
+  explicit StageTimer(nfftcu_ctx *ctx) : c(ctx) {}
+  void mark(int i) { if (c->opt_timing) cudaEventRecord(c->ev[i], c->stream); }
+  void finish(int s0, int s1, int s2) {
+    if (!c->opt_timing) return;
+    cudaEventSynchronize(c->ev[3]);
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+    c->stage_ms[s0] = a;
+    c->stage_ms[s1] = b;
+    c->stage_ms[s2] = d;
+  }
+};
+
+int need_nodes(const nfftcu_ctx *c) {
+  if (!c->have_nodes) {
+    set_error("transform called before nfftcu_set_nodes");
+    return NFFTCU_ESTATE;
+  }
+  return NFFTCU_OK;
+}
+
+int trafo_dev_impl(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
+  NFFTCU_TRY(need_nodes(c));
+  if (c->direct_only) return ndft_trafo(c, f_hat_dev, f_dev);
+  StageTimer tm(c);
+  tm.mark(0);
+  NFFTCU_TRY(stage_D(c, f_hat_dev));
+  tm.mark(1);
+  NFFTCU_TRY(stage_F(c, -1));
+  tm.mark(2);
+  NFFTCU_TRY(stage_B(c, f_dev));
+  tm.mark(3);
+  tm.finish(0, 1, 2);   // MEASURE_TIME_t[0..2] = D, F, B (nfft.c:5415,5513,5515-5521)
+  return NFFTCU_OK;
+}
+
+int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
+  NFFTCU_TRY(need_nodes(c));
+  if (c->direct_only) return ndft_adjoint(c, f_dev, f_hat_dev);
+  StageTimer tm(c);
+  tm.mark(0);
+  NFFTCU_TRY(stage_BT(c, f_dev));
+  tm.mark(1);
+  NFFTCU_TRY(stage_F(c, +1));
+  tm.mark(2);
+  NFFTCU_TRY(stage_DT(c, f_hat_dev));
+  tm.mark(3);
+  tm.finish(2, 1, 0);
+  return NFFTCU_OK;
+}
+
+int nodes_ready(nfftcu_ctx *c) {
+  if (!c->direct_only) {
+    NFFTCU_TRY(sort_nodes(c));
+    if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
+  }
+  c->have_nodes = true;
+  c->nodes_version++;
+  return NFFTCU_OK;
+}
+
+__global__ void differs_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                               long long words, int *flag) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  bool diff = false;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride)
+    diff |= (a[i] != b[i]);
+  if (__syncthreads_or(diff) && threadIdx.x == 0) *flag = 1;
+}
+
+// upload x into the staging buffer; returns changed=false when it equals the resident nodes
+int stage_and_compare(nfftcu_ctx *c, const void *x, cudaMemcpyKind kind, bool *changed) {
+  const size_t bytes = real_size(c) * (size_t) c->M * c->d;
+  *changed = true;
+  if (bytes == 0) { *changed = !c->have_nodes; return NFFTCU_OK; }
+  if (!c->x_stage) NFFTCU_CUDA(cudaMalloc(&c->x_stage, bytes));
+  if (!c->x_dev) NFFTCU_CUDA(cudaMalloc(&c->x_dev, bytes));
+  if (!c->diff_flag) NFFTCU_CUDA(cudaMalloc((void **) &c->diff_flag, sizeof(int)));
+  NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x, bytes, kind, c->stream));
+  if (c->have_nodes) {
+    int h = 0;
+    NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->stream));
+    const long long words = (long long) (bytes / 4);
+    long long blocks = (words + 255) / 256;
+    if (blocks > (long long) c->sm_count * 16) blocks = (long long) c->sm_count * 16;
+    differs_kernel<<<(unsigned) blocks, 256, 0, c->stream>>>((const uint32_t *) c->x_stage,
+                                                           (const uint32_t *) c->x_dev, words,
+                                                           c->diff_flag);
+    c->launches++;
+    NFFTCU_CUDA(cudaMemcpyAsync(&h, c->diff_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+    *changed = (h != 0);
+  }
+  if (*changed) { void *t = c->x_dev; c->x_dev = c->x_stage; c->x_stage = t; }
+  return NFFTCU_OK;
+}
+
+}  // namespace
+}  // namespace nfftcu
+
+using namespace nfftcu;
+
+extern "C" {
+
+const char *nfftcu_last_error(void) { return g_err; }
+
+int nfftcu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n,
+                  int64_t m, int64_t M, unsigned flags, int device) {
+  if (!out || !N || !n || d < 1 || d > NFFTCU_MAX_D || m < 0 || M < 0 ||
+      (precision != NFFTCU_DOUBLE && precision != NFFTCU_FLOAT)) {
+    set_error("nfftcu_create: invalid argument (d=%d, m=%lld, M=%lld, precision=%d)", d,
+              (long long) m, (long long) M, precision);
+    return NFFTCU_EINVAL;
+  }
+  if (M > 0xffffffffll) {
+    set_error("nfftcu_create: M=%lld exceeds the 32-bit node index of the sort", (long long) M);
+    return NFFTCU_EINVAL;
+  }
+  int ndev = nfftcu_device_count();
+  if (ndev <= 0 || device < 0 || device >= ndev) {
+    set_error("nfftcu_create: no usable CUDA device (count=%d, requested %d); there is no CPU path",
+              ndev, device);
+    return NFFTCU_ENODEV;
+  }
+  NFFTCU_CUDA(cudaSetDevice(device));
+  nfftcu_ctx *c = new nfftcu_ctx_s();
+  c->prec = precision;
+  c->d = d;
+  c->device = device;
+  c->m = m;
+  c->M = M;
+  c->flags = flags;
+  c->N_total = 1;
+  c->n_total = 1;
+  for (int t = 0; t < d; t++) {
+    if (N[t] < 1 || n[t] < 1) {
+      set_error("nfftcu_create: N[%d]=%lld, n[%d]=%lld", t, (long long) N[t], t, (long long) n[t]);
+      delete c;
+      return NFFTCU_EINVAL;
+    }
+    c->N[t] = N[t];
+    c->n[t] = n[t];
+    c->N_total *= N[t];
+    c->n_total *= n[t];
+    if (N[t] <= m || n[t] <= 2 * m + 2) c->direct_only = true;
+    // sigma and b in the plan precision like init_help (nfft.c:5961-5964, infft.h:216-222)
+    if (precision == NFFTCU_DOUBLE) {
+      c->sigma[t] = (double) n[t] / (double) N[t];
+      c->b[t] = 3.1415926535897932384626433832795028841971693993751 * (2.0 - 1.0 / c->sigma[t]);
+    } else {
+      const float sg = (float) n[t] / (float) N[t];
+      c->sigma[t] = sg;
+      c->b[t] = (double) ((float) 3.1415926535897932384626433832795028841971693993751 *
+                          (2.0f - 1.0f / sg));
+    }
+  }
+  cudaDeviceProp prop;
+  NFFTCU_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  for (int i = 0; i < 4; i++) NFFTCU_CUDA(cudaEventCreate(&c->ev[i]));
+
+  // c_t[k+N/2] = 1/I0(m sqrt(b^2 - (2 pi k/n)^2)), k = -N/2..  (precompute_phi_hut, nfft.c:5754-5770)
+  const long double two_pi = 6.283185307179586476925286766559005768394L;
+  for (int t = 0; t < d; t++) {
+    c->c_host[t].resize((size_t) N[t]);
+    for (long long ks = 0; ks < N[t]; ks++) {
+      const long double w = two_pi * (long double) (ks - N[t] / 2) / (long double) n[t];
+      const long double bb = (long double) c->b[t];
+      const long double arg2 = bb * bb - w * w;
+      const long double arg = (long double) m * sqrtl(arg2 > 0 ? arg2 : 0.0L);
+      c->c_host[t][(size_t) ks] = (double) (1.0L / bessel_i0_series(arg));
+    }
+    const size_t bytes = real_size(c) * (size_t) N[t];
+    NFFTCU_CUDA(cudaMalloc(&c->c_dev[t], bytes));
+    if (precision == NFFTCU_DOUBLE) {
+      NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], c->c_host[t].data(), bytes, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<float> tmp((size_t) N[t]);
+      for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float) c->c_host[t][i];
+      NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], tmp.data(), bytes, cudaMemcpyHostToDevice));
+    }
+  }
+  if (!c->direct_only) {
+    NFFTCU_CUDA(cudaMalloc(&c->grid, cbytes(c, c->n_total)));
+    int r = fft_plan_axes(c);
+    if (r != NFFTCU_OK) {
+      nfftcu_destroy(c);
+      return r;
+    }
+  }
+  *out = c;
+  return NFFTCU_OK;
+}
+
+int nfftcu_destroy(nfftcu_ctx *c) {
+  if (!c) return NFFTCU_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  fft_free_axes(c);
+  for (int t = 0; t < NFFTCU_MAX_D; t++)
+    if (c->c_dev[t]) cudaFree(c->c_dev[t]);
+  void *bufs[] = {c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
+                  c->sort_tmp, c->fhat_dev, c->f_dev};
+  for (void *p : bufs)
+    if (p) cudaFree(p);
+  for (int i = 0; i < 4; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return NFFTCU_OK;
+}
+
+int nfftcu_get_c_phi_inv(nfftcu_ctx *c, int t, void *out_host) {
+  NFFTCU_TRY(check_ctx(c));
+  if (t < 0 || t >= c->d || !out_host) {
+    set_error("nfftcu_get_c_phi_inv: bad dimension %d", t);
+    return NFFTCU_EINVAL;
+  }
+  for (size_t i = 0; i < c->c_host[t].size(); i++) {
+    if (c->prec == NFFTCU_DOUBLE) ((double *) out_host)[i] = c->c_host[t][i];
+    else ((float *) out_host)[i] = (float) c->c_host[t][i];
+  }
+  return NFFTCU_OK;
+}
+
+int nfftcu_get_window_params(nfftcu_ctx *c, void *b_host, void *sigma_host) {
+  NFFTCU_TRY(check_ctx(c));
+  for (int t = 0; t < c->d; t++) {
+    if (c->prec == NFFTCU_DOUBLE) {
+      if (b_host) ((double *) b_host)[t] = c->b[t];
+      if (sigma_host) ((double *) sigma_host)[t] = c->sigma[t];
+    } else {
+      if (b_host) ((float *) b_host)[t] = (float) c->b[t];
+      if (sigma_host) ((float *) sigma_host)[t] = (float) c->sigma[t];
+    }
+  }
+  return NFFTCU_OK;
+}
+
+int nfftcu_set_nodes(nfftcu_ctx *c, const void *x_host) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  if (c->M > 0 && !x_host) {
+    set_error("nfftcu_set_nodes: x is NULL");
+    return NFFTCU_EINVAL;
+  }
+  bool changed = true;
+  NFFTCU_TRY(stage_and_compare(c, x_host, cudaMemcpyHostToDevice, &changed));
+  if (changed) NFFTCU_TRY(nodes_ready(c));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  return NFFTCU_OK;
+}
+
+int nfftcu_set_nodes_dev(nfftcu_ctx *c, const void *x_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  bool changed = true;
+  NFFTCU_TRY(stage_and_compare(c, x_dev, cudaMemcpyDeviceToDevice, &changed));
+  if (changed) NFFTCU_TRY(nodes_ready(c));
+  return NFFTCU_OK;
+}
+
+int64_t nfftcu_nodes_version(nfftcu_ctx *c) { return c ? c->nodes_version : 0; }
+
+int nfftcu_get_index_x(nfftcu_ctx *c, int64_t *index_x_host) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  if (c->M == 0) return NFFTCU_OK;
+  if (c->direct_only || !c->keys_ref || !c->perm_ref) {
+    set_error("nfftcu_get_index_x: plan has no sorted nodes (direct-only plan)");
+    return NFFTCU_ESTATE;
+  }
+  std::vector<uint64_t> keys((size_t) c->M);
+  std::vector<uint32_t> perm((size_t) c->M);
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  NFFTCU_CUDA(cudaMemcpy(keys.data(), c->keys_ref, sizeof(uint64_t) * keys.size(), cudaMemcpyDeviceToHost));
+  NFFTCU_CUDA(cudaMemcpy(perm.data(), c->perm_ref, sizeof(uint32_t) * perm.size(), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < keys.size(); k++) {
+    index_x_host[2 * k] = (int64_t) keys[k];
+    index_x_host[2 * k + 1] = (int64_t) perm[k];
+  }
+  return NFFTCU_OK;
+}
+
+static int host_transform(nfftcu_ctx *c, const void *in_host, void *out_host, int which) {
+  // which: 0 trafo, 1 adjoint, 2 trafo_direct, 3 adjoint_direct
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  NFFTCU_TRY(ensure_staging(c));
+  const bool forward = (which == 0 || which == 2);
+  const size_t in_bytes = forward ? cbytes(c, c->N_total) : cbytes(c, c->M);
+  const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
+  void *in_dev = forward ? c->fhat_dev : c->f_dev;
+  void *out_dev = forward ? c->f_dev : c->fhat_dev;
+  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  int r;
+  switch (which) {
+    case 0: r = trafo_dev_impl(c, in_dev, out_dev); break;
+    case 1: r = adjoint_dev_impl(c, in_dev, out_dev); break;
+    case 2: r = ndft_trafo(c, in_dev, out_dev); break;
+    default: r = ndft_adjoint(c, in_dev, out_dev); break;
+  }
+  if (r != NFFTCU_OK) return r;
+  if (out_bytes) NFFTCU_CUDA(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  return NFFTCU_OK;
+}
+
+int nfftcu_trafo(nfftcu_ctx *c, const void *f_hat_host, void *f_host) {
+  return host_transform(c, f_hat_host, f_host, 0);
+}
+int nfftcu_adjoint(nfftcu_ctx *c, const void *f_host, void *f_hat_host) {
+  return host_transform(c, f_host, f_hat_host, 1);
+}
+int nfftcu_trafo_direct(nfftcu_ctx *c, const void *f_hat_host, void *f_host) {
+  return host_transform(c, f_hat_host, f_host, 2);
+}
+int nfftcu_adjoint_direct(nfftcu_ctx *c, const void *f_host, void *f_hat_host) {
+  return host_transform(c, f_host, f_hat_host, 3);
+}
+
+int nfftcu_trafo_dev(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  return trafo_dev_impl(c, f_hat_dev, f_dev);
+}
+int nfftcu_adjoint_dev(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  return adjoint_dev_impl(c, f_dev, f_hat_dev);
+}
+int nfftcu_trafo_direct_dev(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  return ndft_trafo(c, f_hat_dev, f_dev);
+}
+int nfftcu_adjoint_direct_dev(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  return ndft_adjoint(c, f_dev, f_hat_dev);
+}
+
+static int need_grid(nfftcu_ctx *c) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  if (c->direct_only) {
+    set_error("stage call on a direct-only plan (some N_t <= m or n_t <= 2m+2): no grid");
+    return NFFTCU_ESTATE;
+  }
+  return NFFTCU_OK;
+}
+
+int nfftcu_stage_D(nfftcu_ctx *c, const void *f_hat_dev) {
+  NFFTCU_TRY(need_grid(c));
+  return stage_D(c, f_hat_dev);
+}
+int nfftcu_stage_F(nfftcu_ctx *c, int sign) {
+  NFFTCU_TRY(need_grid(c));
+  return stage_F(c, sign < 0 ? -1 : +1);
+}
+int nfftcu_stage_B(nfftcu_ctx *c, void *f_dev) {
+  NFFTCU_TRY(need_grid(c));
+  NFFTCU_TRY(need_nodes(c));
+  return stage_B(c, f_dev);
+}
+int nfftcu_stage_BT(nfftcu_ctx *c, const void *f_dev) {
+  NFFTCU_TRY(need_grid(c));
+  NFFTCU_TRY(need_nodes(c));
+  return stage_BT(c, f_dev);
+}
+int nfftcu_stage_DT(nfftcu_ctx *c, void *f_hat_dev) {
+  NFFTCU_TRY(need_grid(c));
+  return stage_DT(c, f_hat_dev);
+}
+void *nfftcu_grid_ptr(nfftcu_ctx *c) { return c ? c->grid : nullptr; }
+
+int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
+  NFFTCU_TRY(check_ctx(c));
+  switch (option) {
+    case NFFTCU_OPT_TIMING: c->opt_timing = (int) value; break;
+    case NFFTCU_OPT_PSI_TABLE: c->opt_psi_table = (int) value; break;
+    case NFFTCU_OPT_B_KERNEL: c->opt_b_kernel = (int) value; break;
+    case NFFTCU_OPT_NODE_ORDER: c->opt_node_order = (int) value; break;
+    default:
+      set_error("nfftcu_set_option: unknown option %d", option);
+      return NFFTCU_EINVAL;
+  }
+  return NFFTCU_OK;
+}
+
+int nfftcu_set_stream(nfftcu_ctx *c, void *cuda_stream) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  if (c->stream) NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (cuda_stream) {
+    c->stream = (cudaStream_t) cuda_stream;
+    c->own_stream = false;
+  } else {
+    NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return NFFTCU_OK;
+}
+
+void *nfftcu_get_stream(nfftcu_ctx *c) { return c ? (void *) c->stream : nullptr; }
+
+int nfftcu_sync(nfftcu_ctx *c) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  return NFFTCU_OK;
+}
+
+int nfftcu_stage_times(nfftcu_ctx *c, float ms[3]) {
+  NFFTCU_TRY(check_ctx(c));
+  for (int i = 0; i < 3; i++) ms[i] = c->stage_ms[i];
+  return NFFTCU_OK;
+}
+
+int64_t nfftcu_launch_count(nfftcu_ctx *c) { return c ? c->launches : 0; }
+
+int nfftcu_malloc_device(void **ptr, size_t bytes, int device) {
+  NFFTCU_CUDA(cudaSetDevice(device));
+  NFFTCU_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+  return NFFTCU_OK;
+}
+int nfftcu_free_device(void *ptr) {
+  if (ptr) NFFTCU_CUDA(cudaFree(ptr));
+  return NFFTCU_OK;
+}
+int nfftcu_malloc_pinned(void **ptr, size_t bytes) {
+  NFFTCU_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return NFFTCU_OK;
+}
+int nfftcu_free_pinned(void *ptr) {
+  if (ptr) NFFTCU_CUDA(cudaFreeHost(ptr));
+  return NFFTCU_OK;
+}
+int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
+  NFFTCU_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return NFFTCU_OK;
+}
+int nfftcu_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes) {
+  NFFTCU_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return NFFTCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// common.cuh -- internal declarations shared by the translation units of libnfftcu.so.
+// Not part of the public boundary (that is include/nfftcu.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nfftcu.h"
+
+namespace nfftcu {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define NFFTCU_CUDA(call)                                                                       \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::nfftcu::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                    \
+                          cudaGetErrorString(e__));                                             \
+      return NFFTCU_ECUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+#define NFFTCU_TRY(call)                                                                        \
+  do {                                                                                          \
+    int r__ = (call);                                                                           \
+    if (r__ != NFFTCU_OK) return r__;                                                           \
+  } while (0)
+
+// ---- scalar/complex type traits ----------------------------------------------------------------
+template <typename T> struct Cplx;
+template <> struct Cplx<double> { typedef double2 type; };
+template <> struct Cplx<float> { typedef float2 type; };
+
+template <typename T> __host__ __device__ inline typename Cplx<T>::type make_c(T re, T im);
+template <> __host__ __device__ inline double2 make_c<double>(double re, double im) { return make_double2(re, im); }
+template <> __host__ __device__ inline float2 make_c<float>(float re, float im) { return make_float2(re, im); }
+
+// ---- plan context -----------------------------------------------------------------------------
+struct FftAxis {
+  int64_t len = 0;
+  void *tw = nullptr;   // len complex (plan precision): exp(-2 pi i q / len)
+  int kind = 0;         // 0: len==1, 1: shared-memory Stockham (power of two), 2: O(len^2) table DFT
+};
+
+}  // namespace nfftcu
+
+struct nfftcu_ctx_s {
+  int prec = NFFTCU_DOUBLE;
+  int d = 0;
+  int device = 0;
+  int64_t N[NFFTCU_MAX_D] = {0}, n[NFFTCU_MAX_D] = {0};
+  int64_t m = 0, M = 0, N_total = 0, n_total = 0;
+  unsigned flags = 0;
+  bool direct_only = false;           // any N_t <= m or n_t <= 2m+2 (nfft.c:5658-5664)
+  double b[NFFTCU_MAX_D] = {0}, sigma[NFFTCU_MAX_D] = {0};
+  std::vector<double> c_host[NFFTCU_MAX_D];   // c_phi_inv in double
+  void *c_dev[NFFTCU_MAX_D] = {nullptr};      // c_phi_inv in plan precision
+  void *grid = nullptr;                       // n_total complex
+  nfftcu::FftAxis fft[NFFTCU_MAX_D];
+
+  // nodes
+  bool have_nodes = false;
+  void *x_dev = nullptr;            // M*d reals, caller order
+  void *x_stage = nullptr;          // upload target, compared against x_dev before re-sorting
+  int *diff_flag = nullptr;         // device flag written by the compare kernel
+  int64_t nodes_version = 0;
+  void *x_sorted = nullptr;         // M*d reals, processing order
+  uint32_t *perm = nullptr;         // processing order -> original node index
+  void *keys_ref = nullptr;         // sorted reference keys (uint64), for index_x
+  uint32_t *perm_ref = nullptr;     // reference permutation (== perm when node order is the reference key)
+  void *psi_table = nullptr;        // optional: M * d * (2m+2) reals in processing order
+  void *sort_tmp = nullptr;         // scratch kept between set_nodes calls
+  size_t sort_tmp_bytes = 0;
+
+  // staging buffers for the host-pointer API
+  void *fhat_dev = nullptr;
+  void *f_dev = nullptr;
+
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[3] = {0.f, 0.f, 0.f};
+  int64_t launches = 0;
+
+  int opt_timing = 0;
+  int opt_psi_table = 0;
+  int opt_b_kernel = 0;
+  int opt_node_order = 0;
+  int sm_count = 148;
+};
+
+namespace nfftcu {
+
+inline size_t real_size(const nfftcu_ctx *c) { return c->prec == NFFTCU_DOUBLE ? 8 : 4; }
+
+// ---- stage entry points, one per translation unit ---------------------------------------------
+int sort_nodes(nfftcu_ctx *c);                                      // sort.cu
+int stage_D(nfftcu_ctx *c, const void *f_hat_dev);                  // deconv.cu
+int stage_DT(nfftcu_ctx *c, void *f_hat_dev);                       // deconv.cu
+int fft_plan_axes(nfftcu_ctx *c);                                   // fft.cu
+void fft_free_axes(nfftcu_ctx *c);                                  // fft.cu
+int stage_F(nfftcu_ctx *c, int sign);                               // fft.cu
+int stage_B(nfftcu_ctx *c, void *f_dev);                            // interp.cu
+int stage_BT(nfftcu_ctx *c, const void *f_dev);                     // spread.cu
+int build_psi_table(nfftcu_ctx *c);                                 // interp.cu
+int ndft_trafo(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev);  // ndft.cu
+int ndft_adjoint(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev);// ndft.cu
+
+// ---- Kaiser-Bessel window, evaluated in double for both precisions ----------------------------
+// phi(t) with t = n*(x - l/n) the distance in grid units, s = m^2 - t^2:
+//   s>0: sinh(b sqrt(s))/(pi sqrt(s)); s<0: sin(b sqrt(-s))/(pi sqrt(-s)); s==0: b/pi
+// (include/infft.h:209-215 of the reference; NOT truncated outside |t|<=m).
+__device__ __forceinline__ double kb_phi(double t, double m2, double b) {
+  const double kInvPi = 0.31830988618379067153776752674502872;
+  const double s = m2 - t * t;
+  if (s > 0.0) {
+    const double r = sqrt(s);
+    return sinh(b * r) * kInvPi / r;
+  }
+  if (s < 0.0) {
+    const double r = sqrt(-s);
+    return sin(b * r) * kInvPi / r;
+  }
+  return b * kInvPi;
+}
+
+// c = floor(x*n) evaluated in the plan's precision exactly as the reference's uo()
+// (nfft.c:324-332): one rounded multiply, then floor.
+__device__ __forceinline__ long long cell_of(double x, long long n) {
+  return (long long) floor(__dmul_rn(x, (double) n));
+}
+__device__ __forceinline__ long long cell_of(float x, long long n) {
+  return (long long) floorf(__fmul_rn(x, (float) n));
+}
+
+}  // namespace nfftcu

@@ -1,0 +1,376 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the drop-in
+boundary: the reference-facing plan API of libnfft3_b200.so (nfft_b200.plan.Plan) or the C ABI of
+libnfftcu.so (nfft_b200.cabi.Engine); the CPU oracle / reference build are only the checker.
+
+Tolerances: fp64 rel-l2 <= 1e-12, fp32 rel-l2 <= 1e-5 against the reference's own NFFT output
+(BASELINE.json north_star); sort permutation bit-exact; against the exact-NDFT fixtures the
+reference's own bound (tests/nfft.c:217-284).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+from common import REF_CASES, make_case, oracle, rel_l2
+from nfft_b200 import cabi, plan_abi as abi
+from nfft_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-12, "float": 1e-5}
+FIX = np.load(common.GOLDEN + "/ndft_fixtures.npz")
+REFOUT = np.load(common.GOLDEN + "/ref_outputs.npz")
+NAMES = sorted({k.split("/")[0] for k in FIX.files})
+BASE = abi.PRE_PHI_HUT | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT | abi.FFT_OUT_OF_PLACE
+
+
+def next_power_of_2(x):
+    return x + 1 if x < 2 else 1 << (int(x) - 1).bit_length()
+
+
+def run_plan(spec, precision, x, fh, f, flags=None):
+    """init_guru -> x -> precompute -> trafo -> adjoint, like tests/nfft.c:check_single."""
+    p = Plan.init_guru(spec["d"], spec["N"], spec["M"], spec["n"], spec["m"],
+                       spec["flags"] if flags is None else flags, precision=precision)
+    p.x[:] = x
+    if p.flags & abi.PRE_ONE_PSI:
+        p.precompute_one_psi()
+    p.f_hat[:] = fh
+    p.trafo()
+    out_f = p.f.copy()
+    p.f[:] = f
+    p.adjoint()
+    out_fh = p.f_hat.copy()
+    perm = p.index_x[:, 1].copy() if (p.flags & abi.NFFT_SORT_NODES) else None
+    p.finalize()
+    return out_f, out_fh, perm
+
+
+# ---- (1) the reference's known-answer fixtures, with the reference's initialiser matrix -------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("initializer", ["init", "init_nd", "guru_pre_psi", "guru_pre_full_psi", "guru_no_psi"])
+@pytest.mark.parametrize("name", NAMES)
+def test_ndft_fixture(name, initializer, precision):
+    N = [int(v) for v in FIX[name + "/N"]]
+    x, fh, f = FIX[name + "/x"], FIX[name + "/f_hat"], FIX[name + "/f"]
+    d, M = len(N), x.shape[0]
+    m = 8 if precision == "double" else 4
+    n = [2 * next_power_of_2(v) for v in N]
+    if initializer == "init":
+        p = Plan.init(d, N, M, precision=precision)
+    elif initializer == "init_nd":
+        p = Plan.init_nd(N, M, precision=precision)
+    else:
+        extra = {"guru_pre_psi": abi.PRE_PSI, "guru_pre_full_psi": abi.PRE_FULL_PSI,
+                 "guru_no_psi": abi.NFFT_SORT_NODES}[initializer]
+        p = Plan.init_guru(d, N, M, n, m, BASE | extra, precision=precision)
+    p.x[:] = x
+    if p.check() is not None:       # odd N etc.: the reference reports OK-skipped (tests/nfft.c:313-324)
+        direct_ok = all(v <= p.m for v in N)
+        if not direct_ok:
+            p.finalize()
+            pytest.skip(p.check() or "nfft_check")
+    if p.flags & abi.PRE_ONE_PSI:
+        p.precompute_one_psi()
+    bound = common.kb_error_bound(p.m, 2.0, precision)
+    if str(FIX[name + "/kind"]) == "trafo":
+        p.f_hat[:] = fh
+        p.trafo_nd() if initializer == "init_nd" else p.trafo()
+        err = np.max(np.abs(p.f - f)) / np.sum(np.abs(fh))
+    else:
+        p.f[:] = f
+        p.adjoint_nd() if initializer == "init_nd" else p.adjoint()
+        err = np.max(np.abs(p.f_hat - fh)) / np.sum(np.abs(f))
+    p.finalize()
+    assert err < bound, (name, initializer, err, bound)
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", ["nfft_1d_50_50", "nfft_2d_20_20_50", "nfft_3d_10_10_10_10",
+                                  "nfft_adjoint_1d_20_50", "nfft_adjoint_2d_10_20_20",
+                                  "nfft_adjoint_3d_10_10_10_10"])
+def test_direct_fixture(name, precision):
+    """nfft_trafo_direct / nfft_adjoint_direct to 48 eps (tests/nfft.c:211-215)."""
+    N = [int(v) for v in FIX[name + "/N"]]
+    x, fh, f = FIX[name + "/x"], FIX[name + "/f_hat"], FIX[name + "/f"]
+    p = Plan.init(len(N), N, x.shape[0], precision=precision)
+    p.x[:] = x
+    eps = np.finfo(p.api.real).eps
+    if str(FIX[name + "/kind"]) == "trafo":
+        p.f_hat[:] = fh
+        p.trafo_direct()
+        err = np.max(np.abs(p.f - f)) / np.sum(np.abs(fh))
+    else:
+        p.f[:] = f
+        p.adjoint_direct()
+        err = np.max(np.abs(p.f_hat - fh)) / np.sum(np.abs(f))
+    p.finalize()
+    assert err < 48 * eps
+
+
+# ---- (2) outputs of the reference itself (committed golden vectors) -----------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("case", sorted(REF_CASES))
+def test_vs_reference_golden(case, precision):
+    spec = REF_CASES[case]
+    x, fh, f = make_case(spec, precision)
+    out_f, out_fh, perm = run_plan(spec, precision, x, fh, f)
+    assert rel_l2(out_f, REFOUT[f"{case}/{precision}/f"]) <= TOL[precision]
+    assert rel_l2(out_fh, REFOUT[f"{case}/{precision}/f_hat"]) <= TOL[precision]
+    assert np.array_equal(perm, REFOUT[f"{case}/{precision}/index_x"])
+
+
+@pytest.mark.skipif(not common.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_vs_live_reference_build(precision):
+    """Same plan run through the unmodified reference (oracle/_ref) and the product."""
+    flags = BASE | abi.NFFT_SORT_NODES | abi.NFFT_OMP_BLOCKWISE_ADJOINT
+    spec = dict(d=3, N=[32, 32, 32], n=[64, 64, 64], m=6, M=30000, seed=99, flags=flags)
+    x, fh, f = make_case(spec, precision)
+    ref = Plan.init_guru(3, spec["N"], spec["M"], spec["n"], 6, flags, api=common.ref_api(precision))
+    ref.x[:] = x
+    ref.f_hat[:] = fh
+    ref.trafo()
+    ref_f = ref.f.copy()
+    ref.f[:] = f
+    ref.adjoint()
+    ref_fh, ref_perm = ref.f_hat.copy(), ref.index_x.copy()
+    ref.finalize()
+    out_f, out_fh, _ = run_plan(spec, precision, x, fh, f)
+    assert rel_l2(out_f, ref_f) <= TOL[precision]
+    assert rel_l2(out_fh, ref_fh) <= TOL[precision]
+    eng = cabi.Engine(spec["N"], spec["n"], 6, spec["M"], precision=precision)
+    eng.set_nodes(x)
+    assert np.array_equal(eng.index_x(), ref_perm)   # keys and permutation, bit-exact
+    eng.close()
+
+
+# ---- (3) the oracle on fresh seeded inputs, sizes the oracle finishes in seconds ----------------------
+ORACLE_CASES = {
+    "cfg1_1d": dict(d=1, N=[1024], n=[2048], m=6, M=10000, seed=20260102, flags=BASE | abi.PRE_PSI),
+    "2d_128": dict(d=2, N=[128, 128], n=[256, 256], m=6, M=40000, seed=21, flags=BASE | abi.PRE_PSI),
+    "2d_m8_rect": dict(d=2, N=[64, 96], n=[128, 256], m=8, M=20000, seed=22, flags=BASE),
+    "3d_32": dict(d=3, N=[32, 32, 32], n=[64, 64, 64], m=6, M=50000, seed=23,
+                  flags=BASE | abi.NFFT_SORT_NODES | abi.NFFT_OMP_BLOCKWISE_ADJOINT),
+    "3d_m2": dict(d=3, N=[16, 24, 32], n=[32, 48, 64], m=2, M=5000, seed=24, flags=BASE),
+    "3d_m9": dict(d=3, N=[24, 24, 24], n=[48, 48, 48], m=9, M=3000, seed=25, flags=BASE),
+    "4d": dict(d=4, N=[8, 8, 8, 8], n=[16, 16, 16, 16], m=2, M=1000, seed=26, flags=BASE),
+    "1d_sigma_big": dict(d=1, N=[100], n=[512], m=5, M=3000, seed=27, flags=BASE),
+}
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("case", sorted(ORACLE_CASES))
+def test_vs_oracle(case, precision):
+    spec = ORACLE_CASES[case]
+    x, fh, f = make_case(spec, precision)
+    o = oracle(precision)
+    out_f, out_fh, _ = run_plan(spec, precision, x, fh, f)
+    assert rel_l2(out_f, o.trafo(spec["N"], spec["n"], spec["m"], x, fh)) <= TOL[precision]
+    assert rel_l2(out_fh, o.adjoint(spec["N"], spec["n"], spec["m"], x, f, True)) <= TOL[precision]
+
+
+# ---- (4) single stages through the C ABI ---------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("N,n,m", [([16, 16, 16], [32, 32, 32], 6), ([20, 30], [50, 72], 5),
+                                   ([64], [256], 4), ([6, 10, 12], [16, 24, 28], 2)])
+def test_stages(N, n, m, precision):
+    rng = np.random.default_rng(5)
+    d, M = len(N), 2000
+    o = oracle(precision)
+    x = (rng.random((M, d)) - 0.5).astype(o.real)
+    NN, nn = int(np.prod(N)), int(np.prod(n))
+    fh = (rng.random(NN) + 1j * rng.random(NN)).astype(o.cplx)
+    f = (rng.random(M) + 1j * rng.random(M)).astype(o.cplx)
+    g_in = (rng.random(nn) - 0.5 + 1j * (rng.random(nn) - 0.5)).astype(o.cplx)
+    tol = 1e-13 if precision == "double" else 2e-6
+    eng = cabi.Engine(N, n, m, M, precision=precision)
+    eng.set_nodes(x)
+    assert np.allclose(eng.c_phi_inv(0), o.c_phi_inv(N[0], n[0], m), rtol=4e-16 if precision == "double" else 3e-7)
+    fh_d = cabi.DeviceBuffer(fh.nbytes).upload(fh)
+    f_d = cabi.DeviceBuffer(f.nbytes).upload(f)
+    # D
+    eng.stage_D(fh_d)
+    assert rel_l2(eng.grid_to_host(), o.stage_D(N, n, m, fh)) <= tol
+    # F, both signs, on random data
+    for sign in (-1, +1):
+        eng.grid_from_host(g_in)
+        eng.stage_F(sign)
+        assert rel_l2(eng.grid_to_host(), o.stage_F(n, sign, g_in)) <= (1e-14 if precision == "double" else 2e-6)
+    # B
+    eng.grid_from_host(g_in)
+    eng.stage_B(f_d)
+    eng.sync()
+    assert rel_l2(f_d.download(o.cplx, M), o.stage_B(N, n, m, x, g_in)) <= tol * 10
+    # B^T
+    f_d.upload(f)
+    eng.stage_BT(f_d)
+    assert rel_l2(eng.grid_to_host(), o.stage_BT(N, n, m, x, f)) <= tol * 10
+    # D^T
+    eng.grid_from_host(g_in)
+    eng.stage_DT(fh_d)
+    eng.sync()
+    assert rel_l2(fh_d.download(o.cplx, NN), o.stage_DT(N, n, m, g_in)) <= tol
+    eng.close()
+
+
+# ---- (5) node sort: bit-exact permutation --------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("n,m,M,mode", [([256, 256, 256], 6, 300000, "uniform"),
+                                        ([64, 64], 4, 100000, "dups"),
+                                        ([50, 72, 40], 5, 50000, "uniform"),
+                                        ([2048], 6, 70000, "dups"),
+                                        ([512, 512, 512], 6, 20000, "edges")])
+def test_sort_bit_exact(n, m, M, mode, precision):
+    rng = np.random.default_rng(77)
+    d = len(n)
+    o = oracle(precision)
+    x = rng.random((M, d)) - 0.5
+    if mode == "dups":      # heavy key duplication: stability decides the order
+        x = np.round(x * 16) / 16
+        x[x >= 0.5] = -0.5
+    if mode == "edges":     # nodes on and next to cell boundaries, +-0.5
+        x = np.round(x * n[0]) / n[0] + rng.choice([0.0, 1e-9, -1e-9], size=(M, d))
+        x = np.clip(x, -0.5, np.nextafter(0.5, 0))
+    x = x.astype(o.real)
+    if precision == "float":
+        x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
+    N = [v // 2 for v in n]
+    eng = cabi.Engine(N, n, m, M, precision=precision)
+    eng.set_nodes(x)
+    got = eng.index_x()
+    eng.close()
+    want = o.sort_nodes(n, m, x)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    assert np.array_equal(got[:, 1], want[:, 1])
+
+
+# ---- (6) edge cases ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_edge_nodes_and_sizes(precision):
+    o = oracle(precision)
+    N, n, m = [16, 16, 16], [32, 32, 32], 6
+    rng = np.random.default_rng(3)
+    NN = 16 ** 3
+    fh = (rng.random(NN) + 1j * rng.random(NN)).astype(o.cplx)
+    lo, hi = -0.5, np.nextafter(o.real(0.5), o.real(0))
+    cases = {
+        "single": np.array([[0.1, -0.2, 0.3]]),
+        "corners": np.array([[lo, lo, lo], [hi, hi, hi], [lo, hi, 0.0], [0.0, 0.0, 0.0], [hi, lo, hi]]),
+        "identical": np.tile(np.array([[0.25, -0.125, 0.0625]]), (257, 1)),
+    }
+    for name, x in cases.items():
+        x = x.astype(o.real)
+        M = x.shape[0]
+        f = (rng.random(M) + 1j * rng.random(M)).astype(o.cplx)
+        spec = dict(d=3, N=N, n=n, m=m, M=M, flags=BASE | abi.NFFT_SORT_NODES)
+        out_f, out_fh, perm = run_plan(spec, precision, x, fh, f)
+        assert rel_l2(out_f, o.trafo(N, n, m, x, fh)) <= TOL[precision], name
+        assert rel_l2(out_fh, o.adjoint(N, n, m, x, f, True)) <= TOL[precision], name
+        assert np.array_equal(perm, o.sort_nodes(n, m, x)[:, 1]), name
+
+
+def test_empty_node_set():
+    p = Plan.init_guru(2, [16, 16], 0, [32, 32], 4, abi.PRE_PHI_HUT | abi.MALLOC_F_HAT | abi.FFTW_INIT)
+    dummy = np.zeros(2, dtype=np.float64)
+    p.c.x = dummy.ctypes.data_as(C.POINTER(C.c_double))
+    p.c.f = dummy.ctypes.data_as(C.POINTER(C.c_double))
+    p.f_hat[:] = 1.0
+    p.adjoint()          # g stays zero -> f_hat == 0 (nfft.c:5137 memset, no nodes)
+    assert np.all(p.f_hat == 0)
+    p.trafo()            # nothing to write
+    p.finalize()
+
+
+def test_small_N_falls_back_to_direct():
+    """any N_t <= m -> exact NDFT (nfft.c:5658-5664): result must equal trafo_direct's."""
+    o = oracle("double")
+    rng = np.random.default_rng(8)
+    N, n, m, M = [4, 32], [8, 64], 6, 100
+    x = rng.random((M, 2)) - 0.5
+    fh = rng.random(128) + 1j * rng.random(128)
+    p = Plan.init_guru(2, N, M, n, m, BASE)
+    p.x[:] = x
+    p.f_hat[:] = fh
+    p.trafo()
+    assert rel_l2(p.f, o.trafo_direct(N, x, fh)) <= 1e-14
+    p.f[:] = fh[:M]
+    p.adjoint()
+    assert rel_l2(p.f_hat, o.adjoint_direct(N, x, fh[:M])) <= 1e-14
+    p.finalize()
+
+
+# ---- (7) host-pointer semantics the callers rely on ---------------------------------------------------------
+def test_pointer_swap_and_node_refresh():
+    """solver.c swaps f/f_hat around each call (kernel/solver/solver.c:240-242,275-277); plans
+    without a psi flag see new nodes on the next call without notification (nfft.c:4889)."""
+    o = oracle("double")
+    rng = np.random.default_rng(9)
+    N, n, m, M = [32, 32], [64, 64], 6, 5000
+    p = Plan.init_guru(2, N, M, n, m, BASE | abi.NFFT_SORT_NODES)
+    x1, x2 = rng.random((M, 2)) - 0.5, rng.random((M, 2)) - 0.5
+    fh = rng.random(1024) + 1j * rng.random(1024)
+    other_f = np.zeros(M, dtype=np.complex128)
+    p.x[:] = x1
+    p.f_hat[:] = fh
+    own_f = p.c.f
+    p.c.f = other_f.ctypes.data_as(C.POINTER(C.c_double))      # CSWAP
+    p.trafo()
+    p.c.f = own_f
+    assert rel_l2(other_f, o.trafo(N, n, m, x1, fh)) <= 1e-12
+    v1 = np.array(p.index_x[:, 1])
+    p.x[:] = x2                                                 # silent node change
+    p.trafo()
+    assert rel_l2(p.f, o.trafo(N, n, m, x2, fh)) <= 1e-12
+    assert np.array_equal(p.index_x[:, 1], o.sort_nodes(n, m, x2)[:, 1])
+    assert not np.array_equal(v1, p.index_x[:, 1])
+    p.finalize()
+
+
+# ---- (8) size-independent properties at the benchmark shape ---------------------------------------------------
+@pytest.mark.parametrize("precision,M", [("double", 2_000_000), ("float", 2_000_000)])
+def test_adjointness_and_linearity_cfg3_grid(precision, M):
+    """3-D N=128^3, n=256^3, m=6 (BASELINE configs[2] grid): <A u, v> == <u, A^H v> and
+    A(u1 + 2 u2) == A u1 + 2 A u2.  No oracle needed, so the node count can be large."""
+    rng = np.random.default_rng(1234)
+    N, n, m = [128] * 3, [256] * 3, 6
+    real = np.float64 if precision == "double" else np.float32
+    cplx = np.complex128 if precision == "double" else np.complex64
+    x = (rng.random((M, 3)) - 0.5).astype(real)
+    if precision == "float":
+        x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
+    NN = 128 ** 3
+    u1 = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(cplx)
+    u2 = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(cplx)
+    v = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(cplx)
+    eng = cabi.Engine(N, n, m, M, precision=precision)
+    eng.set_nodes(x)
+    Au1, Au2 = eng.trafo(u1), eng.trafo(u2)
+    Au12 = eng.trafo((u1 + 2 * u2).astype(cplx))
+    AHv = eng.adjoint(v)
+    eng.close()
+    tol = 1e-12 if precision == "double" else 2e-5
+    assert rel_l2(Au12, Au1.astype(np.complex128) + 2 * Au2.astype(np.complex128)) <= tol
+    lhs = np.vdot(v.astype(np.complex128), Au1.astype(np.complex128))
+    rhs = np.vdot(AHv.astype(np.complex128), u1.astype(np.complex128))
+    scale = np.linalg.norm(v.astype(np.complex128)) * np.linalg.norm(Au1.astype(np.complex128))
+    assert abs(lhs - rhs) / scale <= tol
+
+
+def test_trafo_subsample_vs_oracle_cfg3_grid():
+    """trafo outputs are per-node independent: check a 3000-node subsample of a 10^6-node run on
+    the N=128^3 grid against the oracle's B step fed with the device grid."""
+    rng = np.random.default_rng(4321)
+    N, n, m, M = [128] * 3, [256] * 3, 6, 1_000_000
+    x = rng.random((M, 3)) - 0.5
+    NN = 128 ** 3
+    fh = rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)
+    eng = cabi.Engine(N, n, m, M, precision="double")
+    eng.set_nodes(x)
+    f = eng.trafo(fh)
+    g = eng.grid_to_host()
+    eng.close()
+    sel = rng.choice(M, 3000, replace=False)
+    want = oracle("double").stage_B(N, n, m, x[sel], g)
+    assert rel_l2(f[sel], want) <= 1e-12
