@@ -108,7 +108,7 @@ def run_reference(args, rank):
     so = os.path.join(ROOT, "oracle", "_ref", "libnfft3_ref_fast.so" if prec == "double" else "libnfft3f_ref_fast.so")
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    api = Api(C.CDLL(so), prec)
+    api = Api(C.CDLL(so, mode=os.RTLD_LOCAL | os.RTLD_NOW | getattr(os, 'RTLD_DEEPBIND', 0)), prec)
     flags = (abi.PRE_PHI_HUT | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
              | abi.NFFT_SORT_NODES | abi.NFFT_OMP_BLOCKWISE_ADJOINT)
 

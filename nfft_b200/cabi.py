@@ -41,7 +41,7 @@ def lib() -> C.CDLL:
     if _LIB is None:
         if not os.path.exists(_LIBPATH):
             raise RuntimeError(f"{_LIBPATH} not built (run __graft_entry__.build()); no CPU fallback")
-        L = C.CDLL(_LIBPATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(_LIBPATH, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
         L.nfftcu_last_error.restype = C.c_char_p
         L.nfftcu_device_count.restype = ci

@@ -53,8 +53,10 @@ def product_api(precision: str = "double") -> Api:
                 raise RuntimeError(
                     f"{p} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                     "(nfft_b200 has no CPU fallback)")
-        C.CDLL(cu, mode=C.RTLD_GLOBAL)
-        _PRODUCT[precision] = Api(C.CDLL(host, mode=C.RTLD_GLOBAL), precision)
+        # local scope: libnfft3_b200.so finds libnfftcu.so through its rpath, and nothing else in
+        # the process (e.g. a reference build loaded by the tests) may bind to these nfft_* names
+        mode = os.RTLD_LOCAL | os.RTLD_NOW | getattr(os, "RTLD_DEEPBIND", 0)
+        _PRODUCT[precision] = Api(C.CDLL(host, mode=mode), precision)
     return _PRODUCT[precision]
 
 
