@@ -115,9 +115,17 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
 }
 
 int nodes_ready(nfftcu_ctx *c) {
+  c->ref_sorted = false;
+  c->tile_ready = false;
   if (!c->direct_only) {
-    NFFTCU_TRY(sort_nodes(c));
-    if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
+    const bool use_tile = tile3d_supported(c) && c->opt_b_kernel != 1;
+    // the reference-order sort is the index_x witness and the order the generic kernels walk
+    if (!use_tile || (c->flags & (1u << 11))) {   // NFFT_SORT_NODES
+      NFFTCU_TRY(sort_nodes(c));
+      c->ref_sorted = true;
+    }
+    if (use_tile) NFFTCU_TRY(tile3d_bin_nodes(c));
+    else if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
   }
   c->have_nodes = true;
   c->nodes_version++;
@@ -275,7 +283,7 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) cudaFree(c->c_dev[t]);
-  void *bufs[] = {c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
+  void *bufs[] = {c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)
     if (p) cudaFree(p);
@@ -343,9 +351,13 @@ int nfftcu_get_index_x(nfftcu_ctx *c, int64_t *index_x_host) {
   NFFTCU_TRY(bind_device(c));
   NFFTCU_TRY(need_nodes(c));
   if (c->M == 0) return NFFTCU_OK;
-  if (c->direct_only || !c->keys_ref || !c->perm_ref) {
+  if (c->direct_only) {
     set_error("nfftcu_get_index_x: plan has no sorted nodes (direct-only plan)");
     return NFFTCU_ESTATE;
+  }
+  if (!c->ref_sorted) {   // plans without NFFT_SORT_NODES on the tile path: sort on demand
+    NFFTCU_TRY(sort_nodes(c));
+    c->ref_sorted = true;
   }
   std::vector<uint64_t> keys((size_t) c->M);
   std::vector<uint32_t> perm((size_t) c->M);

@@ -74,6 +74,15 @@ struct nfftcu_ctx_s {
   void *keys_ref = nullptr;         // sorted reference keys (uint64), for index_x
   uint32_t *perm_ref = nullptr;     // reference permutation (== perm when node order is the reference key)
   void *psi_table = nullptr;        // optional: M * d * (2m+2) reals in processing order
+  // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
+  bool tile_ready = false;
+  bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
+  void *tile_keys = nullptr;        // uint64 bin ids, sorted
+  uint32_t *tile_perm = nullptr;    // tile order -> original node index
+  void *tile_x = nullptr;           // M*3 reals in tile order
+  uint32_t *bin_start = nullptr;    // nbins+1 offsets into the tile order
+  void *tile_psi = nullptr;         // optional window table in tile order
+  long long tile_nbins = 0;
   void *sort_tmp = nullptr;         // scratch kept between set_nodes calls
   size_t sort_tmp_bytes = 0;
 
@@ -100,6 +109,12 @@ inline size_t real_size(const nfftcu_ctx *c) { return c->prec == NFFTCU_DOUBLE ?
 
 // ---- stage entry points, one per translation unit ---------------------------------------------
 int sort_nodes(nfftcu_ctx *c);                                      // sort.cu
+int radix_sort_pairs(nfftcu_ctx *c, uint64_t *keys, uint32_t *vals, long long M, int bits);  // sort.cu
+int gather_nodes(nfftcu_ctx *c, const uint32_t *perm, void *dst);   // sort.cu
+bool tile3d_supported(const nfftcu_ctx *c);                         // tile3d.cu
+int tile3d_bin_nodes(nfftcu_ctx *c);                                // tile3d.cu
+int tile3d_interp(nfftcu_ctx *c, void *f_dev);                      // tile3d.cu
+int tile3d_spread(nfftcu_ctx *c, const void *f_dev);                // tile3d.cu
 int stage_D(nfftcu_ctx *c, const void *f_hat_dev);                  // deconv.cu
 int stage_DT(nfftcu_ctx *c, void *f_hat_dev);                       // deconv.cu
 int fft_plan_axes(nfftcu_ctx *c);                                   // fft.cu

@@ -167,16 +167,15 @@ int ilog2_ceil(unsigned long long v) {
 
 }  // namespace
 
-// Builds keys from c->x_dev, sorts, leaves:
-//   c->keys_ref (sorted keys), c->perm_ref (= c->perm), c->x_sorted
-int sort_nodes(nfftcu_ctx *c) {
-  const long long M = c->M;
+// Stable LSD radix sort of (keys, vals) pairs over the low `bits` key bits; the result is left in
+// the arrays passed in.  Scratch (second pair of buffers + counters) lives in c->sort_tmp.
+int radix_sort_pairs(nfftcu_ctx *c, uint64_t *keys, uint32_t *vals, long long M, int bits) {
   if (M == 0) return NFFTCU_OK;
   const int ntiles = (int) ((M + kTile - 1) / kTile);
   const size_t kbytes = sizeof(uint64_t) * (size_t) M, vbytes = sizeof(uint32_t) * (size_t) M;
+  const size_t vpad = ((vbytes + 255) / 256) * 256;
   const size_t cbytes = sizeof(uint32_t) * 256 * (size_t) ntiles;
-  // scratch: second key/val buffers + counters
-  const size_t need = kbytes + vbytes + cbytes + 1024;
+  const size_t need = kbytes + vpad + cbytes;
   if (c->sort_tmp_bytes < need) {
     if (c->sort_tmp) cudaFree(c->sort_tmp);
     c->sort_tmp = nullptr;
@@ -184,28 +183,9 @@ int sort_nodes(nfftcu_ctx *c) {
     NFFTCU_CUDA(cudaMalloc(&c->sort_tmp, need));
     c->sort_tmp_bytes = need;
   }
-  if (!c->keys_ref) NFFTCU_CUDA(cudaMalloc(&c->keys_ref, kbytes));
-  if (!c->perm) NFFTCU_CUDA(cudaMalloc((void **) &c->perm, vbytes));
-  if (!c->x_sorted) NFFTCU_CUDA(cudaMalloc(&c->x_sorted, real_size(c) * (size_t) M * c->d));
-  c->perm_ref = c->perm;
-
-  uint64_t *kA = (uint64_t *) c->keys_ref, *kB = (uint64_t *) c->sort_tmp;
-  uint32_t *vA = c->perm, *vB = (uint32_t *) ((char *) c->sort_tmp + kbytes);
-  uint32_t *counts = (uint32_t *) ((char *) c->sort_tmp + kbytes + ((vbytes + 255) / 256) * 256);
-
-  KeyGeom g;
-  g.d = c->d;
-  g.m = c->m;
-  for (int t = 0; t < c->d; t++) g.n[t] = c->n[t];
-  const int kb = 256;
-  const unsigned kgrid = (unsigned) ((M + kb - 1) / kb);
-  if (c->prec == NFFTCU_DOUBLE)
-    make_keys_kernel<double><<<kgrid, kb, 0, c->stream>>>((const double *) c->x_dev, kA, vA, M, g);
-  else
-    make_keys_kernel<float><<<kgrid, kb, 0, c->stream>>>((const float *) c->x_dev, kA, vA, M, g);
-  c->launches++;
-
-  const int bits = ilog2_ceil((unsigned long long) c->n_total);
+  uint64_t *kA = keys, *kB = (uint64_t *) c->sort_tmp;
+  uint32_t *vA = vals, *vB = (uint32_t *) ((char *) c->sort_tmp + kbytes);
+  uint32_t *counts = (uint32_t *) ((char *) c->sort_tmp + kbytes + vpad);
   const int passes = bits <= 0 ? 1 : (bits + 7) / 8;
   for (int p = 0; p < passes; p++) {
     const int shift = 8 * p;
@@ -217,20 +197,56 @@ int sort_nodes(nfftcu_ctx *c) {
     uint64_t *tk = kA; kA = kB; kB = tk;
     uint32_t *tv = vA; vA = vB; vB = tv;
   }
-  if (kA != (uint64_t *) c->keys_ref) {   // odd number of passes: result sits in the scratch
-    NFFTCU_CUDA(cudaMemcpyAsync(c->keys_ref, kA, kbytes, cudaMemcpyDeviceToDevice, c->stream));
-    NFFTCU_CUDA(cudaMemcpyAsync(c->perm, vA, vbytes, cudaMemcpyDeviceToDevice, c->stream));
+  if (kA != keys) {   // odd number of passes: result sits in the scratch
+    NFFTCU_CUDA(cudaMemcpyAsync(keys, kA, kbytes, cudaMemcpyDeviceToDevice, c->stream));
+    NFFTCU_CUDA(cudaMemcpyAsync(vals, vA, vbytes, cudaMemcpyDeviceToDevice, c->stream));
   }
-  const unsigned ggrid = (unsigned) ((M * c->d + kb - 1) / kb);
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+// dst[k*d+t] = c->x_dev[perm[k]*d+t]
+int gather_nodes(nfftcu_ctx *c, const uint32_t *perm, void *dst) {
+  if (c->M == 0) return NFFTCU_OK;
+  const int kb = 256;
+  const unsigned ggrid = (unsigned) ((c->M * c->d + kb - 1) / kb);
   if (c->prec == NFFTCU_DOUBLE)
-    gather_nodes_kernel<double><<<ggrid, kb, 0, c->stream>>>((const double *) c->x_dev, c->perm,
-                                                            (double *) c->x_sorted, M, c->d);
+    gather_nodes_kernel<double><<<ggrid, kb, 0, c->stream>>>((const double *) c->x_dev, perm,
+                                                            (double *) dst, c->M, c->d);
   else
-    gather_nodes_kernel<float><<<ggrid, kb, 0, c->stream>>>((const float *) c->x_dev, c->perm,
-                                                           (float *) c->x_sorted, M, c->d);
+    gather_nodes_kernel<float><<<ggrid, kb, 0, c->stream>>>((const float *) c->x_dev, perm,
+                                                           (float *) dst, c->M, c->d);
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
+}
+
+// Reference order: keys from c->x_dev, stable sort, leaves c->keys_ref (sorted keys),
+// c->perm (= c->perm_ref) and c->x_sorted.
+int sort_nodes(nfftcu_ctx *c) {
+  const long long M = c->M;
+  if (M == 0) return NFFTCU_OK;
+  const size_t kbytes = sizeof(uint64_t) * (size_t) M, vbytes = sizeof(uint32_t) * (size_t) M;
+  if (!c->keys_ref) NFFTCU_CUDA(cudaMalloc(&c->keys_ref, kbytes));
+  if (!c->perm) NFFTCU_CUDA(cudaMalloc((void **) &c->perm, vbytes));
+  if (!c->x_sorted) NFFTCU_CUDA(cudaMalloc(&c->x_sorted, real_size(c) * (size_t) M * c->d));
+  c->perm_ref = c->perm;
+  KeyGeom g;
+  g.d = c->d;
+  g.m = c->m;
+  for (int t = 0; t < c->d; t++) g.n[t] = c->n[t];
+  const int kb = 256;
+  const unsigned kgrid = (unsigned) ((M + kb - 1) / kb);
+  if (c->prec == NFFTCU_DOUBLE)
+    make_keys_kernel<double><<<kgrid, kb, 0, c->stream>>>((const double *) c->x_dev,
+                                                         (uint64_t *) c->keys_ref, c->perm, M, g);
+  else
+    make_keys_kernel<float><<<kgrid, kb, 0, c->stream>>>((const float *) c->x_dev,
+                                                        (uint64_t *) c->keys_ref, c->perm, M, g);
+  c->launches++;
+  NFFTCU_TRY(radix_sort_pairs(c, (uint64_t *) c->keys_ref, c->perm, M,
+                              ilog2_ceil((unsigned long long) c->n_total)));
+  return gather_nodes(c, c->perm, c->x_sorted);
 }
 
 }  // namespace nfftcu

@@ -374,3 +374,55 @@ def test_trafo_subsample_vs_oracle_cfg3_grid():
     sel = rng.choice(M, 3000, replace=False)
     want = oracle("double").stage_B(N, n, m, x[sel], g)
     assert rel_l2(f[sel], want) <= 1e-12
+
+
+# ---- (9) 3-D fast path (tile3d.cu) against the generic kernels and the oracle ----------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("N,n,m,M", [
+    ([16, 16, 16], [32, 32, 32], 6, 4000),       # power of two
+    ([24, 16, 20], [50, 33, 41], 5, 3000),       # n not divisible by the tile / slab sizes, odd n2
+    ([8, 8, 8], [16, 16, 16], 6, 500),           # footprint (16) == n: rows wrap onto the whole axis
+    ([8, 10, 12], [15, 21, 26], 6, 700),         # footprint larger than n0: footprint rows alias
+    ([32, 32, 32], [64, 64, 64], 2, 6000),
+    ([20, 20, 20], [40, 40, 40], 8, 2000),
+    ([64, 8, 8], [128, 16, 16], 4, 3000),
+])
+def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
+    rng = np.random.default_rng(31)
+    o = oracle(precision)
+    x = (rng.random((M, 3)) - 0.5).astype(o.real)
+    x[: M // 8] = np.round(x[: M // 8] * 4) / 4          # clustered + exact cell-boundary nodes
+    x = np.clip(x, -0.5, np.nextafter(o.real(0.5), o.real(0)))
+    NN = int(np.prod(N))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    want_f = o.trafo(N, n, m, x, fh)
+    want_fh = o.adjoint(N, n, m, x, f)
+    outs = {}
+    for label, kernel, table in (("tile", 0, 0), ("tile+table", 0, 1), ("generic", 1, 0), ("generic+table", 1, 1)):
+        eng = cabi.Engine(N, n, m, M, precision=precision)
+        eng.set_option(cabi.OPT_B_KERNEL, kernel)
+        eng.set_option(cabi.OPT_PSI_TABLE, table)
+        eng.set_nodes(x)
+        outs[label] = (eng.trafo(fh), eng.adjoint(f))
+        eng.close()
+        assert rel_l2(outs[label][0], want_f) <= TOL[precision], label
+        assert rel_l2(outs[label][1], want_fh) <= TOL[precision], label
+    tight = 1e-13 if precision == "double" else 5e-6
+    assert rel_l2(outs["tile"][0], outs["generic"][0]) <= tight
+    assert rel_l2(outs["tile"][1], outs["generic"][1]) <= tight
+
+
+def test_tile3d_z_segments_small_grid_many_nodes():
+    """few tiles -> the sweep is split into z segments; every segment flushes / preloads its window."""
+    rng = np.random.default_rng(32)
+    N, n, m, M = [12, 12, 64], [24, 24, 128], 6, 60000
+    o = oracle("double")
+    x = rng.random((M, 3)) - 0.5
+    fh = rng.random(12 * 12 * 64) + 1j * rng.random(12 * 12 * 64)
+    f = rng.random(M) + 1j * rng.random(M)
+    eng = cabi.Engine(N, n, m, M)
+    eng.set_nodes(x)
+    assert rel_l2(eng.trafo(fh), o.trafo(N, n, m, x, fh)) <= 1e-12
+    assert rel_l2(eng.adjoint(f), o.adjoint(N, n, m, x, f)) <= 1e-12
+    eng.close()
