@@ -267,6 +267,7 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
   if (!c->direct_only) {
     NFFTCU_CUDA(cudaMalloc(&c->grid, cbytes(c, c->n_total)));
     int r = fft_plan_axes(c);
+    if (r == NFFTCU_OK && tile3d_supported(c)) r = build_kb_poly(c);
     if (r != NFFTCU_OK) {
       nfftcu_destroy(c);
       return r;
@@ -283,7 +284,7 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) cudaFree(c->c_dev[t]);
-  void *bufs[] = {c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
+  void *bufs[] = {c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)
     if (p) cudaFree(p);

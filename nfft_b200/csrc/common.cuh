@@ -83,6 +83,11 @@ struct nfftcu_ctx_s {
   uint32_t *bin_start = nullptr;    // nbins+1 offsets into the tile order
   void *tile_psi = nullptr;         // optional window table in tile order
   long long tile_nbins = 0;
+  void *f_tile = nullptr;           // M complex: samples in tile order (gathered / to be scattered)
+  // piecewise-polynomial window (kbpoly.cu): coef[(t*(deg+1)+k)*W + l]
+  int kbpoly_deg = -1;
+  std::vector<double> kbpoly_host;
+  void *kbpoly_dev = nullptr;
   void *sort_tmp = nullptr;         // scratch kept between set_nodes calls
   size_t sort_tmp_bytes = 0;
 
@@ -111,6 +116,7 @@ inline size_t real_size(const nfftcu_ctx *c) { return c->prec == NFFTCU_DOUBLE ?
 int sort_nodes(nfftcu_ctx *c);                                      // sort.cu
 int radix_sort_pairs(nfftcu_ctx *c, uint64_t *keys, uint32_t *vals, long long M, int bits);  // sort.cu
 int gather_nodes(nfftcu_ctx *c, const uint32_t *perm, void *dst);   // sort.cu
+int build_kb_poly(nfftcu_ctx *c);                                   // kbpoly.cu
 bool tile3d_supported(const nfftcu_ctx *c);                         // tile3d.cu
 int tile3d_bin_nodes(nfftcu_ctx *c);                                // tile3d.cu
 int tile3d_interp(nfftcu_ctx *c, void *f_dev);                      // tile3d.cu

@@ -19,13 +19,20 @@
 //                  register indices are static); when the sweep leaves a slab, the SZ cells that
 //                  fall out of the window are retired to the grid with RED.ADD and the window shifts.
 //                  No shared-memory accumulation, no intra-CTA conflicts: a row has one owner.
-//   interpolation  the windows hold grid values, refilled SZ cells per slab straight from L2;
-//                  a node reduces them against psi2, weights by psi0 psi1, and the per-thread partial
-//                  sums of a batch of NB nodes are reduced across the CTA through shared memory.
+//   interpolation  the windows hold grid values, refilled SZ cells per slab straight from L2 (the
+//                  cells of the next slab are prefetched one slab ahead); a node reduces them against
+//                  psi2, weights by psi0 psi1, and the per-thread partial sums of a batch are reduced
+//                  across the CTA through shared memory one batch later.
 // Per tap this costs 2 FP64 FMAs and, per node and thread, WZ broadcast shared-memory loads of psi2
 // -- instead of one 16-byte shared/L1 load per tap -- which moves the kernel from the LSU roof
 // (128 B/clk/SM) to the FP64 roof (64 FMA/clk/SM); see DESIGN.md for the arithmetic and
 // profiles/ for the measurements.  Zero padding costs (W/F0)(W/F1)(W/WZ) = 71% lane efficiency at m = 6.
+//
+// Pipeline inside a CTA.  Nodes are consumed in batches of NB.  While batch b is consumed, the raw
+// data (x, f) of batch b+2 is in flight from HBM into registers and the padded window vectors of
+// batch b+1 are produced into the other half of a double buffer (window values from the
+// piecewise polynomial of kbpoly.cu, the optional per-node table, or the closed form); there is
+// ONE __syncthreads per batch.
 #include "common.cuh"
 
 #include <type_traits>
@@ -43,8 +50,10 @@ struct Cfg {
   static constexpr int WZ = W + SZ - 1;
   static constexpr int WZP = (WZ + 1) & ~1;
   static constexpr int THREADS = ((((ROWS + 1) / 2) + 31) / 32) * 32;
+  static constexpr int NWARPS = THREADS / 32;
   static constexpr int PADLEN = F0 + F1 + WZP;
   static constexpr int MINB = THREADS <= 128 ? 2 : 1;
+  static constexpr int RETIRE_ALL = (WZ + SZ - 1) / SZ;   // slabs after which the whole window has left
 };
 
 struct TileParams {
@@ -52,10 +61,13 @@ struct TileParams {
   int NT0, NT1, NS;
   int zseg;
   int m;
+  int deg;          // polynomial degree, -1: closed form
   double m2, b0, b1, b2;
 };
 
-__device__ __forceinline__ int wrap_idx(long long v, int n) {
+__device__ __forceinline__ int wrap_fast(long long v, int n) {
+  if (v >= 0 && v < n) return (int) v;
+  if (v < 0 && v >= -(long long) n) return (int) (v + n);
   long long r = v % n;
   if (r < 0) r += n;
   return (int) r;
@@ -69,9 +81,9 @@ __global__ void tile_keys_kernel(const T *__restrict__ x, uint64_t *__restrict__
                                  uint32_t *__restrict__ vals, long long M, TileParams P) {
   const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
-  const int u0 = wrap_idx(cell_of(x[3 * j], P.n0) - P.m, P.n0);
-  const int u1 = wrap_idx(cell_of(x[3 * j + 1], P.n1) - P.m, P.n1);
-  const int u2 = wrap_idx(cell_of(x[3 * j + 2], P.n2) - P.m, P.n2);
+  const int u0 = wrap_fast(cell_of(x[3 * j], P.n0) - P.m, P.n0);
+  const int u1 = wrap_fast(cell_of(x[3 * j + 1], P.n1) - P.m, P.n1);
+  const int u2 = wrap_fast(cell_of(x[3 * j + 2], P.n2) - P.m, P.n2);
   const unsigned long long tile = (unsigned long long) (u0 / kT0) * P.NT1 + (u1 / kT1);
   keys[j] = tile * P.NS + (u2 / kSZ);
   vals[j] = (uint32_t) j;
@@ -91,38 +103,130 @@ __global__ void bin_bounds_kernel(const uint64_t *__restrict__ keys, uint32_t *_
   bin_start[b] = (uint32_t) lo;
 }
 
-// ---- shared by both kernels: stage a batch of nodes (zero-padded window vectors) ------------------
-// pads[i] = [ psi0 padded to F0 | psi1 padded to F1 | psi2 padded to WZP ], slab[i] = u2 / SZ
-template <typename T, int W>
-__device__ __forceinline__ void stage_batch(T (*pads)[Cfg<W>::PADLEN], int *slab,
-                                            const T *__restrict__ xt, const T *__restrict__ table,
-                                            long long k, int nb, int a, int b, const TileParams &P) {
+template <typename C>
+__global__ void gather_f_kernel(const C *__restrict__ f, const uint32_t *__restrict__ perm,
+                                C *__restrict__ ft, long long M) {
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < M) ft[k] = f[perm[k]];
+}
+
+template <typename C>
+__global__ void scatter_f_kernel(const C *__restrict__ ft, const uint32_t *__restrict__ perm,
+                                 C *__restrict__ f, long long M) {
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < M) f[perm[k]] = ft[k];
+}
+
+// ---- shared-memory carve-up ------------------------------------------------------------------------
+template <typename T, int W, bool SPREAD>
+struct Smem {
   typedef Cfg<W> CF;
-  T *flat = &pads[0][0];
-  for (int i = threadIdx.x; i < CF::NB * CF::PADLEN; i += CF::THREADS) flat[i] = (T) 0;
-  __syncthreads();
-  for (int it = threadIdx.x; it < nb * 3 * W; it += CF::THREADS) {
-    const int i = it / (3 * W), rem = it - i * (3 * W);
-    const int t = rem / W, l = rem - t * W;
-    const T x = xt[(k + i) * 3 + t];
-    const int n = (t == 0) ? P.n0 : (t == 1) ? P.n1 : P.n2;
-    const long long uu = cell_of(x, n) - P.m;       // unwrapped corner
-    const int u = wrap_idx(uu, n);
-    T psi;
-    if (table) psi = table[((k + i) * 3 + t) * W + l];
-    else {
-      const double bb = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
-      psi = (T) kb_phi((double) x * (double) n - (double) (uu + l), P.m2, bb);
-    }
-    int pos;
-    if (t == 0) pos = (u - a * CF::T0) + l;
-    else if (t == 1) pos = CF::F0 + (u - b * CF::T1) + l;
-    else {
-      pos = CF::F0 + CF::F1 + (u % CF::SZ) + l;
-      if (l == 0) slab[i] = u / CF::SZ;
-    }
-    pads[i][pos] = psi;
+  typedef typename Cplx<T>::type C;
+  C *red;       // [2][NB][THREADS]   interpolation partial sums
+  C *padf;      // [2][NB]            f_j of the batch (spreading)
+  C *rawf;      // [2][NB]
+  double *poly; // [polyN]
+  T *pads;      // [2][NB][PADLEN]
+  T *rawx;      // [2][NB*3]
+  int *slab;    // [2][NB]
+
+  __host__ __device__ static size_t bytes(int polyN) {
+    size_t b = 0;
+    if (!SPREAD) b += sizeof(C) * 2 * CF::NB * CF::THREADS;
+    b += sizeof(C) * 2 * CF::NB * 2;
+    b += sizeof(double) * (size_t) polyN;
+    b += sizeof(T) * 2 * CF::NB * CF::PADLEN;
+    b += sizeof(T) * 2 * CF::NB * 3;
+    b = (b + 7) & ~(size_t) 7;
+    b += sizeof(int) * 2 * CF::NB;
+    return b;
   }
+  __device__ Smem(unsigned char *base, int polyN) {
+    size_t o = 0;
+    red = reinterpret_cast<C *>(base);
+    if (!SPREAD) o += sizeof(C) * 2 * CF::NB * CF::THREADS;
+    padf = reinterpret_cast<C *>(base + o);
+    o += sizeof(C) * 2 * CF::NB;
+    rawf = reinterpret_cast<C *>(base + o);
+    o += sizeof(C) * 2 * CF::NB;
+    poly = reinterpret_cast<double *>(base + o);
+    o += sizeof(double) * (size_t) polyN;
+    pads = reinterpret_cast<T *>(base + o);
+    o += sizeof(T) * 2 * CF::NB * CF::PADLEN;
+    rawx = reinterpret_cast<T *>(base + o);
+    o += sizeof(T) * 2 * CF::NB * 3;
+    o = (o + 7) & ~(size_t) 7;
+    slab = reinterpret_cast<int *>(base + o);
+  }
+};
+
+// raw node data of one batch: issue the global loads (into registers) / park them in shared memory
+template <typename T, int W, bool SPREAD>
+struct RawRegs {
+  typedef Cfg<W> CF;
+  typedef typename Cplx<T>::type C;
+  T px;
+  C pf;
+  __device__ __forceinline__ void load(const T *__restrict__ xt, const C *__restrict__ ft,
+                                       long long kb, long long k1) {
+    const int tid = threadIdx.x;
+    px = (T) 0;
+    pf = make_c<T>((T) 0, (T) 0);
+    if (tid < CF::NB * 3) {
+      const long long idx = kb * 3 + tid;
+      if (idx < k1 * 3) px = xt[idx];
+    } else if (SPREAD && tid < CF::NB * 4) {
+      const long long idx = kb + (tid - CF::NB * 3);
+      if (idx < k1) pf = ft[idx];
+    }
+  }
+  __device__ __forceinline__ void park(const Smem<T, W, SPREAD> &S, int rb) const {
+    const int tid = threadIdx.x;
+    if (tid < CF::NB * 3) S.rawx[rb * CF::NB * 3 + tid] = px;
+    else if (SPREAD && tid < CF::NB * 4) S.rawf[rb * CF::NB + (tid - CF::NB * 3)] = pf;
+  }
+};
+
+// padded window vectors of one batch: every element of pads[pb] is written exactly once
+//   pads[i] = [ psi0 padded to F0 | psi1 padded to F1 | psi2 padded to WZP ],  slab[i] = u2 / SZ
+template <typename T, int W, bool SPREAD>
+__device__ __forceinline__ void produce(const Smem<T, W, SPREAD> &S, int pb, int rb, long long kb,
+                                        int nb, int a, int b, const TileParams &P,
+                                        const T *__restrict__ table) {
+  typedef Cfg<W> CF;
+  for (int it = threadIdx.x; it < CF::NB * CF::PADLEN; it += CF::THREADS) {
+    const int i = it / CF::PADLEN, q = it - i * CF::PADLEN;
+    int t, pos;
+    if (q < CF::F0) { t = 0; pos = q; }
+    else if (q < CF::F0 + CF::F1) { t = 1; pos = q - CF::F0; }
+    else { t = 2; pos = q - CF::F0 - CF::F1; }
+    T val = (T) 0;
+    if (i < nb) {
+      const T x = S.rawx[(rb * CF::NB + i) * 3 + t];
+      const int n = (t == 0) ? P.n0 : (t == 1) ? P.n1 : P.n2;
+      const long long cc = cell_of(x, n);
+      const int u = wrap_fast(cc - P.m, n);
+      const int delta = (t == 0) ? u - a * CF::T0 : (t == 1) ? u - b * CF::T1 : u % CF::SZ;
+      const int l = pos - delta;
+      if (t == 2 && pos == 0) S.slab[pb * CF::NB + i] = u / CF::SZ;
+      if (l >= 0 && l < W) {
+        if (table) val = table[((kb + i) * 3 + t) * W + l];
+        else if (P.deg >= 0) {
+          const double y = 2.0 * ((double) x * (double) n - (double) cc) - 1.0;
+          const double *cf = S.poly + (size_t) t * (P.deg + 1) * W + l;
+          double acc = cf[P.deg * W];
+          for (int k = P.deg - 1; k >= 0; k--) acc = fma(acc, y, cf[k * W]);
+          val = (T) acc;
+        } else {
+          const double bb = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
+          val = (T) kb_phi((double) x * (double) n - (double) (cc - P.m + l), P.m2, bb);
+        }
+      }
+    }
+    S.pads[(pb * CF::NB + i) * CF::PADLEN + q] = val;
+  }
+  if (SPREAD && threadIdx.x < CF::NB)
+    S.padf[pb * CF::NB + threadIdx.x] = S.rawf[rb * CF::NB + threadIdx.x];
 }
 
 template <typename T, int W>
@@ -139,43 +243,59 @@ struct RowSetup {
       const int rr = valid[j] ? r : 0;
       l0[j] = rr / CF::F1;
       l1[j] = rr - l0[j] * CF::F1;
-      const int g0 = wrap_idx((long long) a * CF::T0 + l0[j], P.n0);
-      const int g1 = wrap_idx((long long) b * CF::T1 + l1[j], P.n1);
+      const int g0 = wrap_fast((long long) a * CF::T0 + l0[j], P.n0);
+      const int g1 = wrap_fast((long long) b * CF::T1 + l1[j], P.n1);
       off[j] = ((long long) g0 * P.n1 + g1) * P.n2;
     }
   }
 };
 
+struct TileRange {
+  int a, b;
+  long long k0, k1;
+  __device__ __forceinline__ TileRange(const uint32_t *__restrict__ bin_start, const TileParams &P) {
+    const int tile = blockIdx.x / P.zseg, seg = blockIdx.x - tile * P.zseg;
+    a = tile / P.NT1;
+    b = tile - a * P.NT1;
+    const int s_begin = (int) ((long long) P.NS * seg / P.zseg);
+    const int s_end = (int) ((long long) P.NS * (seg + 1) / P.zseg);
+    const long long bin0 = (long long) tile * P.NS;
+    k0 = bin_start[bin0 + s_begin];
+    k1 = bin_start[bin0 + s_end];
+  }
+};
+
+__device__ __forceinline__ int wrap_z(int z, int n2) {
+  if (z >= n2) z -= n2;
+  if (z >= n2) z %= n2;
+  return z;
+}
+
 // ---- spreading ---------------------------------------------------------------------------------------
 template <typename T, int W>
 __global__ void __launch_bounds__(Cfg<W>::THREADS, Cfg<W>::MINB)
 spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__ xt,
-                   const uint32_t *__restrict__ perm, const typename Cplx<T>::type *__restrict__ f,
-                   const uint32_t *__restrict__ bin_start, const T *__restrict__ table, TileParams P) {
+                   const typename Cplx<T>::type *__restrict__ ft,
+                   const uint32_t *__restrict__ bin_start, const T *__restrict__ table,
+                   const double *__restrict__ poly, int polyN, TileParams P) {
   typedef Cfg<W> CF;
   typedef typename Cplx<T>::type C;
-  __shared__ __align__(16) T pads[CF::NB][CF::PADLEN];
-  __shared__ C fv[CF::NB];
-  __shared__ int slab[CF::NB];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TileRange R(bin_start, P);
+  if (R.k0 == R.k1) return;
+  const Smem<T, W, true> S(smem_raw, polyN);
+  for (int i = threadIdx.x; i < polyN; i += CF::THREADS) S.poly[i] = poly[i];
 
-  const int tile = blockIdx.x / P.zseg, seg = blockIdx.x - tile * P.zseg;
-  const int a = tile / P.NT1, b = tile - a * P.NT1;
-  const int s_begin = (int) ((long long) P.NS * seg / P.zseg);
-  const int s_end = (int) ((long long) P.NS * (seg + 1) / P.zseg);
-  const long long bin0 = (long long) tile * P.NS;
-  const long long k0 = bin_start[bin0 + s_begin], k1 = bin_start[bin0 + s_end];
-  if (k0 == k1) return;
-
-  const RowSetup<T, W> rows(a, b, P);
+  const RowSetup<T, W> rows(R.a, R.b, P);
   T *Gr = reinterpret_cast<T *>(G);
   T accr[2][CF::WZ], acci[2][CF::WZ];
 #pragma unroll
   for (int j = 0; j < 2; j++)
 #pragma unroll
     for (int kz = 0; kz < CF::WZ; kz++) { accr[j][kz] = (T) 0; acci[j][kz] = (T) 0; }
-  int cur = -1;   // slab the window is aligned to; window covers z = cur*SZ .. cur*SZ+WZ-1 (mod n2)
+  int cur = -1;   // slab the window is aligned to: it covers z = cur*SZ .. cur*SZ+WZ-1 (mod n2)
 
-  // retire cells [0, cnt) of the window to the grid and shift the window down by cnt (static cnt)
+  // retire cells [0, CNT) of the window to the grid and shift the window down by CNT
   auto retire = [&](auto cnt_tag) {
     constexpr int CNT = decltype(cnt_tag)::value;
     const int zb = cur * CF::SZ;
@@ -184,10 +304,7 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
       if (rows.valid[j]) {
 #pragma unroll
         for (int kz = 0; kz < CNT; kz++) {
-          int z = zb + kz;
-          if (z >= P.n2) z -= P.n2;
-          if (z >= P.n2) z %= P.n2;
-          T *p = Gr + 2 * (rows.off[j] + z);
+          T *p = Gr + 2 * (rows.off[j] + wrap_z(zb + kz, P.n2));
           red_add(p, accr[j][kz]);
           red_add(p + 1, acci[j][kz]);
         }
@@ -200,17 +317,27 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
     }
   };
 
-  for (long long k = k0; k < k1; k += CF::NB) {
-    const int nb = (int) min((long long) CF::NB, k1 - k);
-    __syncthreads();   // previous batch fully consumed before the pads are rewritten
-    stage_batch<T, W>(pads, slab, xt, table, k, nb, a, b, P);
-    if (threadIdx.x < nb) fv[threadIdx.x] = f[perm[k + threadIdx.x]];
-    __syncthreads();
+  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
+  RawRegs<T, W, true> raw;
+  raw.load(xt, ft, R.k0, R.k1);
+  raw.park(S, 0);
+  raw.load(xt, ft, R.k0 + CF::NB, R.k1);
+  raw.park(S, 1);
+  __syncthreads();
+  produce<T, W, true>(S, 0, 0, R.k0, (int) min((long long) CF::NB, R.k1 - R.k0), R.a, R.b, P, table);
+  __syncthreads();
+
+  for (int bb = 0; bb < nbatch; bb++) {
+    const long long kb = R.k0 + (long long) bb * CF::NB;
+    const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+    const int pb = bb & 1;
+    raw.load(xt, ft, kb + 2 * CF::NB, R.k1);            // batch bb+2: in flight during the consume
+
     for (int i = 0; i < nb; i++) {
-      const int s = slab[i];
+      const int s = S.slab[pb * CF::NB + i];
       if (cur < 0) cur = s;
       while (cur < s) {
-        if (s - cur >= (CF::WZ + CF::SZ - 1) / CF::SZ) {   // the whole window leaves: flush it all
+        if (s - cur >= CF::RETIRE_ALL) {
           retire(std::integral_constant<int, CF::WZ>());
           cur = s;
         } else {
@@ -218,8 +345,8 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
           cur++;
         }
       }
-      const T *pd = pads[i];
-      const C fj = fv[i];
+      const T *pd = S.pads + (pb * CF::NB + i) * CF::PADLEN;
+      const C fj = S.padf[pb * CF::NB + i];
       const T w0 = rows.valid[0] ? pd[rows.l0[0]] * pd[CF::F0 + rows.l1[0]] : (T) 0;
       const T w1 = rows.valid[1] ? pd[rows.l0[1]] * pd[CF::F0 + rows.l1[1]] : (T) 0;
       const T ar0 = w0 * fj.x, ai0 = w0 * fj.y, ar1 = w1 * fj.x, ai1 = w1 * fj.y;
@@ -233,6 +360,12 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
         acci[1][kz] += ai1 * p;
       }
     }
+
+    if (bb + 1 < nbatch)
+      produce<T, W, true>(S, pb ^ 1, pb ^ 1, kb + CF::NB, (int) min((long long) CF::NB, R.k1 - kb - CF::NB),
+                          R.a, R.b, P, table);
+    raw.park(S, pb);   // raw[pb] was last read by the produce of the previous iteration
+    __syncthreads();
   }
   if (cur >= 0) retire(std::integral_constant<int, CF::WZ>());
 }
@@ -241,105 +374,70 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
 template <typename T, int W>
 __global__ void __launch_bounds__(Cfg<W>::THREADS, Cfg<W>::MINB)
 interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__restrict__ xt,
-                   const uint32_t *__restrict__ perm, typename Cplx<T>::type *__restrict__ f,
-                   const uint32_t *__restrict__ bin_start, const T *__restrict__ table, TileParams P) {
+                   typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
+                   const T *__restrict__ table, const double *__restrict__ poly, int polyN,
+                   TileParams P) {
   typedef Cfg<W> CF;
   typedef typename Cplx<T>::type C;
-  __shared__ __align__(16) T pads[CF::NB][CF::PADLEN];
-  __shared__ int slab[CF::NB];
-  __shared__ __align__(16) C red[CF::NB][CF::THREADS];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TileRange R(bin_start, P);
+  if (R.k0 == R.k1) return;
+  const Smem<T, W, false> S(smem_raw, polyN);
+  for (int i = threadIdx.x; i < polyN; i += CF::THREADS) S.poly[i] = poly[i];
 
-  const int tile = blockIdx.x / P.zseg, seg = blockIdx.x - tile * P.zseg;
-  const int a = tile / P.NT1, b = tile - a * P.NT1;
-  const int s_begin = (int) ((long long) P.NS * seg / P.zseg);
-  const int s_end = (int) ((long long) P.NS * (seg + 1) / P.zseg);
-  const long long bin0 = (long long) tile * P.NS;
-  const long long k0 = bin_start[bin0 + s_begin], k1 = bin_start[bin0 + s_end];
-  if (k0 == k1) return;
-
-  const RowSetup<T, W> rows(a, b, P);
+  const RowSetup<T, W> rows(R.a, R.b, P);
   T winr[2][CF::WZ], wini[2][CF::WZ];
+  T nxr[2][CF::SZ], nxi[2][CF::SZ];   // the SZ cells that enter the window at the next slab
   int cur = -1;
 
-  // (re)load window cells [FROM, WZ) for the current alignment
-  auto fill = [&](auto from_tag) {
-    constexpr int FROM = decltype(from_tag)::value;
+  auto fill_all = [&]() {
     const int zb = cur * CF::SZ;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
+    for (int j = 0; j < 2; j++)
 #pragma unroll
-      for (int kz = FROM; kz < CF::WZ; kz++) {
-        int z = zb + kz;
-        if (z >= P.n2) z -= P.n2;
-        if (z >= P.n2) z %= P.n2;
-        const C v = rows.valid[j] ? G[rows.off[j] + z] : make_c<T>((T) 0, (T) 0);
+      for (int kz = 0; kz < CF::WZ; kz++) {
+        const C v = rows.valid[j] ? G[rows.off[j] + wrap_z(zb + kz, P.n2)] : make_c<T>((T) 0, (T) 0);
         winr[j][kz] = v.x;
         wini[j][kz] = v.y;
       }
-    }
   };
-  auto shift = [&]() {
+  auto prefetch_next = [&]() {
+    const int zb = cur * CF::SZ + CF::WZ;
 #pragma unroll
     for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int q = 0; q < CF::SZ; q++) {
+        const C v = rows.valid[j] ? G[rows.off[j] + wrap_z(zb + q, P.n2)] : make_c<T>((T) 0, (T) 0);
+        nxr[j][q] = v.x;
+        nxi[j][q] = v.y;
+      }
+  };
+  auto step_one = [&]() {   // move the window up by one slab using the prefetched cells
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
 #pragma unroll
       for (int kz = 0; kz + CF::SZ < CF::WZ; kz++) {
         winr[j][kz] = winr[j][kz + CF::SZ];
         wini[j][kz] = wini[j][kz + CF::SZ];
       }
+#pragma unroll
+      for (int q = 0; q < CF::SZ; q++) {
+        winr[j][CF::WZ - CF::SZ + q] = nxr[j][q];
+        wini[j][CF::WZ - CF::SZ + q] = nxi[j][q];
+      }
+    }
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NWARPS = CF::THREADS / 32;
-
-  for (long long k = k0; k < k1; k += CF::NB) {
-    const int nb = (int) min((long long) CF::NB, k1 - k);
-    __syncthreads();
-    stage_batch<T, W>(pads, slab, xt, table, k, nb, a, b, P);
-    __syncthreads();
-    T pr[CF::NB], pi[CF::NB];
-#pragma unroll
-    for (int i = 0; i < CF::NB; i++) {
-      pr[i] = (T) 0;
-      pi[i] = (T) 0;
-      if (i < nb) {
-        const int s = slab[i];
-        if (cur < 0) { cur = s; fill(std::integral_constant<int, 0>()); }
-        while (cur < s) {
-          if (s - cur >= (CF::WZ + CF::SZ - 1) / CF::SZ) {
-            cur = s;
-            fill(std::integral_constant<int, 0>());
-          } else {
-            shift();
-            cur++;
-            fill(std::integral_constant<int, CF::WZ - CF::SZ>());
-          }
-        }
-        const T *pd = pads[i];
-        const T w0 = rows.valid[0] ? pd[rows.l0[0]] * pd[CF::F0 + rows.l1[0]] : (T) 0;
-        const T w1 = rows.valid[1] ? pd[rows.l0[1]] * pd[CF::F0 + rows.l1[1]] : (T) 0;
-        const T *p2 = pd + CF::F0 + CF::F1;
-        T t0r = (T) 0, t0i = (T) 0, t1r = (T) 0, t1i = (T) 0;
-#pragma unroll
-        for (int kz = 0; kz < CF::WZ; kz++) {
-          const T p = p2[kz];
-          t0r += p * winr[0][kz];
-          t0i += p * wini[0][kz];
-          t1r += p * winr[1][kz];
-          t1i += p * wini[1][kz];
-        }
-        pr[i] = w0 * t0r + w1 * t1r;
-        pi[i] = w0 * t0i + w1 * t1i;
-      }
-    }
-    // CTA-wide reduction of the NB partial sums: shared-memory transpose, one warp per node
-#pragma unroll
-    for (int i = 0; i < CF::NB; i++) red[i][threadIdx.x] = make_c<T>(pr[i], pi[i]);
-    __syncthreads();
-    for (int i = warp; i < nb; i += NWARPS) {
+  auto reduce_batch = [&](int bb) {   // partial sums of batch bb -> ft (tile order), one warp per node
+    const long long kb = R.k0 + (long long) bb * CF::NB;
+    const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+    const C *red = S.red + (size_t) (bb & 1) * CF::NB * CF::THREADS;
+    for (int i = warp; i < nb; i += CF::NWARPS) {
       T sr = (T) 0, si = (T) 0;
 #pragma unroll
-      for (int q = 0; q < NWARPS; q++) {
-        const C v = red[i][lane + 32 * q];
+      for (int q = 0; q < CF::NWARPS; q++) {
+        const C v = red[i * CF::THREADS + lane + 32 * q];
         sr += v.x;
         si += v.y;
       }
@@ -348,9 +446,64 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
         sr += __shfl_xor_sync(0xffffffffu, sr, o);
         si += __shfl_xor_sync(0xffffffffu, si, o);
       }
-      if (lane == 0) f[perm[k + i]] = make_c<T>(sr, si);
+      if (lane == 0) ft[kb + i] = make_c<T>(sr, si);
     }
+  };
+
+  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
+  RawRegs<T, W, false> raw;
+  raw.load(xt, nullptr, R.k0, R.k1);
+  raw.park(S, 0);
+  raw.load(xt, nullptr, R.k0 + CF::NB, R.k1);
+  raw.park(S, 1);
+  __syncthreads();
+  produce<T, W, false>(S, 0, 0, R.k0, (int) min((long long) CF::NB, R.k1 - R.k0), R.a, R.b, P, table);
+  __syncthreads();
+
+  for (int bb = 0; bb < nbatch; bb++) {
+    const long long kb = R.k0 + (long long) bb * CF::NB;
+    const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+    const int pb = bb & 1;
+    raw.load(xt, nullptr, kb + 2 * CF::NB, R.k1);
+    if (bb > 0) reduce_batch(bb - 1);
+
+    C *red = S.red + (size_t) pb * CF::NB * CF::THREADS;
+    for (int i = 0; i < nb; i++) {
+      const int s = S.slab[pb * CF::NB + i];
+      if (cur < 0) { cur = s; fill_all(); prefetch_next(); }
+      while (cur < s) {
+        if (s - cur >= CF::RETIRE_ALL) {
+          cur = s;
+          fill_all();
+        } else {
+          step_one();
+          cur++;
+        }
+        prefetch_next();
+      }
+      const T *pd = S.pads + (pb * CF::NB + i) * CF::PADLEN;
+      const T w0 = rows.valid[0] ? pd[rows.l0[0]] * pd[CF::F0 + rows.l1[0]] : (T) 0;
+      const T w1 = rows.valid[1] ? pd[rows.l0[1]] * pd[CF::F0 + rows.l1[1]] : (T) 0;
+      const T *p2 = pd + CF::F0 + CF::F1;
+      T t0r = (T) 0, t0i = (T) 0, t1r = (T) 0, t1i = (T) 0;
+#pragma unroll
+      for (int kz = 0; kz < CF::WZ; kz++) {
+        const T p = p2[kz];
+        t0r += p * winr[0][kz];
+        t0i += p * wini[0][kz];
+        t1r += p * winr[1][kz];
+        t1i += p * wini[1][kz];
+      }
+      red[i * CF::THREADS + threadIdx.x] = make_c<T>(w0 * t0r + w1 * t1r, w0 * t0i + w1 * t1i);
+    }
+
+    if (bb + 1 < nbatch)
+      produce<T, W, false>(S, pb ^ 1, pb ^ 1, kb + CF::NB, (int) min((long long) CF::NB, R.k1 - kb - CF::NB),
+                           R.a, R.b, P, table);
+    raw.park(S, pb);
+    __syncthreads();
   }
+  reduce_batch(nbatch - 1);
 }
 
 TileParams make_params(const nfftcu_ctx *c) {
@@ -367,6 +520,7 @@ TileParams make_params(const nfftcu_ctx *c) {
   if (zseg > P.NS) zseg = P.NS;
   P.zseg = (int) zseg;
   P.m = (int) c->m;
+  P.deg = c->kbpoly_deg;
   P.m2 = (double) c->m * (double) c->m;
   P.b0 = c->b[0];
   P.b1 = c->b[1];
@@ -377,11 +531,17 @@ TileParams make_params(const nfftcu_ctx *c) {
 template <typename T, int W>
 int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
+  const int kb = 256;
+  gather_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+      (const C *) f_dev, c->tile_perm, (C *) c->f_tile, c->M);
+  const int polyN = (c->tile_psi || P.deg < 0) ? 0 : 3 * (P.deg + 1) * W;
+  const size_t smem = Smem<T, W, true>::bytes(polyN);
+  NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
-  spread_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, 0, c->stream>>>(
-      (C *) c->grid, (const T *) c->tile_x, c->tile_perm, (const C *) f_dev, c->bin_start,
-      (const T *) c->tile_psi, P);
-  c->launches++;
+  spread_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, smem, c->stream>>>(
+      (C *) c->grid, (const T *) c->tile_x, (const C *) c->f_tile, c->bin_start,
+      (const T *) c->tile_psi, (const double *) c->kbpoly_dev, polyN, P);
+  c->launches += 2;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
 }
@@ -389,11 +549,17 @@ int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
 template <typename T, int W>
 int launch_interp(nfftcu_ctx *c, void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
+  const int polyN = (c->tile_psi || P.deg < 0) ? 0 : 3 * (P.deg + 1) * W;
+  const size_t smem = Smem<T, W, false>::bytes(polyN);
+  NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
-  interp_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, 0, c->stream>>>(
-      (const C *) c->grid, (const T *) c->tile_x, c->tile_perm, (C *) f_dev, c->bin_start,
-      (const T *) c->tile_psi, P);
-  c->launches++;
+  interp_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, smem, c->stream>>>(
+      (const C *) c->grid, (const T *) c->tile_x, (C *) c->f_tile, c->bin_start,
+      (const T *) c->tile_psi, (const double *) c->kbpoly_dev, polyN, P);
+  const int kb = 256;
+  scatter_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+      (const C *) c->f_tile, c->tile_perm, (C *) f_dev, c->M);
+  c->launches += 2;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
 }
@@ -457,6 +623,7 @@ int tile3d_bin_nodes(nfftcu_ctx *c) {
   if (!c->tile_keys) NFFTCU_CUDA(cudaMalloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
   if (!c->tile_perm) NFFTCU_CUDA(cudaMalloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
   if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, real_size(c) * (size_t) M * 3));
+  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
   if (!c->bin_start || c->tile_nbins != nbins) {
     if (c->bin_start) cudaFree(c->bin_start);
     NFFTCU_CUDA(cudaMalloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (nbins + 1)));

@@ -166,8 +166,12 @@ def test_vs_oracle(case, precision):
     spec = ORACLE_CASES[case]
     x, fh, f = make_case(spec, precision)
     o = oracle(precision)
+    want_f = o.trafo(spec["N"], spec["n"], spec["m"], x, fh)
+    if not np.all(np.isfinite(want_f)):
+        # m = 9 in 3-D: psi0*psi1*psi2 ~ (1e17)^3 overflows float in the reference's arithmetic too
+        pytest.skip("window product overflows single precision")
     out_f, out_fh, _ = run_plan(spec, precision, x, fh, f)
-    assert rel_l2(out_f, o.trafo(spec["N"], spec["n"], spec["m"], x, fh)) <= TOL[precision]
+    assert rel_l2(out_f, want_f) <= TOL[precision]
     assert rel_l2(out_fh, o.adjoint(spec["N"], spec["n"], spec["m"], x, f, True)) <= TOL[precision]
 
 
