@@ -81,7 +81,8 @@ struct nfftcu_ctx_s {
   uint32_t *tile_perm = nullptr;    // tile order -> original node index
   void *tile_x = nullptr;           // M*3 reals in tile order
   uint32_t *bin_start = nullptr;    // nbins+1 offsets into the tile order
-  void *tile_psi = nullptr;         // optional window table in tile order
+  void *tile_psi = nullptr;         // node records of the pencil kernels (padded window vectors, slab, f)
+  bool tile_psi_valid = false;      // window part of the records matches the current nodes
   long long tile_nbins = 0;
   void *f_tile = nullptr;           // M complex: samples in tile order (gathered / to be scattered)
   // piecewise-polynomial window (kbpoly.cu): coef[(t*(deg+1)+k)*W + l]
@@ -116,6 +117,7 @@ inline size_t real_size(const nfftcu_ctx *c) { return c->prec == NFFTCU_DOUBLE ?
 int sort_nodes(nfftcu_ctx *c);                                      // sort.cu
 int radix_sort_pairs(nfftcu_ctx *c, uint64_t *keys, uint32_t *vals, long long M, int bits);  // sort.cu
 int gather_nodes(nfftcu_ctx *c, const uint32_t *perm, void *dst);   // sort.cu
+constexpr int kKbPolyDeg = 16;                                      // stored degree of the window polynomials
 int build_kb_poly(nfftcu_ctx *c);                                   // kbpoly.cu
 bool tile3d_supported(const nfftcu_ctx *c);                         // tile3d.cu
 int tile3d_bin_nodes(nfftcu_ctx *c);                                // tile3d.cu

@@ -10,8 +10,8 @@
 //     psi_l = phi(frac + m - l) = P_l(y),   y = 2 frac - 1 in [-1,1].
 // P_l is the Chebyshev interpolant of degree p on [-1,1], built here in long double and converted
 // to monomial coefficients; p is raised until the maximum deviation from the long-double window
-// at 64 check points per tap is below 3e-15 of the window's peak (p = 13..16 in practice), so the
-// device evaluates a value with p FMAs (Horner).  If that cannot be reached with p <= 24 the
+// at 64 check points per tap is below 3e-15 of the window's peak (p = 13..16 in practice; capped at kKbPolyDeg = 16), so the
+// device evaluates a value with p FMAs (Horner).  If that cannot be reached the
 // plan keeps the closed form (kb_phi in common.cuh).
 #include "common.cuh"
 
@@ -63,14 +63,16 @@ void cheb_fit_monomial(int p, long double m, long double b, int l, std::vector<l
 
 }  // namespace
 
-// Fills c->kbpoly (host, double) with layout coef[(t*(deg+1) + k)*W + l], k = power of y, and
+// Fills c->kbpoly (host, double) with layout coef[(t*(kKbPolyDeg+1) + k)*W + l], k = power of y, and
 // uploads it.  Returns NFFTCU_OK; c->kbpoly_deg stays -1 when no adequate polynomial was found.
 int build_kb_poly(nfftcu_ctx *c) {
   const int W = 2 * (int) c->m + 2;
   const long double m = (long double) c->m;
   c->kbpoly_deg = -1;
-  for (int p = 10; p <= 24; p++) {
-    std::vector<double> coef((size_t) c->d * (p + 1) * W);
+  // The device keeps the coefficients of one tap in registers and runs a fixed-length Horner loop, so
+  // the table is always stored with kKbPolyDeg+1 coefficients per tap (higher ones zero).
+  for (int p = 10; p <= kKbPolyDeg; p++) {
+    std::vector<double> coef((size_t) c->d * (kKbPolyDeg + 1) * W, 0.0);
     long double worst = 0;
     for (int t = 0; t < c->d; t++) {
       const long double b = (long double) c->b[t];
@@ -78,11 +80,11 @@ int build_kb_poly(nfftcu_ctx *c) {
       for (int l = 0; l < W; l++) {
         std::vector<long double> mono;
         cheb_fit_monomial(p, m, b, l, mono);
-        for (int k = 0; k <= p; k++) coef[((size_t) t * (p + 1) + k) * W + l] = (double) mono[(size_t) k];
+        for (int k = 0; k <= p; k++) coef[((size_t) t * (kKbPolyDeg + 1) + k) * W + l] = (double) mono[(size_t) k];
         for (int q = 0; q <= 64; q++) {   // check the double-precision Horner value itself
           const double y = -1.0 + 2.0 * q / 64.0;
-          double acc = coef[((size_t) t * (p + 1) + p) * W + l];
-          for (int k = p - 1; k >= 0; k--) acc = fma(acc, y, coef[((size_t) t * (p + 1) + k) * W + l]);
+          double acc = coef[((size_t) t * (kKbPolyDeg + 1) + kKbPolyDeg) * W + l];
+          for (int k = kKbPolyDeg - 1; k >= 0; k--) acc = fma(acc, y, coef[((size_t) t * (kKbPolyDeg + 1) + k) * W + l]);
           const long double ref = phi_ld(((long double) y + 1) / 2 + m - l, m, b);
           const long double e = fabsl((long double) acc - ref) / peak;
           if (e > worst) worst = e;
@@ -90,7 +92,7 @@ int build_kb_poly(nfftcu_ctx *c) {
       }
     }
     if (worst < 3e-15L) {
-      c->kbpoly_deg = p;
+      c->kbpoly_deg = kKbPolyDeg;   // stored (padded) degree; the fitted degree is p
       c->kbpoly_host = coef;
       break;
     }

@@ -9,11 +9,11 @@
 //
 // Geometry.  Nodes are binned by the corner u = floor(x n) - m of their (2m+2)^3 tap box:
 //   tile (a,b)  = (u0 / T0, u1 / T1), T0 = T1 = 3        slab s = u2 / SZ, SZ = 2.
-// A CTA owns one tile and sweeps a range of slabs along the contiguous axis z.  Every tap box of
-// the tile lies inside the tile's FOOTPRINT of F0 x F1 = (T0+W-1) x (T1+W-1) grid rows (W = 2m+2;
-// 16 x 16 rows for m = 6) and, for the current slab, inside a z-window of WZ = W+SZ-1 cells.
-// Each thread owns two footprint rows and keeps their z-windows -- 2 x WZ complex values -- in
-// REGISTERS:
+// A group of consumer warps owns one tile and sweeps a range of slabs along the contiguous axis z.
+// Every tap box of the tile lies inside the tile's FOOTPRINT of F0 x F1 = (T0+W-1) x (T1+W-1) grid rows
+// (W = 2m+2; 16 x 16 rows for m = 6) and, for the current slab, inside a z-window of WZ = W+SZ-1
+// cells.  Each consumer thread owns two footprint rows and keeps their z-windows -- 2 x WZ complex
+// values -- in REGISTERS:
 //   spreading      the windows are accumulators; a node adds (psi0 psi1 f_j) * psi2[k] to all WZ cells
 //                  of the thread's rows (psi vectors are zero-padded to the footprint / window, so the
 //                  register indices are static); when the sweep leaves a slab, the SZ cells that
@@ -21,22 +21,28 @@
 //                  No shared-memory accumulation, no intra-CTA conflicts: a row has one owner.
 //   interpolation  the windows hold grid values, refilled SZ cells per slab straight from L2 (the
 //                  cells of the next slab are prefetched one slab ahead); a node reduces them against
-//                  psi2, weights by psi0 psi1, and the per-thread partial sums of a batch are reduced
-//                  across the CTA through shared memory one batch later.
+//                  psi2, weights by psi0 psi1, and the per-thread partial sums are reduced across the
+//                  group through shared memory by the (otherwise idle) producer warp.
 // Per tap this costs 2 FP64 FMAs and, per node and thread, WZ broadcast shared-memory loads of psi2
 // -- instead of one 16-byte shared/L1 load per tap -- which moves the kernel from the LSU roof
 // (128 B/clk/SM) to the FP64 roof (64 FMA/clk/SM); see DESIGN.md for the arithmetic and
 // profiles/ for the measurements.  Zero padding costs (W/F0)(W/F1)(W/WZ) = 71% lane efficiency at m = 6.
 //
-// Warp specialisation inside a CTA.  The consumer warps (two footprint rows per thread) do nothing but
-// the node loop: read the node's padded window vectors from shared memory, FMA into / out of their
-// register windows, advance the window when the slab changes.  One producer warp runs up to
-// STAGES-1 batches (of NB nodes) ahead: it streams the raw node data (x, f) from HBM, evaluates the
-// window (piecewise polynomial of kbpoly.cu, the optional per-node table, or the closed form), writes
-// the zero-padded vectors into a ring of STAGES shared-memory stages and, for interpolation,
-// reduces the consumers' per-thread partial sums of finished batches.  Stages are handed over with
-// named barriers (bar.sync / bar.arrive, one full/empty pair per stage); the consumers never wait
-// on global memory and there is no CTA-wide __syncthreads in the steady state.
+// Two kernels per transform.
+//  (1) expand_nodes_kernel: a streaming pass over the nodes (tile order) that evaluates the window --
+//      piecewise polynomial of kbpoly.cu (Horner chains with the coefficients of a tap in registers),
+//      or the closed form -- and writes one fixed-size RECORD per node:
+//          [ psi0 padded to F0 | psi1 padded to F1 | psi2 padded to WZP | slab | f.re | f.im ]
+//      HBM-bound (REC*sizeof(T) = 416 B per node in fp64) and trivially parallel.  With the PRE_PSI
+//      analogue (NFFTCU_OPT_PSI_TABLE) the records are kept across transforms and only f is refreshed.
+//  (2) the pencil kernel.  A CTA is three warpgroups: two consumer warpgroups and one producer
+//      warpgroup, compiled at 168 registers and rebalanced with setmaxnreg (consumers 232, producers
+//      40; the register file is handed out in units of 4 warps, profiles/r01h shows what the
+//      168-register cap costs).  A producer warp feeds its group's ring of STAGES shared-memory
+//      stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of NB records at a time; the
+//      consumers wait on the stage's "full" mbarrier, run the node loop out of shared memory and
+//      registers only, and release the stage through its "empty" mbarrier.  The consumers never wait
+//      on global memory except for the window refill of interpolation, which is prefetched.
 #include "common.cuh"
 
 namespace nfftcu {
@@ -44,20 +50,30 @@ namespace nfftcu {
 namespace {
 
 constexpr int kT0 = 3, kT1 = 3, kSZ = 2, kNB = 8, kStages = 4;
+constexpr int kCtaThreads = 384;   // two consumer warpgroups + one producer warpgroup
+constexpr int kConsumerRegs = 232, kProducerRegs = 40;   // 128*(232+232+40) = 64512 <= 65536
 
-template <int W_>
+template <typename T, int W_>
 struct Cfg {
   static constexpr int W = W_, T0 = kT0, T1 = kT1, SZ = kSZ, NB = kNB, STAGES = kStages;
   static constexpr int F0 = T0 + W - 1, F1 = T1 + W - 1, ROWS = F0 * F1;
   static constexpr int WZ = W + SZ - 1;
-  static constexpr int WZP = (WZ + 1) & ~1;
-  static constexpr int CT = ((((ROWS + 1) / 2) + 31) / 32) * 32;   // consumer threads
-  static constexpr int NWARPS = CT / 32;                           // consumer warps
-  static constexpr int THREADS = CT + 32;                          // + one producer warp
+  static constexpr int WZP = (WZ + 3) & ~3;
   static constexpr int PADLEN = F0 + F1 + WZP;
-  static constexpr int MINB = THREADS <= 160 ? 2 : 1;
+  static constexpr int RALIGN = 16 / (int) sizeof(T);
+  static constexpr int REC = ((PADLEN + 3 + RALIGN - 1) / RALIGN) * RALIGN;   // record length in T
+  static constexpr int CT = ((((ROWS + 1) / 2) + 31) / 32) * 32;   // consumer threads of a group
+  static constexpr int NWARPS = CT / 32;
+  // W <= 14: each consumer warpgroup is its own group (own tile, own producer warp, own ring);
+  // W >= 16: the two consumer warpgroups form one group of CT = 224 consumers.
+  static constexpr int GROUPS = CT <= 128 ? 2 : 1;
+  static constexpr int CTP = 256 / GROUPS;                         // consumer thread slots per group
   static constexpr int RETIRE_ALL = (WZ + SZ - 1) / SZ;   // slabs after which the whole window has left
-  static_assert(NB * 4 == 32, "the producer warp loads 3 coordinates + 1 sample per node with one lane each");
+  static constexpr int VMAX = F0 > WZP ? (F0 > F1 ? F0 : F1) : (WZP > F1 ? WZP : F1);
+  static constexpr int LPI = VMAX <= 16 ? 16 : 32, IPP = 32 / LPI;   // lanes per item, items per pass
+  static_assert(CT <= 256, "footprint does not fit two consumer warpgroups");
+  static_assert(NB * 4 == 32, "expand: 3 coordinate lanes + 1 sample lane per node");
+  static_assert(VMAX <= 32, "padded vectors longer than a warp");
 };
 
 struct TileParams {
@@ -65,7 +81,7 @@ struct TileParams {
   int NT0, NT1, NS;
   int zseg;
   int m;
-  int deg;          // polynomial degree, -1: closed form
+  int deg;          // kKbPolyDeg when the polynomial window is available, -1: closed form
   double m2, b0, b1, b2;
 };
 
@@ -86,14 +102,32 @@ __device__ __forceinline__ int wrap_z(int z, int n2) {
 __device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
 
-__device__ __forceinline__ void bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+// ---- mbarrier / TMA bulk copy ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-#define BAR_FULL(s) (1 + (s))
-#define BAR_EMPTY(s) (1 + kStages + (s))
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 template <typename T>
 __global__ void tile_keys_kernel(const T *__restrict__ x, uint64_t *__restrict__ keys,
@@ -123,68 +157,136 @@ __global__ void bin_bounds_kernel(const uint64_t *__restrict__ keys, uint32_t *_
 }
 
 template <typename C>
-__global__ void gather_f_kernel(const C *__restrict__ f, const uint32_t *__restrict__ perm,
-                                C *__restrict__ ft, long long M) {
-  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < M) ft[k] = f[perm[k]];
-}
-
-template <typename C>
 __global__ void scatter_f_kernel(const C *__restrict__ ft, const uint32_t *__restrict__ perm,
                                  C *__restrict__ f, long long M) {
   const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (k < M) f[perm[k]] = ft[k];
 }
 
-// ---- shared-memory carve-up ------------------------------------------------------------------------
+// only the samples of the records (spreading with cached records)
+template <typename T, int W>
+__global__ void refresh_f_kernel(T *__restrict__ rec, const typename Cplx<T>::type *__restrict__ f,
+                                 const uint32_t *__restrict__ perm, long long M) {
+  typedef Cfg<T, W> CF;
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const typename Cplx<T>::type v = f[perm[k]];
+  rec[k * CF::REC + CF::PADLEN + 1] = v.x;
+  rec[k * CF::REC + CF::PADLEN + 2] = v.y;
+}
+
+// ---- (1) window expansion ------------------------------------------------------------------------------
+// One warp per chunk of NB nodes (tile order).  Lanes 0..23 fetch the 3*NB coordinates, lanes 24..31
+// the samples.  Polynomial window, lanes <-> taps: a lane keeps the kKbPolyDeg+1 coefficients of ITS
+// tap in registers (reloaded per dimension: the shape parameter b may differ), LPI lanes serve one
+// (node, dimension) item, spare lanes write the zero padding; IPP items per pass and 4 passes are
+// independent Horner chains.
+template <typename T, int W, bool SPREAD>
+__global__ void __launch_bounds__(256)
+expand_nodes_kernel(T *__restrict__ rec, const T *__restrict__ xt,
+                    const typename Cplx<T>::type *__restrict__ f, const uint32_t *__restrict__ perm,
+                    const double *__restrict__ poly, long long M, TileParams P) {
+  typedef Cfg<T, W> CF;
+  typedef typename Cplx<T>::type C;
+  __shared__ double spoly[3 * (kKbPolyDeg + 1) * W];
+  if (P.deg >= 0)
+    for (int i = threadIdx.x; i < 3 * (kKbPolyDeg + 1) * W; i += blockDim.x) spoly[i] = poly[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  const long long nchunks = (M + CF::NB - 1) / CF::NB;
+  const bool xlane = lane < CF::NB * 3;
+  const int half = lane / CF::LPI, l = lane - half * CF::LPI;
+  for (long long ch = warp; ch < nchunks; ch += nwarps) {
+    const long long kb = ch * CF::NB;
+    const int nb = (int) min((long long) CF::NB, M - kb);
+    T x = (T) 0;
+    if (xlane) {
+      if (kb * 3 + lane < M * 3) x = xt[kb * 3 + lane];
+    } else if (SPREAD) {
+      const long long k = kb + (lane - CF::NB * 3);
+      if (k < M) {
+        const C v = f[perm[k]];
+        rec[k * CF::REC + CF::PADLEN + 1] = v.x;
+        rec[k * CF::REC + CF::PADLEN + 2] = v.y;
+      }
+    }
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+      const int nt = (t == 0) ? P.n0 : (t == 1) ? P.n1 : P.n2;
+      const int vb = (t == 0) ? 0 : (t == 1) ? CF::F0 : CF::F0 + CF::F1;
+      const int vl = (t == 0) ? CF::F0 : (t == 1) ? CF::F1 : CF::WZP;
+      const int tmod = (t == 0) ? CF::T0 : (t == 1) ? CF::T1 : CF::SZ;
+      double cf[kKbPolyDeg + 1];
+      if (P.deg >= 0) {
+#pragma unroll
+        for (int k = 0; k <= kKbPolyDeg; k++)
+          cf[k] = (l < W) ? spoly[((size_t) t * (kKbPolyDeg + 1) + k) * W + l] : 0.0;
+      }
+      const double bt = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
+#pragma unroll 4
+      for (int i0 = 0; i0 < CF::NB; i0 += CF::IPP) {
+        const int i = i0 + half;
+        const T xi = __shfl_sync(0xffffffffu, x, 3 * i + t);
+        const long long cc = cell_of(xi, nt);
+        const int u = wrap_fast(cc - P.m, nt);
+        const int delta = u % tmod;
+        double acc;
+        if (P.deg >= 0) {
+          const double y = 2.0 * ((double) xi * (double) nt - (double) cc) - 1.0;
+          acc = cf[kKbPolyDeg];
+#pragma unroll
+          for (int k = kKbPolyDeg - 1; k >= 0; k--) acc = fma(acc, y, cf[k]);
+        } else {
+          acc = (l < W) ? kb_phi((double) xi * (double) nt - (double) (cc - P.m + l), P.m2, bt) : 0.0;
+        }
+        if (i < nb) {
+          T *dst = rec + (kb + i) * CF::REC + vb;
+          if (t == 2 && l == 0) rec[(kb + i) * CF::REC + CF::PADLEN] = (T) (u / CF::SZ);
+          if (l < W) dst[delta + l] = (T) acc;
+          else if (l - W < vl - W) dst[(l - W < delta) ? l - W : l] = (T) 0;
+        }
+      }
+    }
+  }
+}
+
+// ---- (2) pencil kernels ----------------------------------------------------------------------------------
 template <typename T, int W, bool SPREAD>
 struct Smem {
-  typedef Cfg<W> CF;
+  typedef Cfg<T, W> CF;
   typedef typename Cplx<T>::type C;
-  C *red;       // [STAGES][NB][CT]     interpolation partial sums
-  C *padf;      // [STAGES][NB]         f_j of the batch (spreading)
-  double *poly; // [polyN]
-  T *pads;      // [STAGES][NB][PADLEN]
-  T *rawx;      // [NB*3]               producer staging
-  int *slab;    // [STAGES][NB]
-  int *nbv;     // [STAGES]             nodes in the stage
+  C *red;          // [STAGES][NB][CT]   interpolation partial sums
+  T *stage;        // [STAGES][NB*REC]   node records
+  uint64_t *full;  // [STAGES]
+  uint64_t *empty; // [STAGES]
 
-  __host__ __device__ static size_t bytes(int polyN) {
+  __host__ __device__ static size_t bytes() {
     size_t b = 0;
     if (!SPREAD) b += sizeof(C) * CF::STAGES * CF::NB * CF::CT;
-    b += sizeof(C) * CF::STAGES * CF::NB;
-    b += sizeof(double) * (size_t) polyN;
-    b += sizeof(T) * CF::STAGES * CF::NB * CF::PADLEN;
-    b = (b + 15) & ~(size_t) 15;
-    b += sizeof(T) * CF::NB * 3;
-    b = (b + 7) & ~(size_t) 7;
-    b += sizeof(int) * (CF::STAGES * CF::NB + CF::STAGES);
-    return b;
+    b += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
+    b += sizeof(uint64_t) * 2 * CF::STAGES;
+    return (b + 127) & ~(size_t) 127;
   }
-  __device__ __forceinline__ Smem(unsigned char *base, int polyN) {
+  __device__ __forceinline__ Smem(unsigned char *base) {
     size_t o = 0;
     red = reinterpret_cast<C *>(base);
     if (!SPREAD) o += sizeof(C) * CF::STAGES * CF::NB * CF::CT;
-    padf = reinterpret_cast<C *>(base + o);
-    o += sizeof(C) * CF::STAGES * CF::NB;
-    poly = reinterpret_cast<double *>(base + o);
-    o += sizeof(double) * (size_t) polyN;
-    pads = reinterpret_cast<T *>(base + o);
-    o += sizeof(T) * CF::STAGES * CF::NB * CF::PADLEN;
-    o = (o + 15) & ~(size_t) 15;
-    rawx = reinterpret_cast<T *>(base + o);
-    o += sizeof(T) * CF::NB * 3;
-    o = (o + 7) & ~(size_t) 7;
-    slab = reinterpret_cast<int *>(base + o);
-    nbv = slab + CF::STAGES * CF::NB;
+    stage = reinterpret_cast<T *>(base + o);
+    o += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
+    full = reinterpret_cast<uint64_t *>(base + o);
+    empty = full + CF::STAGES;
   }
 };
 
 struct TileRange {
   int a, b;
   long long k0, k1;
-  __device__ __forceinline__ TileRange(const uint32_t *__restrict__ bin_start, const TileParams &P) {
-    const int tile = blockIdx.x / P.zseg, seg = blockIdx.x - tile * P.zseg;
+  __device__ __forceinline__ TileRange(const uint32_t *__restrict__ bin_start, const TileParams &P,
+                                       long long unit, long long units) {
+    if (unit >= units) { a = b = 0; k0 = k1 = 0; return; }
+    const int tile = (int) (unit / P.zseg), seg = (int) (unit - (long long) tile * P.zseg);
     a = tile / P.NT1;
     b = tile - a * P.NT1;
     const int s_begin = (int) ((long long) P.NS * seg / P.zseg);
@@ -195,21 +297,18 @@ struct TileRange {
   }
 };
 
-// ---- producer warp -----------------------------------------------------------------------------------
-// Fills ring stage after ring stage: pads[s][i] = [ psi0 padded to F0 | psi1 padded to F1 | psi2 padded to
-// WZP ], slab[s][i] = u2 / SZ, padf[s][i] = f_j (spreading).  Every pad element is written exactly once.
-// For interpolation it also turns the consumers' partial sums of a finished stage into ft[k].
+// producer warp of a group: TMA-feeds the ring; for interpolation it also turns the consumers' partial
+// sums of a released stage into ft[k]
 template <typename T, int W, bool SPREAD>
 __device__ __forceinline__ void producer_warp(const Smem<T, W, SPREAD> &S, const TileRange &R,
-                                              const TileParams &P, const T *__restrict__ xt,
-                                              typename Cplx<T>::type *__restrict__ ft,
-                                              const T *__restrict__ table) {
-  typedef Cfg<W> CF;
+                                              const T *__restrict__ rec,
+                                              typename Cplx<T>::type *__restrict__ ft) {
+  typedef Cfg<T, W> CF;
   typedef typename Cplx<T>::type C;
   const int lane = threadIdx.x & 31;
   const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
 
-  auto reduce_stage = [&](int bb) {   // interpolation: sum the CT partials of every node of batch bb
+  auto reduce_stage = [&](int bb) {
     const int s = bb % CF::STAGES;
     const long long kb = R.k0 + (long long) bb * CF::NB;
     const int nb = (int) min((long long) CF::NB, R.k1 - kb);
@@ -231,138 +330,91 @@ __device__ __forceinline__ void producer_warp(const Smem<T, W, SPREAD> &S, const
     }
   };
 
-  // raw data of batch 0 (lanes 0..23: coordinates, lanes 24..31: samples)
-  T px = (T) 0;
-  C pf = make_c<T>((T) 0, (T) 0);
-  auto load_raw = [&](long long kb) {
-    px = (T) 0;
-    pf = make_c<T>((T) 0, (T) 0);
-    if (lane < CF::NB * 3) {
-      const long long idx = kb * 3 + lane;
-      if (idx < R.k1 * 3) px = xt[idx];
-    } else if (SPREAD) {
-      const long long idx = kb + (lane - CF::NB * 3);
-      if (idx < R.k1) pf = ft[idx];
-    }
-  };
-  load_raw(R.k0);
-
   for (int bb = 0; bb < nbatch; bb++) {
-    const int s = bb % CF::STAGES;
-    const long long kb = R.k0 + (long long) bb * CF::NB;
-    const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+    const int s = bb % CF::STAGES, r = bb / CF::STAGES;
     if (bb >= CF::STAGES) {
-      bar_sync(BAR_EMPTY(s), CF::THREADS);      // consumers are done with what was in this stage
+      mbar_wait(&S.empty[s], (r - 1) & 1);      // consumers released what was in this stage
       if (!SPREAD) reduce_stage(bb - CF::STAGES);
+      __syncwarp();
     }
-    if (lane < CF::NB * 3) S.rawx[lane] = px;
-    else if (SPREAD) S.padf[s * CF::NB + (lane - CF::NB * 3)] = pf;
-    __syncwarp();
-    load_raw(kb + CF::NB);                       // next batch: in flight while this one is evaluated
-
-    T *pads = S.pads + (size_t) s * CF::NB * CF::PADLEN;
-#pragma unroll 4
-    for (int it = lane; it < CF::NB * CF::PADLEN; it += 32) {
-      const int i = it / CF::PADLEN, q = it - i * CF::PADLEN;
-      int t, pos;
-      if (q < CF::F0) { t = 0; pos = q; }
-      else if (q < CF::F0 + CF::F1) { t = 1; pos = q - CF::F0; }
-      else { t = 2; pos = q - CF::F0 - CF::F1; }
-      T val = (T) 0;
-      if (i < nb) {
-        const T x = S.rawx[i * 3 + t];
-        const int n = (t == 0) ? P.n0 : (t == 1) ? P.n1 : P.n2;
-        const long long cc = cell_of(x, n);
-        const int u = wrap_fast(cc - P.m, n);
-        const int delta = (t == 0) ? u - R.a * CF::T0 : (t == 1) ? u - R.b * CF::T1 : u % CF::SZ;
-        const int l = pos - delta;
-        if (t == 2 && pos == 0) S.slab[s * CF::NB + i] = u / CF::SZ;
-        if (l >= 0 && l < W) {
-          if (table) val = table[((kb + i) * 3 + t) * W + l];
-          else if (P.deg >= 0) {
-            const double y = 2.0 * ((double) x * (double) n - (double) cc) - 1.0;
-            const double *cf = S.poly + (size_t) t * (P.deg + 1) * W + l;
-            double acc = cf[P.deg * W];
-            for (int k = P.deg - 1; k >= 0; k--) acc = fma(acc, y, cf[k * W]);
-            val = (T) acc;
-          } else {
-            const double bb2 = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
-            val = (T) kb_phi((double) x * (double) n - (double) (cc - P.m + l), P.m2, bb2);
-          }
-        }
-      }
-      pads[it] = val;
+    if (lane == 0) {
+      const long long kb = R.k0 + (long long) bb * CF::NB;
+      const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+      const uint32_t bytes = (uint32_t) (nb * CF::REC * sizeof(T));
+      mbar_expect_tx(&S.full[s], bytes);
+      bulk_g2s(S.stage + (size_t) s * CF::NB * CF::REC, rec + kb * CF::REC, bytes, &S.full[s]);
     }
-    if (lane == 0) S.nbv[s] = nb;
-    __syncwarp();
-    __threadfence_block();
-    bar_arrive(BAR_FULL(s), CF::THREADS);
   }
   if (!SPREAD) {
     for (int bb = max(0, nbatch - CF::STAGES); bb < nbatch; bb++) {
-      bar_sync(BAR_EMPTY(bb % CF::STAGES), CF::THREADS);
+      mbar_wait(&S.empty[bb % CF::STAGES], (bb / CF::STAGES) & 1);
       reduce_stage(bb);
     }
   }
 }
 
+// four consecutive psi2 values with vector loads (the psi2 segment of a record starts 16-byte aligned
+// and is padded so that a 4-wide read never leaves it: see Cfg::WZP)
 template <typename T> struct PsiLoad;
 template <> struct PsiLoad<double> {
-  template <int N> static __device__ __forceinline__ void load(const double *p, double (&out)[N]) {
-#pragma unroll
-    for (int k = 0; k + 1 < N; k += 2) {
-      const double2 v = *reinterpret_cast<const double2 *>(p + k);
-      out[k] = v.x;
-      out[k + 1] = v.y;
-    }
-    if (N & 1) out[N - 1] = p[N - 1];
+  static __device__ __forceinline__ void load4(const double *p, double (&q)[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
   }
 };
 template <> struct PsiLoad<float> {
-  template <int N> static __device__ __forceinline__ void load(const float *p, float (&out)[N]) {
-#pragma unroll
-    for (int k = 0; k + 3 < N; k += 4) {
-      const float4 v = *reinterpret_cast<const float4 *>(p + k);
-      out[k] = v.x; out[k + 1] = v.y; out[k + 2] = v.z; out[k + 3] = v.w;
-    }
-#pragma unroll
-    for (int k = N & ~3; k < N; k++) out[k] = p[k];
+  static __device__ __forceinline__ void load4(const float *p, float (&q)[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
   }
 };
 
+// common prologue: roles, work unit, barriers.  Returns false for threads that have nothing to do.
+#define NFFTCU_PENCIL_PROLOGUE(SPREADV)                                                              \
+  typedef Cfg<T, W> CF;                                                                              \
+  typedef typename Cplx<T>::type C;                                                                  \
+  extern __shared__ __align__(128) unsigned char smem_raw[];                                         \
+  const bool is_producer = threadIdx.x >= 256;                                                       \
+  const int g = is_producer ? (threadIdx.x - 256) / 32 : threadIdx.x / CF::CTP;                      \
+  const int tid = is_producer ? CF::CT + (threadIdx.x & 31) : threadIdx.x - g * CF::CTP;             \
+  const int gs = min(g, CF::GROUPS - 1);                                                             \
+  const long long units = (long long) P.NT0 * P.NT1 * P.zseg;                                        \
+  const TileRange R(bin_start, P, (long long) blockIdx.x * CF::GROUPS + gs, units);                  \
+  const Smem<T, W, SPREADV> S(smem_raw + (size_t) gs * Smem<T, W, SPREADV>::bytes());                \
+  if (threadIdx.x < CF::GROUPS) {                                                                    \
+    const Smem<T, W, SPREADV> Sg(smem_raw + (size_t) threadIdx.x * Smem<T, W, SPREADV>::bytes());    \
+    for (int s = 0; s < CF::STAGES; s++) { mbar_init(&Sg.full[s], 1); mbar_init(&Sg.empty[s], CF::NWARPS); } \
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                               \
+  }                                                                                                  \
+  __syncthreads();                                                                                   \
+  if (is_producer) {                                                                                 \
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));                        \
+    if (g < CF::GROUPS && R.k0 != R.k1) producer_warp<T, W, SPREADV>(S, R, rec, ft);                 \
+    return;                                                                                          \
+  }                                                                                                  \
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));                          \
+  if (tid >= CF::CT || R.k0 == R.k1) return;                                                         \
+  const int lane = tid & 31;                                                                         \
+  const int r0 = tid, r1 = tid + CF::CT;                                                             \
+  const bool v1 = r1 < CF::ROWS;                                                                     \
+  const int l0a = r0 / CF::F1, l1a = r0 - l0a * CF::F1;                                              \
+  const int l0b = v1 ? r1 / CF::F1 : 0, l1b = v1 ? r1 - l0b * CF::F1 : 0;                            \
+  const long long offa = ((long long) wrap_fast((long long) R.a * CF::T0 + l0a, P.n0) * P.n1 +       \
+                          wrap_fast((long long) R.b * CF::T1 + l1a, P.n1)) * P.n2;                   \
+  const long long offb = ((long long) wrap_fast((long long) R.a * CF::T0 + l0b, P.n0) * P.n1 +       \
+                          wrap_fast((long long) R.b * CF::T1 + l1b, P.n1)) * P.n2;                   \
+  const int n2 = P.n2;                                                                               \
+  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
+
 // ---- spreading ---------------------------------------------------------------------------------------
 template <typename T, int W>
-__global__ void __launch_bounds__(Cfg<W>::THREADS, Cfg<W>::MINB)
-spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__ xt,
-                   typename Cplx<T>::type *__restrict__ ft,
-                   const uint32_t *__restrict__ bin_start, const T *__restrict__ table,
-                   const double *__restrict__ poly, int polyN, TileParams P) {
-  typedef Cfg<W> CF;
-  typedef typename Cplx<T>::type C;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const TileRange R(bin_start, P);
-  if (R.k0 == R.k1) return;
-  const Smem<T, W, true> S(smem_raw, polyN);
-  for (int i = threadIdx.x; i < polyN; i += CF::THREADS) S.poly[i] = poly[i];
-  __syncthreads();
-
-  if (threadIdx.x >= CF::CT) {
-    producer_warp<T, W, true>(S, R, P, xt, ft, table);
-    return;
-  }
-
-  // ---- consumers ----
-  const int r0 = threadIdx.x, r1 = threadIdx.x + CF::CT;
-  const bool v1 = r1 < CF::ROWS;
-  const int l0a = r0 / CF::F1, l1a = r0 - l0a * CF::F1;
-  const int l0b = v1 ? r1 / CF::F1 : 0, l1b = v1 ? r1 - l0b * CF::F1 : 0;
-  T *const Ga = reinterpret_cast<T *>(G) +
-                2 * (((long long) wrap_fast((long long) R.a * CF::T0 + l0a, P.n0) * P.n1 +
-                      wrap_fast((long long) R.b * CF::T1 + l1a, P.n1)) * P.n2);
-  T *const Gb = reinterpret_cast<T *>(G) +
-                2 * (((long long) wrap_fast((long long) R.a * CF::T0 + l0b, P.n0) * P.n1 +
-                      wrap_fast((long long) R.b * CF::T1 + l1b, P.n1)) * P.n2);
-  const int n2 = P.n2;
+__global__ void __launch_bounds__(kCtaThreads, 1)
+spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__ rec,
+                   typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
+                   TileParams P) {
+  NFFTCU_PENCIL_PROLOGUE(true)
+  T *const Ga = reinterpret_cast<T *>(G) + 2 * offa;
+  T *const Gb = reinterpret_cast<T *>(G) + 2 * offb;
 
   T ar[2][CF::WZ], ai[2][CF::WZ];
 #pragma unroll
@@ -390,14 +442,13 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
     }                                                                                        \
   }
 
-  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
   for (int bb = 0; bb < nbatch; bb++) {
     const int s = bb % CF::STAGES;
-    bar_sync(BAR_FULL(s), CF::THREADS);
-    const int nb = S.nbv[s];
-    const T *pd = S.pads + (size_t) s * CF::NB * CF::PADLEN;
-    for (int i = 0; i < nb; i++, pd += CF::PADLEN) {
-      const int sl = S.slab[s * CF::NB + i];
+    const int nb = (int) min((long long) CF::NB, R.k1 - R.k0 - (long long) bb * CF::NB);
+    mbar_wait(&S.full[s], (bb / CF::STAGES) & 1);
+    const T *pd = S.stage + (size_t) s * CF::NB * CF::REC;
+    for (int i = 0; i < nb; i++, pd += CF::REC) {
+      const int sl = (int) pd[CF::PADLEN];
       if (sl != cur) {
         if (cur < 0) cur = sl;
         while (cur < sl) {
@@ -410,21 +461,28 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
           }
         }
       }
-      const C fj = S.padf[s * CF::NB + i];
+      const T fx = pd[CF::PADLEN + 1], fy = pd[CF::PADLEN + 2];
       const T w0 = pd[l0a] * pd[CF::F0 + l1a];
       const T w1 = v1 ? pd[l0b] * pd[CF::F0 + l1b] : (T) 0;
-      const T a0 = w0 * fj.x, b0 = w0 * fj.y, a1 = w1 * fj.x, b1 = w1 * fj.y;
-      T p2[CF::WZ];
-      PsiLoad<T>::load(pd + CF::F0 + CF::F1, p2);
+      const T a0 = w0 * fx, b0 = w0 * fy, a1 = w1 * fx, b1 = w1 * fy;
+      const T *p2 = pd + CF::F0 + CF::F1;
 #pragma unroll
-      for (int kz = 0; kz < CF::WZ; kz++) {
-        ar[0][kz] += a0 * p2[kz];
-        ai[0][kz] += b0 * p2[kz];
-        ar[1][kz] += a1 * p2[kz];
-        ai[1][kz] += b1 * p2[kz];
+      for (int k0 = 0; k0 < CF::WZ; k0 += 4) {   // psi2 in chunks of 4: few live registers
+        T q[4];
+        PsiLoad<T>::load4(p2 + k0, q);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          if (k0 + kk < CF::WZ) {
+            ar[0][k0 + kk] += a0 * q[kk];
+            ai[0][k0 + kk] += b0 * q[kk];
+            ar[1][k0 + kk] += a1 * q[kk];
+            ai[1][k0 + kk] += b1 * q[kk];
+          }
+        }
       }
     }
-    bar_arrive(BAR_EMPTY(s), CF::THREADS);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[s]);
   }
   if (cur >= 0) NFFTCU_RETIRE(CF::WZ)
 #undef NFFTCU_RETIRE
@@ -432,35 +490,13 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
 
 // ---- interpolation -----------------------------------------------------------------------------------
 template <typename T, int W>
-__global__ void __launch_bounds__(Cfg<W>::THREADS, Cfg<W>::MINB)
-interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__restrict__ xt,
+__global__ void __launch_bounds__(kCtaThreads, 1)
+interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__restrict__ rec,
                    typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
-                   const T *__restrict__ table, const double *__restrict__ poly, int polyN,
                    TileParams P) {
-  typedef Cfg<W> CF;
-  typedef typename Cplx<T>::type C;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const TileRange R(bin_start, P);
-  if (R.k0 == R.k1) return;
-  const Smem<T, W, false> S(smem_raw, polyN);
-  for (int i = threadIdx.x; i < polyN; i += CF::THREADS) S.poly[i] = poly[i];
-  __syncthreads();
-
-  if (threadIdx.x >= CF::CT) {
-    producer_warp<T, W, false>(S, R, P, xt, ft, table);
-    return;
-  }
-
-  // ---- consumers ----
-  const int r0 = threadIdx.x, r1 = threadIdx.x + CF::CT;
-  const bool v1 = r1 < CF::ROWS;
-  const int l0a = r0 / CF::F1, l1a = r0 - l0a * CF::F1;
-  const int l0b = v1 ? r1 / CF::F1 : 0, l1b = v1 ? r1 - l0b * CF::F1 : 0;
-  const C *const Ga = G + ((long long) wrap_fast((long long) R.a * CF::T0 + l0a, P.n0) * P.n1 +
-                           wrap_fast((long long) R.b * CF::T1 + l1a, P.n1)) * P.n2;
-  const C *const Gb = G + ((long long) wrap_fast((long long) R.a * CF::T0 + l0b, P.n0) * P.n1 +
-                           wrap_fast((long long) R.b * CF::T1 + l1b, P.n1)) * P.n2;
-  const int n2 = P.n2;
+  NFFTCU_PENCIL_PROLOGUE(false)
+  const C *const Ga = G + offa;
+  const C *const Gb = G + offb;
 
   T wr[2][CF::WZ], wi[2][CF::WZ];
   T nr[2][CF::SZ], ni[2][CF::SZ];   // the SZ cells that enter the window at the next slab
@@ -496,15 +532,14 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
     }                                                                           \
   }
 
-  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
   for (int bb = 0; bb < nbatch; bb++) {
     const int s = bb % CF::STAGES;
-    bar_sync(BAR_FULL(s), CF::THREADS);
-    const int nb = S.nbv[s];
-    const T *pd = S.pads + (size_t) s * CF::NB * CF::PADLEN;
-    C *red = S.red + (size_t) s * CF::NB * CF::CT + threadIdx.x;
-    for (int i = 0; i < nb; i++, pd += CF::PADLEN, red += CF::CT) {
-      const int sl = S.slab[s * CF::NB + i];
+    const int nb = (int) min((long long) CF::NB, R.k1 - R.k0 - (long long) bb * CF::NB);
+    mbar_wait(&S.full[s], (bb / CF::STAGES) & 1);
+    const T *pd = S.stage + (size_t) s * CF::NB * CF::REC;
+    C *red = S.red + (size_t) s * CF::NB * CF::CT + tid;
+    for (int i = 0; i < nb; i++, pd += CF::REC, red += CF::CT) {
+      const int sl = (int) pd[CF::PADLEN];
       if (sl != cur) {
         if (cur < 0) { cur = sl; NFFTCU_FILL_ALL() NFFTCU_PREFETCH() }
         while (cur < sl) {
@@ -520,20 +555,26 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
       }
       const T w0 = pd[l0a] * pd[CF::F0 + l1a];
       const T w1 = v1 ? pd[l0b] * pd[CF::F0 + l1b] : (T) 0;
-      T p2[CF::WZ];
-      PsiLoad<T>::load(pd + CF::F0 + CF::F1, p2);
+      const T *p2 = pd + CF::F0 + CF::F1;
       T t0r = (T) 0, t0i = (T) 0, t1r = (T) 0, t1i = (T) 0;
 #pragma unroll
-      for (int kz = 0; kz < CF::WZ; kz++) {
-        t0r += p2[kz] * wr[0][kz];
-        t0i += p2[kz] * wi[0][kz];
-        t1r += p2[kz] * wr[1][kz];
-        t1i += p2[kz] * wi[1][kz];
+      for (int k0 = 0; k0 < CF::WZ; k0 += 4) {
+        T q[4];
+        PsiLoad<T>::load4(p2 + k0, q);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          if (k0 + kk < CF::WZ) {
+            t0r += q[kk] * wr[0][k0 + kk];
+            t0i += q[kk] * wi[0][k0 + kk];
+            t1r += q[kk] * wr[1][k0 + kk];
+            t1i += q[kk] * wi[1][k0 + kk];
+          }
+        }
       }
       *red = make_c<T>(w0 * t0r + w1 * t1r, w0 * t0i + w1 * t1i);
     }
-    __threadfence_block();
-    bar_arrive(BAR_EMPTY(s), CF::THREADS);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[s]);
   }
 #undef NFFTCU_FILL_ALL
 #undef NFFTCU_PREFETCH
@@ -563,19 +604,56 @@ TileParams make_params(const nfftcu_ctx *c) {
 }
 
 template <typename T, int W>
+size_t record_bytes(long long M) { return sizeof(T) * (size_t) Cfg<T, W>::REC * (size_t) M; }
+
+// make sure the node records exist and are current: window part once per node set when cached
+// (NFFTCU_OPT_PSI_TABLE), else on every transform; samples on every spreading call
+template <typename T, int W>
+int prepare_records(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
+  typedef typename Cplx<T>::type C;
+  const size_t bytes = record_bytes<T, W>(c->M);
+  if (!c->tile_psi) {
+    NFFTCU_CUDA(cudaMalloc(&c->tile_psi, bytes));
+    NFFTCU_CUDA(cudaMemsetAsync(c->tile_psi, 0, bytes, c->stream));
+    c->tile_psi_valid = false;
+  }
+  const int kb = 256;
+  const bool cached = c->opt_psi_table && c->tile_psi_valid;
+  if (!cached) {
+    long long blocks = ((c->M + kNB - 1) / kNB + 7) / 8;
+    const long long cap = (long long) c->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (f_dev)
+      expand_nodes_kernel<T, W, true><<<(unsigned) blocks, 256, 0, c->stream>>>(
+          (T *) c->tile_psi, (const T *) c->tile_x, (const C *) f_dev, c->tile_perm,
+          (const double *) c->kbpoly_dev, c->M, P);
+    else
+      expand_nodes_kernel<T, W, false><<<(unsigned) blocks, 256, 0, c->stream>>>(
+          (T *) c->tile_psi, (const T *) c->tile_x, nullptr, c->tile_perm,
+          (const double *) c->kbpoly_dev, c->M, P);
+    c->tile_psi_valid = true;
+    c->launches++;
+  } else if (f_dev) {
+    refresh_f_kernel<T, W><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+        (T *) c->tile_psi, (const C *) f_dev, c->tile_perm, c->M);
+    c->launches++;
+  }
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+template <typename T, int W>
 int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
-  const int kb = 256;
-  gather_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
-      (const C *) f_dev, c->tile_perm, (C *) c->f_tile, c->M);
-  const int polyN = (c->tile_psi || P.deg < 0) ? 0 : 3 * (P.deg + 1) * W;
-  const size_t smem = Smem<T, W, true>::bytes(polyN);
-  NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
-  spread_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, smem, c->stream>>>(
-      (C *) c->grid, (const T *) c->tile_x, (C *) c->f_tile, c->bin_start,
-      (const T *) c->tile_psi, (const double *) c->kbpoly_dev, polyN, P);
-  c->launches += 2;
+  typedef Cfg<T, W> CF;
+  NFFTCU_TRY((prepare_records<T, W>(c, f_dev, P)));
+  const size_t smem = Smem<T, W, true>::bytes() * CF::GROUPS;
+  NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const unsigned grid = (unsigned) (((long long) P.NT0 * P.NT1 * P.zseg + CF::GROUPS - 1) / CF::GROUPS);
+  spread_tile_kernel<T, W><<<grid, kCtaThreads, smem, c->stream>>>(
+      (C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
+  c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
 }
@@ -583,13 +661,13 @@ int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
 template <typename T, int W>
 int launch_interp(nfftcu_ctx *c, void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
-  const int polyN = (c->tile_psi || P.deg < 0) ? 0 : 3 * (P.deg + 1) * W;
-  const size_t smem = Smem<T, W, false>::bytes(polyN);
-  NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
-  interp_tile_kernel<T, W><<<grid, Cfg<W>::THREADS, smem, c->stream>>>(
-      (const C *) c->grid, (const T *) c->tile_x, (C *) c->f_tile, c->bin_start,
-      (const T *) c->tile_psi, (const double *) c->kbpoly_dev, polyN, P);
+  typedef Cfg<T, W> CF;
+  NFFTCU_TRY((prepare_records<T, W>(c, nullptr, P)));
+  const size_t smem = Smem<T, W, false>::bytes() * CF::GROUPS;
+  NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const unsigned grid = (unsigned) (((long long) P.NT0 * P.NT1 * P.zseg + CF::GROUPS - 1) / CF::GROUPS);
+  interp_tile_kernel<T, W><<<grid, kCtaThreads, smem, c->stream>>>(
+      (const C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
   const int kb = 256;
   scatter_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
       (const C *) c->f_tile, c->tile_perm, (C *) f_dev, c->M);
@@ -615,26 +693,8 @@ int dispatch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
     default: break;
   }
 #undef NFFTCU_TILE_CASE
-  set_error("tile3d: unsupported window cut-off m=%lld", (long long) c->m);
+  set_error("pencil3d: unsupported window cut-off m=%lld", (long long) c->m);
   return NFFTCU_EINVAL;
-}
-
-template <typename T>
-__global__ void tile_psi_kernel(const T *__restrict__ xt, T *__restrict__ table, long long M,
-                                TileParams P) {
-  const int W = 2 * P.m + 2;
-  const long long total = M * 3 * W;
-  const long long stride = (long long) gridDim.x * blockDim.x;
-  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long k = i / (3 * W);
-    const int r = (int) (i - k * 3 * W);
-    const int t = r / W, l = r - t * W;
-    const T x = xt[k * 3 + t];
-    const int n = (t == 0) ? P.n0 : (t == 1) ? P.n1 : P.n2;
-    const double bb = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
-    const long long uu = cell_of(x, n) - P.m;
-    table[i] = (T) kb_phi((double) x * (double) n - (double) (uu + l), P.m2, bb);
-  }
 }
 
 }  // namespace
@@ -643,14 +703,15 @@ bool tile3d_supported(const nfftcu_ctx *c) {
   if (c->d != 3 || c->direct_only) return false;
   if (c->m < 2 || c->m > 8) return false;
   for (int t = 0; t < 3; t++)
-    if (c->n[t] > 0x3fffffff) return false;
+    if (c->n[t] > 0x3fffff) return false;   // slab index is carried as a float in fp32 records
   return true;
 }
 
-// tile-binned processing order: keys, stable sort, node gather, bin offsets, optional psi table
+// tile-binned processing order: keys, stable sort, node gather, bin offsets
 int tile3d_bin_nodes(nfftcu_ctx *c) {
   const long long M = c->M;
   c->tile_ready = false;
+  c->tile_psi_valid = false;
   if (M == 0) return NFFTCU_OK;
   const TileParams P = make_params(c);
   const long long nbins = (long long) P.NT0 * P.NT1 * P.NS;
@@ -679,19 +740,6 @@ int tile3d_bin_nodes(nfftcu_ctx *c) {
   bin_bounds_kernel<<<(unsigned) ((nbins + 1 + kb - 1) / kb), kb, 0, c->stream>>>(
       (const uint64_t *) c->tile_keys, c->bin_start, nbins, M);
   c->launches++;
-  if (c->opt_psi_table) {
-    const size_t bytes = real_size(c) * (size_t) M * 3 * (2 * (size_t) c->m + 2);
-    if (!c->tile_psi) NFFTCU_CUDA(cudaMalloc(&c->tile_psi, bytes));
-    long long blocks = (M * 3 * (2 * c->m + 2) + kb - 1) / kb;
-    if (blocks > (long long) c->sm_count * 16) blocks = (long long) c->sm_count * 16;
-    if (c->prec == NFFTCU_DOUBLE)
-      tile_psi_kernel<double><<<(unsigned) blocks, kb, 0, c->stream>>>((const double *) c->tile_x,
-                                                                      (double *) c->tile_psi, M, P);
-    else
-      tile_psi_kernel<float><<<(unsigned) blocks, kb, 0, c->stream>>>((const float *) c->tile_x,
-                                                                     (float *) c->tile_psi, M, P);
-    c->launches++;
-  }
   NFFTCU_CUDA(cudaGetLastError());
   c->tile_ready = true;
   return NFFTCU_OK;

@@ -402,6 +402,8 @@ def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
     f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
     want_f = o.trafo(N, n, m, x, fh)
     want_fh = o.adjoint(N, n, m, x, f)
+    if not (np.all(np.isfinite(want_f)) and np.all(np.isfinite(want_fh))):
+        pytest.skip("psi0*psi1*psi2 overflows single precision at this m (in the reference too)")
     outs = {}
     for label, kernel, table in (("tile", 0, 0), ("tile+table", 0, 1), ("generic", 1, 0), ("generic+table", 1, 1)):
         eng = cabi.Engine(N, n, m, M, precision=precision)
