@@ -35,14 +35,15 @@
 //          [ psi0 padded to F0 | psi1 padded to F1 | psi2 padded to WZP | slab | f.re | f.im ]
 //      HBM-bound (REC*sizeof(T) = 416 B per node in fp64) and trivially parallel.  With the PRE_PSI
 //      analogue (NFFTCU_OPT_PSI_TABLE) the records are kept across transforms and only f is refreshed.
-//  (2) the pencil kernel.  A CTA is three warpgroups: two consumer warpgroups and one producer
-//      warpgroup, compiled at 168 registers and rebalanced with setmaxnreg (consumers 232, producers
-//      40; the register file is handed out in units of 4 warps, profiles/r01h shows what the
-//      168-register cap costs).  A producer warp feeds its group's ring of STAGES shared-memory
-//      stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of NB records at a time; the
-//      consumers wait on the stage's "full" mbarrier, run the node loop out of shared memory and
-//      registers only, and release the stage through its "empty" mbarrier.  The consumers never wait
-//      on global memory except for the window refill of interpolation, which is prefetched.
+//  (2) the pencil kernel.  A CTA is one group of consumer warps (128 threads for m <= 6: two CTAs per
+//      SM at 255 registers per thread -- the 2 x WZ complex windows alone are 120; the register file is
+//      handed out in units of 4 warps, so adding a producer warp to the CTA would cap every thread at
+//      168 registers and spill the windows, profiles/r01h..r01q).  Thread 0 doubles as the TMA issuer:
+//      it keeps a ring of STAGES shared-memory stages filled with bulk copies (cp.async.bulk + mbarrier
+//      complete_tx) of NB records at a time, up to STAGES-1 batches ahead.  The consumers wait on the stage's
+//      "full" mbarrier, run the node loop out of shared memory and registers only, and release the
+//      stage through its "empty" mbarrier; they never wait on global memory except for the window
+//      refill of interpolation, which is prefetched one slab ahead.
 #include "common.cuh"
 
 namespace nfftcu {
@@ -50,8 +51,6 @@ namespace nfftcu {
 namespace {
 
 constexpr int kT0 = 3, kT1 = 3, kSZ = 2, kNB = 8, kStages = 4;
-constexpr int kCtaThreads = 384;   // two consumer warpgroups + one producer warpgroup
-constexpr int kConsumerRegs = 232, kProducerRegs = 40;   // 128*(232+232+40) = 64512 <= 65536
 
 template <typename T, int W_>
 struct Cfg {
@@ -64,14 +63,10 @@ struct Cfg {
   static constexpr int REC = ((PADLEN + 3 + RALIGN - 1) / RALIGN) * RALIGN;   // record length in T
   static constexpr int CT = ((((ROWS + 1) / 2) + 31) / 32) * 32;   // consumer threads of a group
   static constexpr int NWARPS = CT / 32;
-  // W <= 14: each consumer warpgroup is its own group (own tile, own producer warp, own ring);
-  // W >= 16: the two consumer warpgroups form one group of CT = 224 consumers.
-  static constexpr int GROUPS = CT <= 128 ? 2 : 1;
-  static constexpr int CTP = 256 / GROUPS;                         // consumer thread slots per group
+  static constexpr int MINB = CT <= 128 ? 2 : 1;                   // CTAs per SM the register budget is sized for
   static constexpr int RETIRE_ALL = (WZ + SZ - 1) / SZ;   // slabs after which the whole window has left
   static constexpr int VMAX = F0 > WZP ? (F0 > F1 ? F0 : F1) : (WZP > F1 ? WZP : F1);
   static constexpr int LPI = VMAX <= 16 ? 16 : 32, IPP = 32 / LPI;   // lanes per item, items per pass
-  static_assert(CT <= 256, "footprint does not fit two consumer warpgroups");
   static_assert(NB * 4 == 32, "expand: 3 coordinate lanes + 1 sample lane per node");
   static_assert(VMAX <= 32, "padded vectors longer than a warp");
 };
@@ -123,6 +118,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// producer-side wait: the producer runs STAGES batches ahead and mostly waits; sleep between polls so
+// that the polling loop does not take issue slots from the consumer warps of its scheduler
+// (profiles/r01p: the bare try_wait loop was 25% of all executed instructions)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, int parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -257,14 +268,14 @@ template <typename T, int W, bool SPREAD>
 struct Smem {
   typedef Cfg<T, W> CF;
   typedef typename Cplx<T>::type C;
-  C *red;          // [STAGES][NB][CT]   interpolation partial sums
+  C *red;          // [2][NB][CT]        interpolation partial sums (double-buffered across batches)
   T *stage;        // [STAGES][NB*REC]   node records
   uint64_t *full;  // [STAGES]
   uint64_t *empty; // [STAGES]
 
   __host__ __device__ static size_t bytes() {
     size_t b = 0;
-    if (!SPREAD) b += sizeof(C) * CF::STAGES * CF::NB * CF::CT;
+    if (!SPREAD) b += sizeof(C) * 2 * CF::NB * CF::CT;
     b += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
     b += sizeof(uint64_t) * 2 * CF::STAGES;
     return (b + 127) & ~(size_t) 127;
@@ -272,7 +283,7 @@ struct Smem {
   __device__ __forceinline__ Smem(unsigned char *base) {
     size_t o = 0;
     red = reinterpret_cast<C *>(base);
-    if (!SPREAD) o += sizeof(C) * CF::STAGES * CF::NB * CF::CT;
+    if (!SPREAD) o += sizeof(C) * 2 * CF::NB * CF::CT;
     stage = reinterpret_cast<T *>(base + o);
     o += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
     full = reinterpret_cast<uint64_t *>(base + o);
@@ -297,60 +308,17 @@ struct TileRange {
   }
 };
 
-// producer warp of a group: TMA-feeds the ring; for interpolation it also turns the consumers' partial
-// sums of a released stage into ft[k]
+// thread 0: bulk-copy the records of batch bb into its ring stage (arms the stage's full barrier)
 template <typename T, int W, bool SPREAD>
-__device__ __forceinline__ void producer_warp(const Smem<T, W, SPREAD> &S, const TileRange &R,
-                                              const T *__restrict__ rec,
-                                              typename Cplx<T>::type *__restrict__ ft) {
+__device__ __forceinline__ void tma_fill(const Smem<T, W, SPREAD> &S, const TileRange &R,
+                                         const T *__restrict__ rec, int bb) {
   typedef Cfg<T, W> CF;
-  typedef typename Cplx<T>::type C;
-  const int lane = threadIdx.x & 31;
-  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
-
-  auto reduce_stage = [&](int bb) {
-    const int s = bb % CF::STAGES;
-    const long long kb = R.k0 + (long long) bb * CF::NB;
-    const int nb = (int) min((long long) CF::NB, R.k1 - kb);
-    const C *red = S.red + (size_t) s * CF::NB * CF::CT;
-    for (int i = 0; i < nb; i++) {
-      T sr = (T) 0, si = (T) 0;
-#pragma unroll
-      for (int q = 0; q < CF::NWARPS; q++) {
-        const C v = red[i * CF::CT + lane + 32 * q];
-        sr += v.x;
-        si += v.y;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        si += __shfl_xor_sync(0xffffffffu, si, o);
-      }
-      if (lane == 0) ft[kb + i] = make_c<T>(sr, si);
-    }
-  };
-
-  for (int bb = 0; bb < nbatch; bb++) {
-    const int s = bb % CF::STAGES, r = bb / CF::STAGES;
-    if (bb >= CF::STAGES) {
-      mbar_wait(&S.empty[s], (r - 1) & 1);      // consumers released what was in this stage
-      if (!SPREAD) reduce_stage(bb - CF::STAGES);
-      __syncwarp();
-    }
-    if (lane == 0) {
-      const long long kb = R.k0 + (long long) bb * CF::NB;
-      const int nb = (int) min((long long) CF::NB, R.k1 - kb);
-      const uint32_t bytes = (uint32_t) (nb * CF::REC * sizeof(T));
-      mbar_expect_tx(&S.full[s], bytes);
-      bulk_g2s(S.stage + (size_t) s * CF::NB * CF::REC, rec + kb * CF::REC, bytes, &S.full[s]);
-    }
-  }
-  if (!SPREAD) {
-    for (int bb = max(0, nbatch - CF::STAGES); bb < nbatch; bb++) {
-      mbar_wait(&S.empty[bb % CF::STAGES], (bb / CF::STAGES) & 1);
-      reduce_stage(bb);
-    }
-  }
+  const int s = bb % CF::STAGES;
+  const long long kb = R.k0 + (long long) bb * CF::NB;
+  const int nb = (int) min((long long) CF::NB, R.k1 - kb);
+  const uint32_t bytes = (uint32_t) (nb * CF::REC * sizeof(T));
+  mbar_expect_tx(&S.full[s], bytes);
+  bulk_g2s(S.stage + (size_t) s * CF::NB * CF::REC, rec + kb * CF::REC, bytes, &S.full[s]);
 }
 
 // four consecutive psi2 values with vector loads (the psi2 segment of a record starts 16-byte aligned
@@ -369,32 +337,23 @@ template <> struct PsiLoad<float> {
   }
 };
 
-// common prologue: roles, work unit, barriers.  Returns false for threads that have nothing to do.
+// common prologue: work unit, barriers, first fills, row ownership
 #define NFFTCU_PENCIL_PROLOGUE(SPREADV)                                                              \
   typedef Cfg<T, W> CF;                                                                              \
   typedef typename Cplx<T>::type C;                                                                  \
   extern __shared__ __align__(128) unsigned char smem_raw[];                                         \
-  const bool is_producer = threadIdx.x >= 256;                                                       \
-  const int g = is_producer ? (threadIdx.x - 256) / 32 : threadIdx.x / CF::CTP;                      \
-  const int tid = is_producer ? CF::CT + (threadIdx.x & 31) : threadIdx.x - g * CF::CTP;             \
-  const int gs = min(g, CF::GROUPS - 1);                                                             \
+  const int tid = threadIdx.x, lane = threadIdx.x & 31;                                              \
   const long long units = (long long) P.NT0 * P.NT1 * P.zseg;                                        \
-  const TileRange R(bin_start, P, (long long) blockIdx.x * CF::GROUPS + gs, units);                  \
-  const Smem<T, W, SPREADV> S(smem_raw + (size_t) gs * Smem<T, W, SPREADV>::bytes());                \
-  if (threadIdx.x < CF::GROUPS) {                                                                    \
-    const Smem<T, W, SPREADV> Sg(smem_raw + (size_t) threadIdx.x * Smem<T, W, SPREADV>::bytes());    \
-    for (int s = 0; s < CF::STAGES; s++) { mbar_init(&Sg.full[s], 1); mbar_init(&Sg.empty[s], CF::NWARPS); } \
+  const TileRange R(bin_start, P, (long long) blockIdx.x, units);                                    \
+  if (R.k0 == R.k1) return;                                                                          \
+  const Smem<T, W, SPREADV> S(smem_raw);                                                             \
+  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);                                    \
+  if (tid == 0) {                                                                                    \
+    for (int s = 0; s < CF::STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CF::NWARPS); } \
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                               \
+    for (int bb = 0; bb < CF::STAGES && bb < nbatch; bb++) tma_fill<T, W, SPREADV>(S, R, rec, bb);   \
   }                                                                                                  \
   __syncthreads();                                                                                   \
-  if (is_producer) {                                                                                 \
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));                        \
-    if (g < CF::GROUPS && R.k0 != R.k1) producer_warp<T, W, SPREADV>(S, R, rec, ft);                 \
-    return;                                                                                          \
-  }                                                                                                  \
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));                          \
-  if (tid >= CF::CT || R.k0 == R.k1) return;                                                         \
-  const int lane = tid & 31;                                                                         \
   const int r0 = tid, r1 = tid + CF::CT;                                                             \
   const bool v1 = r1 < CF::ROWS;                                                                     \
   const int l0a = r0 / CF::F1, l1a = r0 - l0a * CF::F1;                                              \
@@ -403,12 +362,19 @@ template <> struct PsiLoad<float> {
                           wrap_fast((long long) R.b * CF::T1 + l1a, P.n1)) * P.n2;                   \
   const long long offb = ((long long) wrap_fast((long long) R.a * CF::T0 + l0b, P.n0) * P.n1 +       \
                           wrap_fast((long long) R.b * CF::T1 + l1b, P.n1)) * P.n2;                   \
-  const int n2 = P.n2;                                                                               \
-  const int nbatch = (int) ((R.k1 - R.k0 + CF::NB - 1) / CF::NB);
+  const int n2 = P.n2;
+
+// thread 0, once per batch: refill the stage that batch bb-1 occupied (all warps have released it, or
+// are about to) with batch bb-1+STAGES
+#define NFFTCU_REFILL(SPREADV)                                                                       \
+  if (tid == 0 && bb >= 1 && bb - 1 + CF::STAGES < nbatch) {                                         \
+    mbar_wait(&S.empty[(bb - 1) % CF::STAGES], ((bb - 1) / CF::STAGES) & 1);                         \
+    tma_fill<T, W, SPREADV>(S, R, rec, bb - 1 + CF::STAGES);                                         \
+  }
 
 // ---- spreading ---------------------------------------------------------------------------------------
 template <typename T, int W>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(Cfg<T, W>::CT, Cfg<T, W>::MINB)
 spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__ rec,
                    typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
                    TileParams P) {
@@ -445,6 +411,7 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
   for (int bb = 0; bb < nbatch; bb++) {
     const int s = bb % CF::STAGES;
     const int nb = (int) min((long long) CF::NB, R.k1 - R.k0 - (long long) bb * CF::NB);
+    NFFTCU_REFILL(true)
     mbar_wait(&S.full[s], (bb / CF::STAGES) & 1);
     const T *pd = S.stage + (size_t) s * CF::NB * CF::REC;
     for (int i = 0; i < nb; i++, pd += CF::REC) {
@@ -490,7 +457,7 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
 
 // ---- interpolation -----------------------------------------------------------------------------------
 template <typename T, int W>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+__global__ void __launch_bounds__(Cfg<T, W>::CT, Cfg<T, W>::MINB)
 interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__restrict__ rec,
                    typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
                    TileParams P) {
@@ -535,9 +502,11 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
   for (int bb = 0; bb < nbatch; bb++) {
     const int s = bb % CF::STAGES;
     const int nb = (int) min((long long) CF::NB, R.k1 - R.k0 - (long long) bb * CF::NB);
+    NFFTCU_REFILL(false)
     mbar_wait(&S.full[s], (bb / CF::STAGES) & 1);
     const T *pd = S.stage + (size_t) s * CF::NB * CF::REC;
-    C *red = S.red + (size_t) s * CF::NB * CF::CT + tid;
+    C *const redb = S.red + (size_t) (bb & 1) * CF::NB * CF::CT;
+    C *red = redb + tid;
     for (int i = 0; i < nb; i++, pd += CF::REC, red += CF::CT) {
       const int sl = (int) pd[CF::PADLEN];
       if (sl != cur) {
@@ -574,7 +543,26 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
       *red = make_c<T>(w0 * t0r + w1 * t1r, w0 * t0i + w1 * t1i);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty[s]);
+    if (lane == 0) mbar_arrive(&S.empty[s]);          // the stage's records are no longer needed
+    // CTA-wide reduction of the batch's partial sums: after the barrier every warp sums the CT partials
+    // of its share of the nodes.  red is double-buffered over batches; a warp can be at most one batch
+    // ahead of the slowest one because of this barrier.
+    __syncthreads();
+    for (int i = tid >> 5; i < nb; i += CF::NWARPS) {
+      T sr = (T) 0, si = (T) 0;
+#pragma unroll
+      for (int q = 0; q < CF::NWARPS; q++) {
+        const C v = redb[i * CF::CT + lane + 32 * q];
+        sr += v.x;
+        si += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (lane == 0) ft[R.k0 + (long long) bb * CF::NB + i] = make_c<T>(sr, si);
+    }
   }
 #undef NFFTCU_FILL_ALL
 #undef NFFTCU_PREFETCH
@@ -648,10 +636,10 @@ int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
   typedef Cfg<T, W> CF;
   NFFTCU_TRY((prepare_records<T, W>(c, f_dev, P)));
-  const size_t smem = Smem<T, W, true>::bytes() * CF::GROUPS;
+  const size_t smem = Smem<T, W, true>::bytes();
   NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  const unsigned grid = (unsigned) (((long long) P.NT0 * P.NT1 * P.zseg + CF::GROUPS - 1) / CF::GROUPS);
-  spread_tile_kernel<T, W><<<grid, kCtaThreads, smem, c->stream>>>(
+  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  spread_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
@@ -663,10 +651,10 @@ int launch_interp(nfftcu_ctx *c, void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
   typedef Cfg<T, W> CF;
   NFFTCU_TRY((prepare_records<T, W>(c, nullptr, P)));
-  const size_t smem = Smem<T, W, false>::bytes() * CF::GROUPS;
+  const size_t smem = Smem<T, W, false>::bytes();
   NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  const unsigned grid = (unsigned) (((long long) P.NT0 * P.NT1 * P.zseg + CF::GROUPS - 1) / CF::GROUPS);
-  interp_tile_kernel<T, W><<<grid, kCtaThreads, smem, c->stream>>>(
+  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  interp_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (const C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
   const int kb = 256;
   scatter_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
