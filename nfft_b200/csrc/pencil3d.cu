@@ -269,6 +269,8 @@ struct Smem {
   typedef Cfg<T, W> CF;
   typedef typename Cplx<T>::type C;
   C *red;          // [2][NB][CT]        interpolation partial sums (double-buffered across batches)
+  C *stg;          // [2*CT][8]          spreading: retired cells staged per row, flushed as 128-byte runs
+  long long *rowoff; // [2*CT]           spreading: grid offset of every footprint row
   T *stage;        // [STAGES][NB*REC]   node records
   uint64_t *full;  // [STAGES]
   uint64_t *empty; // [STAGES]
@@ -276,6 +278,7 @@ struct Smem {
   __host__ __device__ static size_t bytes() {
     size_t b = 0;
     if (!SPREAD) b += sizeof(C) * 2 * CF::NB * CF::CT;
+    else b += sizeof(C) * 2 * CF::CT * 8 + sizeof(long long) * 2 * CF::CT;
     b += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
     b += sizeof(uint64_t) * 2 * CF::STAGES;
     return (b + 127) & ~(size_t) 127;
@@ -283,7 +286,10 @@ struct Smem {
   __device__ __forceinline__ Smem(unsigned char *base) {
     size_t o = 0;
     red = reinterpret_cast<C *>(base);
+    stg = reinterpret_cast<C *>(base);
+    rowoff = reinterpret_cast<long long *>(base + sizeof(C) * 2 * CF::CT * 8);
     if (!SPREAD) o += sizeof(C) * 2 * CF::NB * CF::CT;
+    else o += sizeof(C) * 2 * CF::CT * 8 + sizeof(long long) * 2 * CF::CT;
     stage = reinterpret_cast<T *>(base + o);
     o += sizeof(T) * CF::STAGES * CF::NB * CF::REC;
     full = reinterpret_cast<uint64_t *>(base + o);
@@ -379,9 +385,7 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
                    typename Cplx<T>::type *__restrict__ ft, const uint32_t *__restrict__ bin_start,
                    TileParams P) {
   NFFTCU_PENCIL_PROLOGUE(true)
-  T *const Ga = reinterpret_cast<T *>(G) + 2 * offa;
-  T *const Gb = reinterpret_cast<T *>(G) + 2 * offb;
-
+  (void) offa; (void) offb;
   T ar[2][CF::WZ], ai[2][CF::WZ];
 #pragma unroll
   for (int j = 0; j < 2; j++)
@@ -389,17 +393,51 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
     for (int kz = 0; kz < CF::WZ; kz++) { ar[j][kz] = (T) 0; ai[j][kz] = (T) 0; }
   int cur = -1;   // slab the window is aligned to: it covers z = cur*SZ .. cur*SZ+WZ-1 (mod n2)
 
+  // Retired cells are not sent to the grid one by one (a warp's rows are 4 KB apart: 32 different
+  // lines per RED instruction, and L2 resolves scattered reductions at ~60-100 G/s, which bounded
+  // the kernel at ~10 ms, profiles/r01u).  They are staged per row in shared memory, 8 cells = 128 bytes
+  // per row, and every warp flushes the finished 8-cell blocks of ITS OWN rows as contiguous runs:
+  // 16 lanes cover one 128-byte line.  Untouched cells of a block are zero, so partial blocks
+  // (start, end, jumps, wrap-around) are flushed the same way.
+  const int warp = tid >> 5;
+  for (int r = tid; r < 2 * CF::CT; r += CF::CT) {
+    const int l0 = r / CF::F1, l1 = r - l0 * CF::F1;
+    S.rowoff[r] = r < CF::ROWS ? ((long long) wrap_fast((long long) R.a * CF::T0 + l0, P.n0) * P.n1 +
+                                  wrap_fast((long long) R.b * CF::T1 + l1, P.n1)) * P.n2 : -1;
+#pragma unroll
+    for (int q = 0; q < 8; q++) S.stg[r * 8 + q] = make_c<T>((T) 0, (T) 0);
+  }
+  __syncwarp();   // a warp only ever touches the staging rows it owns: rows tid and tid+CT of its lanes
+  int pend = -1;  // 8-cell block (index z/8) with staged, unflushed cells
+  T *const Gr = reinterpret_cast<T *>(G);
+  auto flush_block = [&](int blk) {
+    __syncwarp();
+    const int zb8 = blk * 8;
+    const int cell = (lane & 15) >> 1, comp = lane & 1;
+#pragma unroll 4
+    for (int it = 0; it < 32; it++) {
+      const int rr = 2 * it + (lane >> 4);
+      const int row = (rr < 32) ? warp * 32 + rr : CF::CT + warp * 32 + (rr - 32);
+      const long long off = S.rowoff[row];
+      T *slot = reinterpret_cast<T *>(S.stg + row * 8 + cell) + comp;
+      const T v = *slot;
+      if (off >= 0 && zb8 + cell < n2) red_add(Gr + 2 * (off + zb8 + cell) + comp, v);
+      *slot = (T) 0;
+    }
+    __syncwarp();
+  };
+
 #define NFFTCU_RETIRE(CNT)                                                                   \
   {                                                                                          \
     const int zb = cur * CF::SZ;                                                             \
     _Pragma("unroll") for (int kz = 0; kz < (CNT); kz++) {                                   \
       const int z = wrap_z(zb + kz, n2);                                                     \
-      red_add(Ga + 2 * z, ar[0][kz]);                                                        \
-      red_add(Ga + 2 * z + 1, ai[0][kz]);                                                    \
-      if (v1) {                                                                              \
-        red_add(Gb + 2 * z, ar[1][kz]);                                                      \
-        red_add(Gb + 2 * z + 1, ai[1][kz]);                                                  \
+      if ((z >> 3) != pend) {                                                                \
+        if (pend >= 0) flush_block(pend);                                                    \
+        pend = z >> 3;                                                                       \
       }                                                                                      \
+      S.stg[r0 * 8 + (z & 7)] = make_c<T>(ar[0][kz], ai[0][kz]);                             \
+      S.stg[r1 * 8 + (z & 7)] = make_c<T>(ar[1][kz], ai[1][kz]);                             \
     }                                                                                        \
     _Pragma("unroll") for (int j = 0; j < 2; j++)                                            \
     _Pragma("unroll") for (int kz = 0; kz < CF::WZ; kz++) {                                  \
@@ -451,7 +489,10 @@ spread_tile_kernel(typename Cplx<T>::type *__restrict__ G, const T *__restrict__
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.empty[s]);
   }
-  if (cur >= 0) NFFTCU_RETIRE(CF::WZ)
+  if (cur >= 0) {
+    NFFTCU_RETIRE(CF::WZ)
+    if (pend >= 0) flush_block(pend);
+  }
 #undef NFFTCU_RETIRE
 }
 
@@ -525,7 +566,9 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
       const T w0 = pd[l0a] * pd[CF::F0 + l1a];
       const T w1 = v1 ? pd[l0b] * pd[CF::F0 + l1b] : (T) 0;
       const T *p2 = pd + CF::F0 + CF::F1;
-      T t0r = (T) 0, t0i = (T) 0, t1r = (T) 0, t1i = (T) 0;
+      // two partial sums per component: 8 independent FMA chains of WZ/2 instead of 4 of WZ
+      // (DFMA latency 8.4 cycles, issue 2.1: profiles/r01u)
+      T t0r[2] = {(T) 0, (T) 0}, t0i[2] = {(T) 0, (T) 0}, t1r[2] = {(T) 0, (T) 0}, t1i[2] = {(T) 0, (T) 0};
 #pragma unroll
       for (int k0 = 0; k0 < CF::WZ; k0 += 4) {
         T q[4];
@@ -533,14 +576,15 @@ interp_tile_kernel(const typename Cplx<T>::type *__restrict__ G, const T *__rest
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
           if (k0 + kk < CF::WZ) {
-            t0r += q[kk] * wr[0][k0 + kk];
-            t0i += q[kk] * wi[0][k0 + kk];
-            t1r += q[kk] * wr[1][k0 + kk];
-            t1i += q[kk] * wi[1][k0 + kk];
+            t0r[kk & 1] += q[kk] * wr[0][k0 + kk];
+            t0i[kk & 1] += q[kk] * wi[0][k0 + kk];
+            t1r[kk & 1] += q[kk] * wr[1][k0 + kk];
+            t1i[kk & 1] += q[kk] * wi[1][k0 + kk];
           }
         }
       }
-      *red = make_c<T>(w0 * t0r + w1 * t1r, w0 * t0i + w1 * t1i);
+      *red = make_c<T>(w0 * (t0r[0] + t0r[1]) + w1 * (t1r[0] + t1r[1]),
+                       w0 * (t0i[0] + t0i[1]) + w1 * (t1i[0] + t1i[1]));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.empty[s]);          // the stage's records are no longer needed
