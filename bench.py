@@ -203,6 +203,10 @@ def run_ours(args, rank, world, local_rank):
     eng.set_option(cabi.OPT_TIMING, 1)
     if args.psi_table:
         eng.set_option(cabi.OPT_PSI_TABLE, 1)
+    if args.b_kernel:
+        eng.set_option(cabi.OPT_B_KERNEL, args.b_kernel)
+    if args.b_flush:
+        eng.set_option(cabi.OPT_B_FLUSH, args.b_flush)
     t0 = time.perf_counter()
     sp.set_nodes_dev(x_d)
     torch.cuda.synchronize()
@@ -345,6 +349,8 @@ def main():
     ap.add_argument("--nodes", type=int, default=0, help="override M per GPU (debug)")
     ap.add_argument("--psi-table", action="store_true", help="per-node window table (PRE_PSI analogue)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--b-kernel", type=int, default=0, help="debug: NFFTCU_OPT_B_KERNEL (1 generic, 2 pencil, 3 DMMA)")
+    ap.add_argument("--b-flush", type=int, default=0, help="debug: NFFTCU_OPT_B_FLUSH (1: RED.ADD instead of TMA reductions)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

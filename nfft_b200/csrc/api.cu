@@ -117,14 +117,18 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
 int nodes_ready(nfftcu_ctx *c) {
   c->ref_sorted = false;
   c->tile_ready = false;
+  c->mma_ready = false;
   if (!c->direct_only) {
-    const bool use_tile = tile3d_supported(c) && c->opt_b_kernel != 1;
+    // B / B^T kernel family: DMMA (mma3d.cu) > register pencils (pencil3d.cu) > generic warp-per-node
+    const bool use_mma = mma3d_supported(c) && (c->opt_b_kernel == 0 || c->opt_b_kernel == 3);
+    const bool use_tile = !use_mma && tile3d_supported(c) && c->opt_b_kernel != 1;
     // the reference-order sort is the index_x witness and the order the generic kernels walk
-    if (!use_tile || (c->flags & (1u << 11))) {   // NFFT_SORT_NODES
+    if (!(use_tile || use_mma) || (c->flags & (1u << 11))) {   // NFFT_SORT_NODES
       NFFTCU_TRY(sort_nodes(c));
       c->ref_sorted = true;
     }
-    if (use_tile) NFFTCU_TRY(tile3d_bin_nodes(c));
+    if (use_mma) NFFTCU_TRY(mma3d_bin_nodes(c));
+    else if (use_tile) NFFTCU_TRY(tile3d_bin_nodes(c));
     else if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
   }
   c->have_nodes = true;
@@ -474,6 +478,7 @@ int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
     case NFFTCU_OPT_PSI_TABLE: c->opt_psi_table = (int) value; break;
     case NFFTCU_OPT_B_KERNEL: c->opt_b_kernel = (int) value; break;
     case NFFTCU_OPT_NODE_ORDER: c->opt_node_order = (int) value; break;
+    case NFFTCU_OPT_B_FLUSH: c->opt_b_flush = (int) value; break;
     default:
       set_error("nfftcu_set_option: unknown option %d", option);
       return NFFTCU_EINVAL;

@@ -76,6 +76,7 @@ struct nfftcu_ctx_s {
   void *psi_table = nullptr;        // optional: M * d * (2m+2) reals in processing order
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;
+  bool mma_ready = false;           // tile_* hold the (tile, u2) order of the DMMA kernels (mma3d.cu)
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index
@@ -87,6 +88,7 @@ struct nfftcu_ctx_s {
   void *f_tile = nullptr;           // M complex: samples in tile order (gathered / to be scattered)
   // piecewise-polynomial window (kbpoly.cu): coef[(t*(deg+1)+k)*W + l]
   int kbpoly_deg = -1;
+  int kbpoly_fit = -1;              // degree the fit needed (<= kbpoly_deg): Horner length of the DMMA kernels
   std::vector<double> kbpoly_host;
   void *kbpoly_dev = nullptr;
   void *sort_tmp = nullptr;         // scratch kept between set_nodes calls
@@ -106,6 +108,7 @@ struct nfftcu_ctx_s {
   int opt_psi_table = 0;
   int opt_b_kernel = 0;
   int opt_node_order = 0;
+  int opt_b_flush = 0;
   int sm_count = 148;
 };
 
@@ -123,6 +126,10 @@ bool tile3d_supported(const nfftcu_ctx *c);                         // tile3d.cu
 int tile3d_bin_nodes(nfftcu_ctx *c);                                // tile3d.cu
 int tile3d_interp(nfftcu_ctx *c, void *f_dev);                      // tile3d.cu
 int tile3d_spread(nfftcu_ctx *c, const void *f_dev);                // tile3d.cu
+bool mma3d_supported(const nfftcu_ctx *c);                          // mma3d.cu
+int mma3d_bin_nodes(nfftcu_ctx *c);                                 // mma3d.cu
+int mma3d_interp(nfftcu_ctx *c, void *f_dev);                       // mma3d.cu
+int mma3d_spread(nfftcu_ctx *c, const void *f_dev);                 // mma3d.cu
 int stage_D(nfftcu_ctx *c, const void *f_hat_dev);                  // deconv.cu
 int stage_DT(nfftcu_ctx *c, void *f_hat_dev);                       // deconv.cu
 int fft_plan_axes(nfftcu_ctx *c);                                   // fft.cu

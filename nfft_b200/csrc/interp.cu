@@ -154,6 +154,7 @@ int run_generic(nfftcu_ctx *c, void *f_dev) {
 
 int stage_B(nfftcu_ctx *c, void *f_dev) {
   if (c->M == 0) return NFFTCU_OK;
+  if (c->mma_ready) return mma3d_interp(c, f_dev);
   if (c->tile_ready && c->opt_b_kernel != 1) return tile3d_interp(c, f_dev);
   if (!c->ref_sorted) {
     set_error("stage_B: generic kernel needs the reference node order (set NFFTCU_OPT_B_KERNEL before set_nodes)");

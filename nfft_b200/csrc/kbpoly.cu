@@ -69,6 +69,7 @@ int build_kb_poly(nfftcu_ctx *c) {
   const int W = 2 * (int) c->m + 2;
   const long double m = (long double) c->m;
   c->kbpoly_deg = -1;
+  c->kbpoly_fit = -1;
   // The device keeps the coefficients of one tap in registers and runs a fixed-length Horner loop, so
   // the table is always stored with kKbPolyDeg+1 coefficients per tap (higher ones zero).
   for (int p = 10; p <= kKbPolyDeg; p++) {
@@ -93,6 +94,7 @@ int build_kb_poly(nfftcu_ctx *c) {
     }
     if (worst < 3e-15L) {
       c->kbpoly_deg = kKbPolyDeg;   // stored (padded) degree; the fitted degree is p
+      c->kbpoly_fit = p;
       c->kbpoly_host = coef;
       break;
     }

@@ -1,0 +1,626 @@
+// mma3d.cu -- 3-D interpolation (B) and spreading (B^T) in fp64 with the window contraction along z
+// issued as FP64 tensor-core instructions (DMMA, mma.sync.m8n8k4.f64): the fast path for d = 3, m <= 6.
+//
+// Reference being replaced: nfft_trafo_3d_B / nfft_trafo_3d_compute (kernel/nfft/nfft.c:4687-4914,
+// 4020-4265) and nfft_adjoint_3d_B with its atomic / blockwise compute variants (5126-5384,
+// 4393-4436, 4289-4388).  Same arithmetic -- f_j = sum psi0 psi1 psi2 g, g += psi0 psi1 psi2 f_j -- in
+// a different summation order.
+//
+// Why DMMA.  The taps of one node are a rank-1 (separable) weight on a (2m+2)^3 box; 2m+2 = 14 gives
+// 5488 FP64 FMAs per node and direction, and the B200 FP64 pipe delivers the same 64 FMA/clk/SM
+// whether it is fed by DFMA or by DMMA (profiles/r01w_microbench_dmma.txt: 36.9 TFLOP/s either way,
+// the two share the pipe).  A DFMA tap loop needs one issue slot and 1/15 of a broadcast shared-memory
+// load per 32 FMAs and ran at 30-44 % of the pipe (profiles/r01u); one DMMA carries 256 FMAs, takes its
+// operands from registers and leaves the LSU and the issue slots almost idle.  The contraction becomes
+// a small GEMM once nodes are processed in BATCHES of 8 that share a grid window:
+//
+//   tile (a,b) = (u0 / T, u1 / T), T = 17 - (2m+2)  => every tap box of the tile lies in a FOOTPRINT of
+//   16 x 16 grid rows (pencils along z);  nodes of a tile are walked in ascending u2 (their lowest tap
+//   in z), 8 at a time, and a batch only takes nodes with u2 in [zlo, zlo+2], zlo even, so that all its
+//   taps fall in the WINDOW z in [zlo, zlo+16).
+//
+//   interpolation   T[row, node] = sum_z G[row, z] * psi2[z, node]     rows = 256 pencils x (re, im)
+//                   f_node       = sum_row psi0[row, node] psi1[row, node] T[row, node]
+//   spreading       G[row, z]   += sum_node (psi0 psi1 f)[row, node] * psi2[node, z]
+//
+// A CTA of 4 warps owns a tile; warp w owns footprint rows l0 = 4w..4w+3, all 16 l1, i.e. 8 groups of
+// 8 pencils x (re, im) = 16 m-tiles.  The window lives in REGISTERS for the whole sweep of the tile along z:
+// as A fragments for interpolation (64 doubles per lane, refilled two cells at a time from L2, one
+// pair prefetched a batch ahead), as C accumulators for spreading (64 doubles per lane, retired two
+// cells at a time).  Window slots are circular (cell z lives in slot z mod 16), so sliding the window
+// moves no registers.  Per batch a warp issues 64 DMMAs (16 m-tiles x 4 k-steps, resp. 16 m-tiles x 2
+// n-tiles x 2 k-steps) = 16384 FMAs for 8 nodes: lane efficiency (14/16)^3 = 67 % of the useful 5488 per node.
+//
+// Window values are evaluated in the kernel from the node coordinates (24 bytes per node instead of a
+// 416-byte record): the piecewise polynomials of kbpoly.cu, one Horner chain per (dimension, slot, node)
+// entry, 3 entries per thread and batch, written zero-padded and already placed (offset in the
+// footprint, circular slot in z) into a double-buffered shared operand block, one __syncthreads per batch.
+//
+// Spreading retires cells through shared memory: a warp stages the retired pairs of ITS rows as
+// 128-byte runs (8 cells) and hands complete runs to the TMA unit as bulk reductions
+// (cp.reduce.async.bulk .add.f64), so that L2 sees line-sized reductions instead of scattered RED.64.
+#include "common.cuh"
+
+namespace nfftcu {
+
+namespace {
+
+constexpr int kNB = 8;        // nodes per batch
+constexpr int kF = 16;        // footprint rows per axis, window slots
+constexpr unsigned kFull = 0xffffffffu;
+
+struct MmaParams {
+  int n0, n1, n2;
+  int T;            // tile edge: 17 - W
+  int NT0, NT1;
+  int zseg;         // work units per tile along z
+  int m;
+  int deg;          // Horner length (fitted polynomial degree)
+};
+
+__device__ __forceinline__ int wrapi(int v, int n) {
+  if (v < 0) v += n;
+  if (v >= n) v -= n;
+  if (v < 0 || v >= n) { v %= n; if (v < 0) v += n; }
+  return v;
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+// ---- binning ---------------------------------------------------------------------------------------------
+__global__ void mma_keys_kernel(const double *__restrict__ x, uint64_t *__restrict__ keys,
+                                uint32_t *__restrict__ vals, long long M, MmaParams P) {
+  const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int u0 = wrapi((int) (cell_of(x[3 * j], P.n0) - P.m), P.n0);
+  const int u1 = wrapi((int) (cell_of(x[3 * j + 1], P.n1) - P.m), P.n1);
+  const int u2 = wrapi((int) (cell_of(x[3 * j + 2], P.n2) - P.m), P.n2);
+  const unsigned long long tile = (unsigned long long) (u0 / P.T) * P.NT1 + (u1 / P.T);
+  keys[j] = tile * P.n2 + u2;
+  vals[j] = (uint32_t) j;
+}
+
+// unit_start[u] = first position whose key >= first key of work unit u, u = 0..units
+__global__ void mma_unit_bounds_kernel(const uint64_t *__restrict__ keys, uint32_t *__restrict__ unit_start,
+                                       long long units, long long M, MmaParams P) {
+  const long long u = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > units) return;
+  const long long tile = u / P.zseg, seg = u - tile * P.zseg;
+  const uint64_t key = (uint64_t) tile * P.n2 + (uint64_t) ((long long) P.n2 * seg / P.zseg);
+  long long lo = 0, hi = M;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (keys[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  unit_start[u] = (uint32_t) lo;
+}
+
+__global__ void mma_gather_f_kernel(const double2 *__restrict__ f, const uint32_t *__restrict__ perm,
+                                    double2 *__restrict__ ft, long long M) {
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < M) ft[k] = f[perm[k]];
+}
+
+// ---- shared operand block -------------------------------------------------------------------------------
+// ops[buf][v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
+// (spreading), 2: psi2 in circular window slots, 3: psi1*f.im (spreading only)
+template <int W, bool SPREAD>
+struct Shared {
+  double ops[2][SPREAD ? 4 : 3][kF][kNB];
+  double red[2][4][2 * kNB];
+  double coef[3 * (kKbPolyDeg + 1) * W];
+  unsigned rowoff[kF * kF];
+};
+
+struct Batch {
+  long long kb;   // first node (tile order)
+  int nb;         // nodes in the batch, 1..8
+  int zlo;        // window base (even, unwrapped = in [0, n2))
+};
+
+// Every thread of the CTA holds the coordinates of node kb + (tid & 7) of the NEXT batch; this evaluates
+// that batch's extent (uniform across the CTA) and the thread's 3 (4) entries of the operand block.
+template <int W, bool SPREAD>
+__device__ __forceinline__ Batch prepare_batch(Shared<W, SPREAD> &S, int buf, long long kb, long long k1,
+                                               const double (&xn)[3], double fr, double fi, int a, int bt,
+                                               const MmaParams &P, int tid) {
+  const int i = tid & 7, q = tid >> 3;
+  const long long c0 = cell_of(xn[0], P.n0), c1 = cell_of(xn[1], P.n1), c2 = cell_of(xn[2], P.n2);
+  const int u0 = wrapi((int) (c0 - P.m), P.n0), u1 = wrapi((int) (c1 - P.m), P.n1);
+  const int u2 = wrapi((int) (c2 - P.m), P.n2);
+  Batch B;
+  B.kb = kb;
+  B.zlo = __shfl_sync(kFull, u2, 0) & ~1;
+  const bool valid = (kb + i < k1) && (u2 <= B.zlo + 2);
+  B.nb = __popc(__ballot_sync(kFull, valid) & 0xffu);   // nodes are sorted by u2: the valid ones are a prefix
+  const bool live = i < B.nb;
+  const double y0 = 2.0 * (xn[0] * (double) P.n0 - (double) c0) - 1.0;
+  const double y1 = 2.0 * (xn[1] * (double) P.n1 - (double) c1) - 1.0;
+  const double y2 = 2.0 * (xn[2] * (double) P.n2 - (double) c2) - 1.0;
+  const int l0 = q - (u0 - P.T * a), l1 = q - (u1 - P.T * bt), l2 = (q - u2) & (kF - 1);
+  const bool ok0 = live && l0 >= 0 && l0 < W, ok1 = live && l1 >= 0 && l1 < W, ok2 = live && l2 < W;
+  const double *cf0 = S.coef + (ok0 ? l0 : 0);
+  const double *cf1 = S.coef + (kKbPolyDeg + 1) * W + (ok1 ? l1 : 0);
+  const double *cf2 = S.coef + 2 * (kKbPolyDeg + 1) * W + (ok2 ? l2 : 0);
+  double v0 = cf0[P.deg * W], v1 = cf1[P.deg * W], v2 = cf2[P.deg * W];
+#pragma unroll 4
+  for (int k = P.deg - 1; k >= 0; k--) {
+    v0 = fma(v0, y0, cf0[k * W]);
+    v1 = fma(v1, y1, cf1[k * W]);
+    v2 = fma(v2, y2, cf2[k * W]);
+  }
+  S.ops[buf][0][q][i] = ok0 ? v0 : 0.0;
+  S.ops[buf][2][q][i] = ok2 ? v2 : 0.0;
+  if (SPREAD) {
+    S.ops[buf][1][q][i] = ok1 ? v1 * fr : 0.0;
+    S.ops[buf][SPREAD ? 3 : 0][q][i] = ok1 ? v1 * fi : 0.0;
+  } else {
+    S.ops[buf][1][q][i] = ok1 ? v1 : 0.0;
+  }
+  return B;
+}
+
+#define NFFTCU_MMA_PROLOGUE(SPREADV)                                                                  \
+  constexpr int T = kF + 1 - W;                                                                       \
+  extern __shared__ __align__(128) unsigned char smem_raw[];                                          \
+  Shared<W, SPREADV> &S = *reinterpret_cast<Shared<W, SPREADV> *>(smem_raw);                          \
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;                                      \
+  const int kq = lane & 3, nr = lane >> 2;                                                            \
+  const int n2 = P.n2;                                                                                \
+  const long long unit = blockIdx.x;                                                                  \
+  const long long k0 = unit_start[unit], k1 = unit_start[unit + 1];                                   \
+  if (k0 == k1) return;                                                                               \
+  const int tile = (int) (unit / P.zseg);                                                             \
+  const int a = tile / P.NT1, bt = tile - a * P.NT1;                                                  \
+  for (int i = tid; i < 3 * (kKbPolyDeg + 1) * W; i += 128) S.coef[i] = poly[i];                      \
+  for (int r = tid; r < kF * kF; r += 128) {                                                          \
+    const int l0 = r >> 4, l1 = r & 15;                                                               \
+    S.rowoff[r] = (unsigned) ((wrapi(T * a + l0, P.n0) * (long long) P.n1 + wrapi(T * bt + l1, P.n1)) * n2); \
+  }                                                                                                   \
+  __syncthreads();                                                                                    \
+  unsigned rowoff[8];                                                                                 \
+  _Pragma("unroll") for (int g = 0; g < 8; g++)                                                       \
+    rowoff[g] = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + nr];
+
+// ---- interpolation ------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(128, 2)
+interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
+                  const uint32_t *__restrict__ perm, double *__restrict__ f,
+                  const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+  NFFTCU_MMA_PROLOGUE(false)
+
+  double A[8][2][4];   // [group][re/im][slot]: grid value of pencil (group, nr) at the cell of slot 4*s+kq
+  double tr[8], ti[8]; // prefetched pair
+  int pf_z = -1;       // unwrapped first cell of the prefetched pair, -1: none
+
+  auto load_x = [&](long long kb, double (&xn)[3]) {
+    const long long k = kb + (tid & 7);
+    if (k < k1) { xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2]; }
+    else { xn[0] = xn[1] = xn[2] = 0.0; }
+  };
+  auto fill_all = [&](int zlo) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      int z = zlo + ((4 * s + kq - zlo) & 15);
+      if (z >= n2) z -= n2;
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        const double2 v = G[rowoff[g] + z];
+        A[g][0][s] = v.x;
+        A[g][1][s] = v.y;
+      }
+    }
+  };
+  // pair (zp, zp+1), zp even: cell zp+(kq&1) belongs to the lanes with (kq>>1) == (zp>>1)&1, slot (zp>>2)&3
+  auto load_pair = [&](int zp) {
+    if ((kq >> 1) == ((zp >> 1) & 1)) {
+      int z = zp + (kq & 1);
+      if (z >= n2) z -= n2;
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        const double2 v = G[rowoff[g] + z];
+        tr[g] = v.x;
+        ti[g] = v.y;
+      }
+    }
+  };
+  auto commit_pair = [&](int zp) {
+    if ((kq >> 1) == ((zp >> 1) & 1)) {
+      switch ((zp >> 2) & 3) {
+#define NFFTCU_COMMIT(SL)                                                                    \
+        case SL:                                                                             \
+          _Pragma("unroll") for (int g = 0; g < 8; g++) { A[g][0][SL] = tr[g]; A[g][1][SL] = ti[g]; } \
+          break;
+        NFFTCU_COMMIT(0) NFFTCU_COMMIT(1) NFFTCU_COMMIT(2) NFFTCU_COMMIT(3)
+#undef NFFTCU_COMMIT
+      }
+    }
+  };
+
+  double xn[3];
+  load_x(k0, xn);
+  Batch nxt = prepare_batch<W, false>(S, 0, k0, k1, xn, 0.0, 0.0, a, bt, P, tid);
+  load_x(nxt.kb + nxt.nb, xn);
+  __syncthreads();
+  int zwin = -1000;   // window base (unwrapped, even); the window holds cells [zwin, zwin+16)
+
+  for (int b = 0;; b++) {
+    const int cur = b & 1;
+    const Batch B = nxt;
+    const bool more = B.kb + B.nb < k1;
+    if (more) {
+      nxt = prepare_batch<W, false>(S, cur ^ 1, B.kb + B.nb, k1, xn, 0.0, 0.0, a, bt, P, tid);
+      load_x(nxt.kb + nxt.nb, xn);
+    }
+    // ---- slide the window to B.zlo
+    if (B.zlo != zwin) {
+      if (B.zlo - zwin >= kF || zwin < 0) {
+        fill_all(B.zlo);
+        zwin = B.zlo;
+      } else {
+        if (pf_z == zwin + kF) { commit_pair(pf_z); zwin += 2; }
+        while (zwin < B.zlo) { load_pair(zwin + kF); commit_pair(zwin + kF); zwin += 2; }
+      }
+    }
+    pf_z = -1;
+    if (more && nxt.zlo > zwin && nxt.zlo - zwin < kF) { pf_z = zwin + kF; load_pair(pf_z); }
+
+    // ---- T = G * psi2, weighted row sums
+    double bf[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) bf[s] = S.ops[cur][2][4 * s + kq][nr];
+    const double2 p1a = *reinterpret_cast<const double2 *>(&S.ops[cur][1][nr][2 * kq]);
+    const double2 p1b = *reinterpret_cast<const double2 *>(&S.ops[cur][1][8 + nr][2 * kq]);
+    double accr0 = 0.0, accr1 = 0.0, acci0 = 0.0, acci1 = 0.0;
+#pragma unroll
+    for (int h = 0; h < 4; h++) {   // footprint row l0 = 4*warp + h: groups 2h (l1 < 8) and 2h+1
+      double c[2][2][2];
+#pragma unroll
+      for (int gg = 0; gg < 2; gg++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) c[gg][cc][0] = c[gg][cc][1] = 0.0;
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int gg = 0; gg < 2; gg++)
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) dmma(c[gg][cc][0], c[gg][cc][1], A[2 * h + gg][cc][s], bf[s]);
+      const double2 p0 = *reinterpret_cast<const double2 *>(&S.ops[cur][0][4 * warp + h][2 * kq]);
+      const double wa0 = p0.x * p1a.x, wa1 = p0.y * p1a.y, wb0 = p0.x * p1b.x, wb1 = p0.y * p1b.y;
+      accr0 = fma(wa0, c[0][0][0], accr0); accr1 = fma(wa1, c[0][0][1], accr1);
+      acci0 = fma(wa0, c[0][1][0], acci0); acci1 = fma(wa1, c[0][1][1], acci1);
+      accr0 = fma(wb0, c[1][0][0], accr0); accr1 = fma(wb1, c[1][0][1], accr1);
+      acci0 = fma(wb0, c[1][1][0], acci0); acci1 = fma(wb1, c[1][1][1], acci1);
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      accr0 += __shfl_xor_sync(kFull, accr0, o);
+      accr1 += __shfl_xor_sync(kFull, accr1, o);
+      acci0 += __shfl_xor_sync(kFull, acci0, o);
+      acci1 += __shfl_xor_sync(kFull, acci1, o);
+    }
+    if (nr == 0) {
+      *reinterpret_cast<double2 *>(&S.red[cur][warp][4 * kq]) = make_double2(accr0, acci0);
+      *reinterpret_cast<double2 *>(&S.red[cur][warp][4 * kq + 2]) = make_double2(accr1, acci1);
+    }
+    __syncthreads();
+    if (tid < 2 * kNB) {
+      const int node = tid >> 1;
+      if (node < B.nb) {
+        const double v = S.red[cur][0][tid] + S.red[cur][1][tid] + S.red[cur][2][tid] + S.red[cur][3][tid];
+        f[2 * (size_t) perm[B.kb + node] + (tid & 1)] = v;
+      }
+    }
+    if (!more) break;
+  }
+}
+
+// ---- spreading ------------------------------------------------------------------------------------------
+// FLUSH = 0: retired cells go to the grid with RED.ADD straight from the accumulator registers
+// FLUSH = 1: staged per warp in shared memory as 128-byte runs and reduced into the grid by the TMA unit
+constexpr int kStgRow = 9;   // staging row pitch in 16-byte cells: 8 cells + 1 pad (bank-conflict-free, 16-byte aligned)
+
+template <int W, int FLUSH>
+__global__ void __launch_bounds__(128, 2)
+spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const double2 *__restrict__ ft,
+                  const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+  NFFTCU_MMA_PROLOGUE(true)
+  // staging: [buffer][warp][64 rows][kStgRow] double2 behind the Shared block
+  double2 *const stg_base = reinterpret_cast<double2 *>(smem_raw + ((sizeof(Shared<W, true>) + 127) & ~(size_t) 127));
+  double2 *const stg_w = stg_base + (size_t) warp * 64 * kStgRow;   // + buf * 4*64*kStgRow
+  constexpr int kStgBuf = 4 * 64 * kStgRow;
+
+  double C[8][2][2][2];   // [group][re/im][n-tile][col]: accumulator of pencil (group, nr), slot 8*nt + 2*kq + col
+#pragma unroll
+  for (int g = 0; g < 8; g++)
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) C[g][cc][nt][0] = C[g][cc][nt][1] = 0.0;
+
+  auto load_node = [&](long long kb, double (&xn)[3], double &fr, double &fi) {
+    const long long k = kb + (tid & 7);
+    if (k < k1) {
+      xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2];
+      const double2 v = ft[k];
+      fr = v.x; fi = v.y;
+    } else { xn[0] = xn[1] = xn[2] = 0.0; fr = fi = 0.0; }
+  };
+
+  // staging state (uniform across the warp)
+  int sblk = -1;      // 8-cell block (wrapped z >> 3) being staged, -1: none
+  int snext = 0;      // next pair position (0,2,4,6) of the block that has not been written
+  int sbuf = 0;
+  double *const Gd = reinterpret_cast<double *>(G);
+
+  auto stage_store = [&](int pos, bool zero, int nt) {   // pair position pos (even) of the staged block
+    if (kq == (pos >> 1)) {
+      double2 *dst = stg_w + (size_t) sbuf * kStgBuf + (size_t) nr * kStgRow + pos;
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+        if (!zero) {
+          if (nt == 0) { v0 = make_double2(C[g][0][0][0], C[g][1][0][0]); v1 = make_double2(C[g][0][0][1], C[g][1][0][1]); }
+          else { v0 = make_double2(C[g][0][1][0], C[g][1][1][0]); v1 = make_double2(C[g][0][1][1], C[g][1][1][1]); }
+        }
+        dst[(size_t) g * 8 * kStgRow] = v0;
+        dst[(size_t) g * 8 * kStgRow + 1] = v1;
+      }
+    }
+  };
+  auto flush_block = [&]() {   // complete the staged block with zeros and hand its 64 rows to the TMA unit
+    while (snext < 8) { stage_store(snext, true, 0); snext += 2; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const int row = 2 * lane + rr;   // warp-local row = g*8 + pencil
+      const int g = row >> 3, pn = row & 7;
+      const unsigned off = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + pn];
+      const double2 *src = stg_w + (size_t) sbuf * kStgBuf + (size_t) row * kStgRow;
+      double2 *dst = G + off + 8 * sblk;
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;"
+                   ::"l"(dst), "r"(smem_addr(src)) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    sbuf ^= 1;
+    // the buffer we switch to was handed over two flushes ago: wait until the TMA unit has read it
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    sblk = -1;
+    snext = 0;
+  };
+  // retire pair (zp, zp+1) of the window (zp even, unwrapped): n-tile (zp>>3)&1, lanes kq == (zp&7)>>1
+  auto retire_pair = [&](int zp) {
+    int zw = zp;
+    if (zw >= n2) zw -= n2;
+    const int nt = (zp >> 3) & 1;
+    if (FLUSH == 1) {
+      const int blk = zw >> 3, pos = zw & 7;
+      if (blk != sblk) {
+        if (sblk >= 0) flush_block();
+        sblk = blk;
+        snext = 0;
+      }
+      while (snext < pos) { stage_store(snext, true, 0); snext += 2; }
+      stage_store(pos, false, nt);
+      snext = pos + 2;
+      if (snext == 8) flush_block();
+    }
+    if (kq == ((zp & 7) >> 1)) {
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        if (FLUSH == 0) {
+          double *dst = Gd + 2 * ((size_t) rowoff[g] + zw);
+          if (nt == 0) {
+            atomicAdd(dst, C[g][0][0][0]); atomicAdd(dst + 1, C[g][1][0][0]);
+            atomicAdd(dst + 2, C[g][0][0][1]); atomicAdd(dst + 3, C[g][1][0][1]);
+          } else {
+            atomicAdd(dst, C[g][0][1][0]); atomicAdd(dst + 1, C[g][1][1][0]);
+            atomicAdd(dst + 2, C[g][0][1][1]); atomicAdd(dst + 3, C[g][1][1][1]);
+          }
+        }
+        if (nt == 0) { C[g][0][0][0] = C[g][1][0][0] = C[g][0][0][1] = C[g][1][0][1] = 0.0; }
+        else { C[g][0][1][0] = C[g][1][1][0] = C[g][0][1][1] = C[g][1][1][1] = 0.0; }
+      }
+    }
+  };
+
+  double xn[3], fr, fi;
+  load_node(k0, xn, fr, fi);
+  Batch nxt = prepare_batch<W, true>(S, 0, k0, k1, xn, fr, fi, a, bt, P, tid);
+  load_node(nxt.kb + nxt.nb, xn, fr, fi);
+  __syncthreads();
+  int zwin = nxt.zlo;
+
+  for (int b = 0;; b++) {
+    const int cur = b & 1;
+    const Batch B = nxt;
+    const bool more = B.kb + B.nb < k1;
+    if (more) {
+      nxt = prepare_batch<W, true>(S, cur ^ 1, B.kb + B.nb, k1, xn, fr, fi, a, bt, P, tid);
+      load_node(nxt.kb + nxt.nb, xn, fr, fi);
+    }
+    // ---- slide the window to B.zlo: the cells below it are final
+    if (B.zlo != zwin) {
+      const int zend = (B.zlo - zwin >= kF) ? zwin + kF : B.zlo;
+      for (int zp = zwin; zp < zend; zp += 2) retire_pair(zp);
+      zwin = B.zlo;
+    }
+    // ---- G += (psi0 psi1 f) * psi2
+    double bf[2][2];   // [n-tile][k-step]
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) bf[nt][ks] = S.ops[cur][2][8 * nt + nr][4 * ks + kq];
+    double p1r[2][2], p1i[2][2];   // [half][k-step]
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        p1r[hh][ks] = S.ops[cur][1][8 * hh + nr][4 * ks + kq];
+        p1i[hh][ks] = S.ops[cur][3][8 * hh + nr][4 * ks + kq];
+      }
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      const double p00 = S.ops[cur][0][4 * warp + h][kq], p01 = S.ops[cur][0][4 * warp + h][4 + kq];
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        const int g = 2 * h + hh;
+        const double ar0 = p00 * p1r[hh][0], ai0 = p00 * p1i[hh][0];
+        const double ar1 = p01 * p1r[hh][1], ai1 = p01 * p1i[hh][1];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          dmma(C[g][0][nt][0], C[g][0][nt][1], ar0, bf[nt][0]);
+          dmma(C[g][1][nt][0], C[g][1][nt][1], ai0, bf[nt][0]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          dmma(C[g][0][nt][0], C[g][0][nt][1], ar1, bf[nt][1]);
+          dmma(C[g][1][nt][0], C[g][1][nt][1], ai1, bf[nt][1]);
+        }
+      }
+    }
+    __syncthreads();
+    if (!more) break;
+  }
+  for (int zp = zwin; zp < zwin + kF; zp += 2) retire_pair(zp);
+  if (FLUSH == 1) {
+    if (sblk >= 0) flush_block();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+MmaParams make_params(const nfftcu_ctx *c) {
+  MmaParams P;
+  P.n0 = (int) c->n[0];
+  P.n1 = (int) c->n[1];
+  P.n2 = (int) c->n[2];
+  P.m = (int) c->m;
+  P.T = kF + 1 - (2 * P.m + 2);
+  P.NT0 = (P.n0 + P.T - 1) / P.T;
+  P.NT1 = (P.n1 + P.T - 1) / P.T;
+  const long long tiles = (long long) P.NT0 * P.NT1;
+  long long zseg = (8ll * c->sm_count + tiles - 1) / tiles;
+  if (zseg < 1) zseg = 1;
+  if (zseg > P.n2 / 16) zseg = P.n2 / 16;
+  if (zseg < 1) zseg = 1;
+  P.zseg = (int) zseg;
+  P.deg = c->kbpoly_fit;
+  return P;
+}
+
+template <int W, int FLUSH>
+size_t spread_smem() {
+  size_t b = (sizeof(Shared<W, true>) + 127) & ~(size_t) 127;
+  if (FLUSH == 1) b += sizeof(double2) * 2 * 4 * 64 * kStgRow;
+  return b;
+}
+
+template <int W>
+int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
+  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  const double *xt = (const double *) c->tile_x;
+  const double *poly = (const double *) c->kbpoly_dev;
+  if (!spread) {
+    const size_t smem = sizeof(Shared<W, false>);
+    NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    interp_mma_kernel<W><<<grid, 128, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
+                                                         (double *) f_out, c->bin_start, poly, P);
+    c->launches++;
+  } else {
+    const int kb = 256;
+    mma_gather_f_kernel<<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+        (const double2 *) f_in, c->tile_perm, (double2 *) c->f_tile, c->M);
+    const bool bulk = (P.n2 % 8 == 0) && c->opt_b_flush != 1;
+    if (bulk) {
+      const size_t smem = spread_smem<W, 1>();
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<W, 1><<<grid, 128, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
+                                                              c->bin_start, poly, P);
+    } else {
+      const size_t smem = spread_smem<W, 0>();
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<W, 0><<<grid, 128, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
+                                                              c->bin_start, poly, P);
+    }
+    c->launches += 2;
+  }
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+int dispatch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
+  const MmaParams P = make_params(c);
+  switch (2 * (int) c->m + 2) {
+    case 6: return launch<6>(c, f_in, f_out, spread, P);
+    case 8: return launch<8>(c, f_in, f_out, spread, P);
+    case 10: return launch<10>(c, f_in, f_out, spread, P);
+    case 12: return launch<12>(c, f_in, f_out, spread, P);
+    case 14: return launch<14>(c, f_in, f_out, spread, P);
+    default: break;
+  }
+  set_error("mma3d: unsupported window cut-off m=%lld", (long long) c->m);
+  return NFFTCU_EINVAL;
+}
+
+}  // namespace
+
+bool mma3d_supported(const nfftcu_ctx *c) {
+  if (c->d != 3 || c->direct_only || c->prec != NFFTCU_DOUBLE) return false;
+  if (c->m < 2 || c->m > 6 || c->kbpoly_fit < 0) return false;
+  for (int t = 0; t < 3; t++)
+    if (c->n[t] < kF || c->n[t] > 0x3fffff) return false;
+  if (c->n[2] % 2 != 0) return false;
+  if (c->n_total >= (1ll << 31)) return false;   // 32-bit row offsets
+  const long long T = kF + 1 - (2 * c->m + 2);
+  const long long units = ((c->n[0] + T - 1) / T) * ((c->n[1] + T - 1) / T) * 64;
+  return units < (1ll << 31);
+}
+
+// processing order of the DMMA kernels: nodes sorted by (tile, u2), work-unit offsets
+int mma3d_bin_nodes(nfftcu_ctx *c) {
+  const long long M = c->M;
+  c->mma_ready = false;
+  if (M == 0) return NFFTCU_OK;
+  const MmaParams P = make_params(c);
+  const long long units = (long long) P.NT0 * P.NT1 * P.zseg;
+  const long long nkeys = (long long) P.NT0 * P.NT1 * P.n2;
+  if (!c->tile_keys) NFFTCU_CUDA(cudaMalloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
+  if (!c->tile_perm) NFFTCU_CUDA(cudaMalloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
+  if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, sizeof(double) * (size_t) M * 3));
+  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, sizeof(double2) * (size_t) M));
+  if (!c->bin_start || c->tile_nbins != units) {
+    if (c->bin_start) cudaFree(c->bin_start);
+    c->bin_start = nullptr;
+    NFFTCU_CUDA(cudaMalloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    c->tile_nbins = units;
+  }
+  const int kb = 256;
+  mma_keys_kernel<<<(unsigned) ((M + kb - 1) / kb), kb, 0, c->stream>>>(
+      (const double *) c->x_dev, (uint64_t *) c->tile_keys, c->tile_perm, M, P);
+  c->launches++;
+  int bits = 0;
+  while ((1ll << bits) < nkeys && bits < 62) bits++;
+  NFFTCU_TRY(radix_sort_pairs(c, (uint64_t *) c->tile_keys, c->tile_perm, M, bits));
+  NFFTCU_TRY(gather_nodes(c, c->tile_perm, c->tile_x));
+  mma_unit_bounds_kernel<<<(unsigned) ((units + 1 + kb - 1) / kb), kb, 0, c->stream>>>(
+      (const uint64_t *) c->tile_keys, c->bin_start, units, M, P);
+  c->launches++;
+  NFFTCU_CUDA(cudaGetLastError());
+  c->mma_ready = true;
+  return NFFTCU_OK;
+}
+
+int mma3d_interp(nfftcu_ctx *c, void *f_dev) { return dispatch(c, nullptr, f_dev, false); }
+
+int mma3d_spread(nfftcu_ctx *c, const void *f_dev) { return dispatch(c, f_dev, nullptr, true); }
+
+}  // namespace nfftcu

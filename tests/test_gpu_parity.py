@@ -390,6 +390,9 @@ def test_trafo_subsample_vs_oracle_cfg3_grid():
     ([32, 32, 32], [64, 64, 64], 2, 6000),
     ([20, 20, 20], [40, 40, 40], 8, 2000),
     ([64, 8, 8], [128, 16, 16], 4, 3000),
+    ([20, 18, 21], [40, 36, 42], 6, 5000),       # DMMA path with n2 % 8 != 0 (RED flush), n % 16 != 0
+    ([12, 12, 12], [24, 24, 24], 6, 20000),      # DMMA path, many nodes per tile, window wraps in z
+    ([16, 16, 16], [32, 32, 40], 3, 4000),       # DMMA path, tile edge 9
 ])
 def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
     rng = np.random.default_rng(31)
@@ -405,18 +408,24 @@ def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
     if not (np.all(np.isfinite(want_f)) and np.all(np.isfinite(want_fh))):
         pytest.skip("psi0*psi1*psi2 overflows single precision at this m (in the reference too)")
     outs = {}
-    for label, kernel, table in (("tile", 0, 0), ("tile+table", 0, 1), ("generic", 1, 0), ("generic+table", 1, 1)):
+    variants = [("tile", 0, 0, 0), ("pencil", 2, 0, 0), ("pencil+table", 2, 1, 0), ("generic", 1, 0, 0),
+                ("generic+table", 1, 1, 0)]
+    if precision == "double":
+        variants += [("mma", 3, 0, 0), ("mma+red", 3, 0, 1)]
+    for label, kernel, table, flush in variants:
         eng = cabi.Engine(N, n, m, M, precision=precision)
         eng.set_option(cabi.OPT_B_KERNEL, kernel)
         eng.set_option(cabi.OPT_PSI_TABLE, table)
+        eng.set_option(cabi.OPT_B_FLUSH, flush)
         eng.set_nodes(x)
         outs[label] = (eng.trafo(fh), eng.adjoint(f))
         eng.close()
         assert rel_l2(outs[label][0], want_f) <= TOL[precision], label
         assert rel_l2(outs[label][1], want_fh) <= TOL[precision], label
     tight = 1e-13 if precision == "double" else 5e-6
-    assert rel_l2(outs["tile"][0], outs["generic"][0]) <= tight
-    assert rel_l2(outs["tile"][1], outs["generic"][1]) <= tight
+    for label in outs:
+        assert rel_l2(outs[label][0], outs["generic"][0]) <= tight, label
+        assert rel_l2(outs[label][1], outs["generic"][1]) <= tight, label
 
 
 def test_tile3d_z_segments_small_grid_many_nodes():
