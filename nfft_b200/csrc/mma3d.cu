@@ -107,33 +107,69 @@ __global__ void mma_gather_f_kernel(const double2 *__restrict__ f, const uint32_
   if (k < M) ft[k] = f[perm[k]];
 }
 
-// ---- shared operand block -------------------------------------------------------------------------------
-// ops[buf][v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
+// ---- mbarrier helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, int parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+  while (!mbar_test(bar, parity)) {}
+}
+
+// ---- shared memory ----------------------------------------------------------------------------------------
+// A ring of kStages operand blocks filled by the producer warpgroup and consumed by the MMA warpgroup.
+// ops[v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
 // (spreading), 2: psi2 in circular window slots, 3: psi1*f.im (spreading only)
+constexpr int kStages = 4;
+constexpr int kMmaRegs = 208, kProdRegs = 48;   // setmaxnreg: 128 * (208 + 48) = 2 CTAs per SM
+
+struct Meta {
+  long long kb;   // first node of the batch (tile order)
+  int nb;         // nodes in the batch, 1..8
+  int zlo;        // window base (even, in [0, n2))
+  int last;       // no batch follows
+  int pad;
+};
+
 template <int W, bool SPREAD>
 struct Shared {
-  double ops[2][SPREAD ? 4 : 3][kF][kNB];
-  double red[2][4][2 * kNB];
+  double ops[kStages][SPREAD ? 4 : 3][kF][kNB];
+  double red[kStages][4][2 * kNB];   // interpolation: per-MMA-warp partial sums of the batch
+  Meta meta[kStages];
+  uint64_t full[kStages], empty[kStages];
   double coef[3 * (kKbPolyDeg + 1) * W];
   unsigned rowoff[kF * kF];
 };
 
 struct Batch {
-  long long kb;   // first node (tile order)
-  int nb;         // nodes in the batch, 1..8
-  int zlo;        // window base (even, unwrapped = in [0, n2))
+  long long kb;
+  int nb;
+  int zlo;
 };
 
-// Every thread of the CTA holds the coordinates of node kb + (tid & 7) of the NEXT batch; this evaluates
-// that batch's extent (uniform across the CTA) and the thread's 3 (4) entries of the operand block.
+// Producer thread p (0..127) holds the coordinates of node kb + (p & 7) of the batch; this evaluates the
+// batch's extent (uniform across the warpgroup) and the thread's 3 (4) entries of the operand block.
 template <int W, bool SPREAD>
-__device__ __forceinline__ Batch prepare_batch(Shared<W, SPREAD> &S, int buf, long long kb, long long k1,
+__device__ __forceinline__ Batch prepare_batch(Shared<W, SPREAD> &S, int st, long long kb, long long k1,
                                                const double (&xn)[3], double fr, double fi, int a, int bt,
-                                               const MmaParams &P, int tid) {
-  const int i = tid & 7, q = tid >> 3;
-  const long long c0 = cell_of(xn[0], P.n0), c1 = cell_of(xn[1], P.n1), c2 = cell_of(xn[2], P.n2);
-  const int u0 = wrapi((int) (c0 - P.m), P.n0), u1 = wrapi((int) (c1 - P.m), P.n1);
-  const int u2 = wrapi((int) (c2 - P.m), P.n2);
+                                               const MmaParams &P, int p) {
+  const int i = p & 7, q = p >> 3;
+  const int c0 = __double2int_rd(__dmul_rn(xn[0], (double) P.n0));
+  const int c1 = __double2int_rd(__dmul_rn(xn[1], (double) P.n1));
+  const int c2 = __double2int_rd(__dmul_rn(xn[2], (double) P.n2));
+  const int u0 = wrapi(c0 - P.m, P.n0), u1 = wrapi(c1 - P.m, P.n1), u2 = wrapi(c2 - P.m, P.n2);
   Batch B;
   B.kb = kb;
   B.zlo = __shfl_sync(kFull, u2, 0) & ~1;
@@ -155,56 +191,118 @@ __device__ __forceinline__ Batch prepare_batch(Shared<W, SPREAD> &S, int buf, lo
     v1 = fma(v1, y1, cf1[k * W]);
     v2 = fma(v2, y2, cf2[k * W]);
   }
-  S.ops[buf][0][q][i] = ok0 ? v0 : 0.0;
-  S.ops[buf][2][q][i] = ok2 ? v2 : 0.0;
+  S.ops[st][0][q][i] = ok0 ? v0 : 0.0;
+  S.ops[st][2][q][i] = ok2 ? v2 : 0.0;
   if (SPREAD) {
-    S.ops[buf][1][q][i] = ok1 ? v1 * fr : 0.0;
-    S.ops[buf][SPREAD ? 3 : 0][q][i] = ok1 ? v1 * fi : 0.0;
+    S.ops[st][1][q][i] = ok1 ? v1 * fr : 0.0;
+    S.ops[st][SPREAD ? 3 : 0][q][i] = ok1 ? v1 * fi : 0.0;
   } else {
-    S.ops[buf][1][q][i] = ok1 ? v1 : 0.0;
+    S.ops[st][1][q][i] = ok1 ? v1 : 0.0;
   }
   return B;
+}
+
+// The producer warpgroup (threads 128..255): walks the unit's nodes, forms the batches, fills the ring and --
+// for interpolation -- finishes the batches the MMA warps have released (cross-warp sum, scatter to f).
+template <int W, bool SPREAD>
+__device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double *__restrict__ xt,
+                                              const double2 *__restrict__ ft, const uint32_t *__restrict__ perm,
+                                              double *__restrict__ f, long long k0, long long k1, int a, int bt,
+                                              const MmaParams &P, int p) {
+  auto load_node = [&](long long kb, double (&xn)[3], double &fr, double &fi) {
+    const long long k = kb + (p & 7);
+    fr = fi = 0.0;
+    if (k < k1) {
+      xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2];
+      if (SPREAD) { const double2 v = ft[k]; fr = v.x; fi = v.y; }
+    } else { xn[0] = xn[1] = xn[2] = 0.0; }
+  };
+  auto finalize = [&](int st) {   // interpolation: batch in stage st has been released by all MMA warps
+    if (!SPREAD && p < 2 * kNB) {
+      const Meta mt = S.meta[st];
+      if ((p >> 1) < mt.nb) {
+        const double v = S.red[st][0][p] + S.red[st][1][p] + S.red[st][2][p] + S.red[st][3][p];
+        f[2 * (size_t) perm[mt.kb + (p >> 1)] + (p & 1)] = v;
+      }
+    }
+    __syncwarp();
+  };
+  double xn[3], fr, fi;
+  load_node(k0, xn, fr, fi);
+  long long kb = k0;
+  int j = 0;
+  for (;; j++) {
+    const int st = j % kStages;
+    if (j >= kStages) {
+      mbar_wait(&S.empty[st], ((j / kStages) - 1) & 1);
+      finalize(st);
+    }
+    const Batch B = prepare_batch<W, SPREAD>(S, st, kb, k1, xn, fr, fi, a, bt, P, p);
+    kb = B.kb + B.nb;
+    const bool more = kb < k1;
+    if (p == 0) {
+      Meta mt;
+      mt.kb = B.kb; mt.nb = B.nb; mt.zlo = B.zlo; mt.last = more ? 0 : 1; mt.pad = 0;
+      S.meta[st] = mt;
+    }
+    if (more) load_node(kb, xn, fr, fi);
+    mbar_arrive(&S.full[st]);
+    if (!more) break;
+  }
+  if (!SPREAD) {
+    for (int jj = (j >= kStages ? j - kStages + 1 : 0); jj <= j; jj++) {
+      const int st = jj % kStages;
+      mbar_wait(&S.empty[st], (jj / kStages) & 1);
+      finalize(st);
+    }
+  }
 }
 
 #define NFFTCU_MMA_PROLOGUE(SPREADV)                                                                  \
   constexpr int T = kF + 1 - W;                                                                       \
   extern __shared__ __align__(128) unsigned char smem_raw[];                                          \
   Shared<W, SPREADV> &S = *reinterpret_cast<Shared<W, SPREADV> *>(smem_raw);                          \
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;                                      \
-  const int kq = lane & 3, nr = lane >> 2;                                                            \
+  const int tid = threadIdx.x;                                                                        \
   const int n2 = P.n2;                                                                                \
   const long long unit = blockIdx.x;                                                                  \
   const long long k0 = unit_start[unit], k1 = unit_start[unit + 1];                                   \
   if (k0 == k1) return;                                                                               \
   const int tile = (int) (unit / P.zseg);                                                             \
   const int a = tile / P.NT1, bt = tile - a * P.NT1;                                                  \
-  for (int i = tid; i < 3 * (kKbPolyDeg + 1) * W; i += 128) S.coef[i] = poly[i];                      \
-  for (int r = tid; r < kF * kF; r += 128) {                                                          \
-    const int l0 = r >> 4, l1 = r & 15;                                                               \
-    S.rowoff[r] = (unsigned) ((wrapi(T * a + l0, P.n0) * (long long) P.n1 + wrapi(T * bt + l1, P.n1)) * n2); \
+  for (int i = tid; i < 3 * (kKbPolyDeg + 1) * W; i += 256) S.coef[i] = poly[i];                      \
+  {                                                                                                   \
+    const int l0 = tid >> 4, l1 = tid & 15;                                                           \
+    S.rowoff[tid] = (unsigned) ((wrapi(T * a + l0, P.n0) * (long long) P.n1 + wrapi(T * bt + l1, P.n1)) * n2); \
+  }                                                                                                   \
+  if (tid == 0) {                                                                                     \
+    for (int st = 0; st < kStages; st++) { mbar_init(&S.full[st], 128); mbar_init(&S.empty[st], 4); } \
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                                \
   }                                                                                                   \
   __syncthreads();                                                                                    \
+  if (tid >= 128) {                                                                                   \
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));                             \
+    producer_loop<W, SPREADV>(S, xt, ft, perm, f, k0, k1, a, bt, P, tid - 128);                       \
+    return;                                                                                           \
+  }                                                                                                   \
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
+  const int lane = tid & 31, warp = tid >> 5;                                                         \
+  const int kq = lane & 3, nr = lane >> 2;                                                            \
   unsigned rowoff[8];                                                                                 \
   _Pragma("unroll") for (int g = 0; g < 8; g++)                                                       \
     rowoff[g] = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + nr];
 
 // ---- interpolation ------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
                   const uint32_t *__restrict__ perm, double *__restrict__ f,
                   const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+  const double2 *const ft = nullptr;
   NFFTCU_MMA_PROLOGUE(false)
 
   double A[8][2][4];   // [group][re/im][slot]: grid value of pencil (group, nr) at the cell of slot 4*s+kq
-  double tr[8], ti[8]; // prefetched pair
-  int pf_z = -1;       // unwrapped first cell of the prefetched pair, -1: none
+  int zwin = -1000;    // window base (even); the window holds cells [zwin, zwin+16), cell z in slot z mod 16
 
-  auto load_x = [&](long long kb, double (&xn)[3]) {
-    const long long k = kb + (tid & 7);
-    if (k < k1) { xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2]; }
-    else { xn[0] = xn[1] = xn[2] = 0.0; }
-  };
   auto fill_all = [&](int zlo) {
 #pragma unroll
     for (int s = 0; s < 4; s++) {
@@ -223,61 +321,41 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
     if ((kq >> 1) == ((zp >> 1) & 1)) {
       int z = zp + (kq & 1);
       if (z >= n2) z -= n2;
-#pragma unroll
-      for (int g = 0; g < 8; g++) {
-        const double2 v = G[rowoff[g] + z];
-        tr[g] = v.x;
-        ti[g] = v.y;
-      }
-    }
-  };
-  auto commit_pair = [&](int zp) {
-    if ((kq >> 1) == ((zp >> 1) & 1)) {
       switch ((zp >> 2) & 3) {
-#define NFFTCU_COMMIT(SL)                                                                    \
-        case SL:                                                                             \
-          _Pragma("unroll") for (int g = 0; g < 8; g++) { A[g][0][SL] = tr[g]; A[g][1][SL] = ti[g]; } \
+#define NFFTCU_LOADPAIR(SL)                                                                     \
+        case SL:                                                                                \
+          _Pragma("unroll") for (int g = 0; g < 8; g++) {                                       \
+            const double2 v = G[rowoff[g] + z];                                                 \
+            A[g][0][SL] = v.x;                                                                  \
+            A[g][1][SL] = v.y;                                                                  \
+          }                                                                                     \
           break;
-        NFFTCU_COMMIT(0) NFFTCU_COMMIT(1) NFFTCU_COMMIT(2) NFFTCU_COMMIT(3)
-#undef NFFTCU_COMMIT
+        NFFTCU_LOADPAIR(0) NFFTCU_LOADPAIR(1) NFFTCU_LOADPAIR(2) NFFTCU_LOADPAIR(3)
+#undef NFFTCU_LOADPAIR
       }
     }
   };
-
-  double xn[3];
-  load_x(k0, xn);
-  Batch nxt = prepare_batch<W, false>(S, 0, k0, k1, xn, 0.0, 0.0, a, bt, P, tid);
-  load_x(nxt.kb + nxt.nb, xn);
-  __syncthreads();
-  int zwin = -1000;   // window base (unwrapped, even); the window holds cells [zwin, zwin+16)
-
-  for (int b = 0;; b++) {
-    const int cur = b & 1;
-    const Batch B = nxt;
-    const bool more = B.kb + B.nb < k1;
-    if (more) {
-      nxt = prepare_batch<W, false>(S, cur ^ 1, B.kb + B.nb, k1, xn, 0.0, 0.0, a, bt, P, tid);
-      load_x(nxt.kb + nxt.nb, xn);
+  auto advance_to = [&](int zlo) {
+    if (zlo - zwin >= kF || zwin < 0) {
+      fill_all(zlo);
+      zwin = zlo;
+    } else {
+      while (zwin < zlo) { load_pair(zwin + kF); zwin += 2; }
     }
-    // ---- slide the window to B.zlo
-    if (B.zlo != zwin) {
-      if (B.zlo - zwin >= kF || zwin < 0) {
-        fill_all(B.zlo);
-        zwin = B.zlo;
-      } else {
-        if (pf_z == zwin + kF) { commit_pair(pf_z); zwin += 2; }
-        while (zwin < B.zlo) { load_pair(zwin + kF); commit_pair(zwin + kF); zwin += 2; }
-      }
-    }
-    pf_z = -1;
-    if (more && nxt.zlo > zwin && nxt.zlo - zwin < kF) { pf_z = zwin + kF; load_pair(pf_z); }
+  };
+
+  for (int j = 0;; j++) {
+    const int st = j % kStages;
+    mbar_wait(&S.full[st], (j / kStages) & 1);
+    const int zlo = S.meta[st].zlo, last = S.meta[st].last;
+    if (zlo != zwin) advance_to(zlo);
 
     // ---- T = G * psi2, weighted row sums
     double bf[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) bf[s] = S.ops[cur][2][4 * s + kq][nr];
-    const double2 p1a = *reinterpret_cast<const double2 *>(&S.ops[cur][1][nr][2 * kq]);
-    const double2 p1b = *reinterpret_cast<const double2 *>(&S.ops[cur][1][8 + nr][2 * kq]);
+    for (int s = 0; s < 4; s++) bf[s] = S.ops[st][2][4 * s + kq][nr];
+    const double2 p1a = *reinterpret_cast<const double2 *>(&S.ops[st][1][nr][2 * kq]);
+    const double2 p1b = *reinterpret_cast<const double2 *>(&S.ops[st][1][8 + nr][2 * kq]);
     double accr0 = 0.0, accr1 = 0.0, acci0 = 0.0, acci1 = 0.0;
 #pragma unroll
     for (int h = 0; h < 4; h++) {   // footprint row l0 = 4*warp + h: groups 2h (l1 < 8) and 2h+1
@@ -292,12 +370,21 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
         for (int gg = 0; gg < 2; gg++)
 #pragma unroll
           for (int cc = 0; cc < 2; cc++) dmma(c[gg][cc][0], c[gg][cc][1], A[2 * h + gg][cc][s], bf[s]);
-      const double2 p0 = *reinterpret_cast<const double2 *>(&S.ops[cur][0][4 * warp + h][2 * kq]);
+      const double2 p0 = *reinterpret_cast<const double2 *>(&S.ops[st][0][4 * warp + h][2 * kq]);
       const double wa0 = p0.x * p1a.x, wa1 = p0.y * p1a.y, wb0 = p0.x * p1b.x, wb1 = p0.y * p1b.y;
       accr0 = fma(wa0, c[0][0][0], accr0); accr1 = fma(wa1, c[0][0][1], accr1);
       acci0 = fma(wa0, c[0][1][0], acci0); acci1 = fma(wa1, c[0][1][1], acci1);
       accr0 = fma(wb0, c[1][0][0], accr0); accr1 = fma(wb1, c[1][0][1], accr1);
       acci0 = fma(wb0, c[1][1][0], acci0); acci1 = fma(wb1, c[1][1][1], acci1);
+    }
+    // the window registers are free again: if the next batch is already in the ring, slide the window
+    // now, so that the refill loads fly while this batch is being reduced
+    if (!last) {
+      const int s1 = (j + 1) % kStages;
+      if (mbar_test(&S.full[s1], ((j + 1) / kStages) & 1)) {
+        const int z1 = S.meta[s1].zlo;
+        if (z1 != zwin) advance_to(z1);
+      }
     }
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
@@ -307,18 +394,12 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
       acci1 += __shfl_xor_sync(kFull, acci1, o);
     }
     if (nr == 0) {
-      *reinterpret_cast<double2 *>(&S.red[cur][warp][4 * kq]) = make_double2(accr0, acci0);
-      *reinterpret_cast<double2 *>(&S.red[cur][warp][4 * kq + 2]) = make_double2(accr1, acci1);
+      *reinterpret_cast<double2 *>(&S.red[st][warp][4 * kq]) = make_double2(accr0, acci0);
+      *reinterpret_cast<double2 *>(&S.red[st][warp][4 * kq + 2]) = make_double2(accr1, acci1);
     }
-    __syncthreads();
-    if (tid < 2 * kNB) {
-      const int node = tid >> 1;
-      if (node < B.nb) {
-        const double v = S.red[cur][0][tid] + S.red[cur][1][tid] + S.red[cur][2][tid] + S.red[cur][3][tid];
-        f[2 * (size_t) perm[B.kb + node] + (tid & 1)] = v;
-      }
-    }
-    if (!more) break;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[st]);
+    if (last) break;
   }
 }
 
@@ -328,9 +409,11 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
 constexpr int kStgRow = 9;   // staging row pitch in 16-byte cells: 8 cells + 1 pad (bank-conflict-free, 16-byte aligned)
 
 template <int W, int FLUSH>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const double2 *__restrict__ ft,
                   const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+  const uint32_t *const perm = nullptr;
+  double *const f = nullptr;
   NFFTCU_MMA_PROLOGUE(true)
   // staging: [buffer][warp][64 rows][kStgRow] double2 behind the Shared block
   double2 *const stg_base = reinterpret_cast<double2 *>(smem_raw + ((sizeof(Shared<W, true>) + 127) & ~(size_t) 127));
@@ -344,15 +427,6 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
     for (int cc = 0; cc < 2; cc++)
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) C[g][cc][nt][0] = C[g][cc][nt][1] = 0.0;
-
-  auto load_node = [&](long long kb, double (&xn)[3], double &fr, double &fi) {
-    const long long k = kb + (tid & 7);
-    if (k < k1) {
-      xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2];
-      const double2 v = ft[k];
-      fr = v.x; fi = v.y;
-    } else { xn[0] = xn[1] = xn[2] = 0.0; fr = fi = 0.0; }
-  };
 
   // staging state (uniform across the warp)
   int sblk = -1;      // 8-cell block (wrapped z >> 3) being staged, -1: none
@@ -433,49 +507,44 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
     }
   };
 
-  double xn[3], fr, fi;
-  load_node(k0, xn, fr, fi);
-  Batch nxt = prepare_batch<W, true>(S, 0, k0, k1, xn, fr, fi, a, bt, P, tid);
-  load_node(nxt.kb + nxt.nb, xn, fr, fi);
-  __syncthreads();
-  int zwin = nxt.zlo;
-
-  for (int b = 0;; b++) {
-    const int cur = b & 1;
-    const Batch B = nxt;
-    const bool more = B.kb + B.nb < k1;
-    if (more) {
-      nxt = prepare_batch<W, true>(S, cur ^ 1, B.kb + B.nb, k1, xn, fr, fi, a, bt, P, tid);
-      load_node(nxt.kb + nxt.nb, xn, fr, fi);
-    }
-    // ---- slide the window to B.zlo: the cells below it are final
-    if (B.zlo != zwin) {
-      const int zend = (B.zlo - zwin >= kF) ? zwin + kF : B.zlo;
+  int zwin = -1;
+  for (int j = 0;; j++) {
+    const int st = j % kStages;
+    mbar_wait(&S.full[st], (j / kStages) & 1);
+    const int zlo = S.meta[st].zlo, last = S.meta[st].last;
+    // ---- slide the window to zlo: the cells below it are final
+    if (zwin < 0) zwin = zlo;
+    if (zlo != zwin) {
+      const int zend = (zlo - zwin >= kF) ? zwin + kF : zlo;
       for (int zp = zwin; zp < zend; zp += 2) retire_pair(zp);
-      zwin = B.zlo;
+      zwin = zlo;
     }
     // ---- G += (psi0 psi1 f) * psi2
     double bf[2][2];   // [n-tile][k-step]
 #pragma unroll
     for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-      for (int ks = 0; ks < 2; ks++) bf[nt][ks] = S.ops[cur][2][8 * nt + nr][4 * ks + kq];
+      for (int ks = 0; ks < 2; ks++) bf[nt][ks] = S.ops[st][2][8 * nt + nr][4 * ks + kq];
     double p1r[2][2], p1i[2][2];   // [half][k-step]
 #pragma unroll
     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        p1r[hh][ks] = S.ops[cur][1][8 * hh + nr][4 * ks + kq];
-        p1i[hh][ks] = S.ops[cur][3][8 * hh + nr][4 * ks + kq];
+        p1r[hh][ks] = S.ops[st][1][8 * hh + nr][4 * ks + kq];
+        p1i[hh][ks] = S.ops[st][3][8 * hh + nr][4 * ks + kq];
       }
+    double p0[4][2];
+#pragma unroll
+    for (int h = 0; h < 4; h++) { p0[h][0] = S.ops[st][0][4 * warp + h][kq]; p0[h][1] = S.ops[st][0][4 * warp + h][4 + kq]; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[st]);   // operands are in registers: the stage can be refilled
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-      const double p00 = S.ops[cur][0][4 * warp + h][kq], p01 = S.ops[cur][0][4 * warp + h][4 + kq];
 #pragma unroll
       for (int hh = 0; hh < 2; hh++) {
         const int g = 2 * h + hh;
-        const double ar0 = p00 * p1r[hh][0], ai0 = p00 * p1i[hh][0];
-        const double ar1 = p01 * p1r[hh][1], ai1 = p01 * p1i[hh][1];
+        const double ar0 = p0[h][0] * p1r[hh][0], ai0 = p0[h][0] * p1i[hh][0];
+        const double ar1 = p0[h][1] * p1r[hh][1], ai1 = p0[h][1] * p1i[hh][1];
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           dmma(C[g][0][nt][0], C[g][0][nt][1], ar0, bf[nt][0]);
@@ -488,8 +557,7 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
         }
       }
     }
-    __syncthreads();
-    if (!more) break;
+    if (last) break;
   }
   for (int zp = zwin; zp < zwin + kF; zp += 2) retire_pair(zp);
   if (FLUSH == 1) {
@@ -532,7 +600,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   if (!spread) {
     const size_t smem = sizeof(Shared<W, false>);
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    interp_mma_kernel<W><<<grid, 128, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
+    interp_mma_kernel<W><<<grid, 256, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
                                                          (double *) f_out, c->bin_start, poly, P);
     c->launches++;
   } else {
@@ -543,12 +611,12 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     if (bulk) {
       const size_t smem = spread_smem<W, 1>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<W, 1><<<grid, 128, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
+      spread_mma_kernel<W, 1><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
                                                               c->bin_start, poly, P);
     } else {
       const size_t smem = spread_smem<W, 0>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<W, 0><<<grid, 128, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
+      spread_mma_kernel<W, 0><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
                                                               c->bin_start, poly, P);
     }
     c->launches += 2;
