@@ -77,6 +77,10 @@ struct nfftcu_ctx_s {
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;
   bool mma_ready = false;           // tile_* hold the (tile, u2) order of the DMMA kernels (mma3d.cu)
+  void *mma_batches = nullptr;      // uint2 per batch: first node, zlo | nb << 24 | last << 28
+  uint32_t *mma_batch_start = nullptr;   // units+1 offsets into mma_batches
+  uint32_t *mma_counts = nullptr;   // scratch: batches per unit
+  long long mma_units = 0, mma_batch_cap = 0;
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

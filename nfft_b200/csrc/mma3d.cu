@@ -31,10 +31,15 @@
 // moves no registers.  Per batch a warp issues 64 DMMAs (16 m-tiles x 4 k-steps, resp. 16 m-tiles x 2
 // n-tiles x 2 k-steps) = 16384 FMAs for 8 nodes: lane efficiency (14/16)^3 = 67 % of the useful 5488 per node.
 //
-// Window values are evaluated in the kernel from the node coordinates (24 bytes per node instead of a
-// 416-byte record): the piecewise polynomials of kbpoly.cu, one Horner chain per (dimension, slot, node)
-// entry, 3 entries per thread and batch, written zero-padded and already placed (offset in the
-// footprint, circular slot in z) into a double-buffered shared operand block, one __syncthreads per batch.
+// Batches are formed once per node set (plan time, like the reference's precompute_psi): a table of
+// (first node, count, window base) per batch and the batch range of every work unit.
+//
+// Warp specialisation.  A CTA has two warpgroups.  The PRODUCER warps evaluate the window from the node
+// coordinates (24 bytes per node instead of a 416-byte record): the piecewise polynomials of kbpoly.cu,
+// one Horner chain per (dimension, slot, node) entry -- a warp owns every 4th batch and runs its 12
+// chains per lane interleaved -- written zero-padded and already placed (offset in the footprint,
+// circular slot in z) into a ring of shared operand blocks.  The MMA warps only wait on the ring's
+// mbarriers; setmaxnreg moves the registers the producers do not need to them (200 / 56).
 //
 // Spreading retires cells through shared memory: a warp stages the retired pairs of ITS rows as
 // 128-byte runs (8 cells) and hands complete runs to the TMA unit as bulk reductions
@@ -107,6 +112,69 @@ __global__ void mma_gather_f_kernel(const double2 *__restrict__ f, const uint32_
   if (k < M) ft[k] = f[perm[k]];
 }
 
+// ---- batch table (plan time) ------------------------------------------------------------------------------
+// entry.x = first node (tile order), entry.y = zlo | nb << 24 | last << 28
+__device__ __forceinline__ int bt_zlo(uint2 e) { return (int) (e.y & 0xffffffu); }
+__device__ __forceinline__ int bt_nb(uint2 e) { return (int) ((e.y >> 24) & 0xfu); }
+__device__ __forceinline__ int bt_last(uint2 e) { return (int) ((e.y >> 28) & 1u); }
+
+// One warp per work unit walks the unit's sorted nodes 32 at a time and cuts them into batches: a batch
+// starts at the first unassigned node, zlo = its u2 rounded down to even, and takes up to 8 nodes with
+// u2 <= zlo + 2.  FILL = false counts, FILL = true writes the entries at batch_start[unit].
+template <bool FILL>
+__global__ void mma_batches_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ unit_start,
+                                   uint32_t *__restrict__ counts, const uint32_t *__restrict__ batch_start,
+                                   uint2 *__restrict__ table, long long units, MmaParams P) {
+  const long long unit = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (unit >= units) return;
+  const long long k0 = unit_start[unit], k1 = unit_start[unit + 1];
+  const uint64_t base = (uint64_t) (unit / P.zseg) * P.n2;
+  const uint32_t out = FILL ? batch_start[unit] : 0;
+  uint32_t nbat = 0;
+  long long pos = k0;
+  while (pos < k1) {
+    const long long idx = pos + lane;
+    const int u = idx < k1 ? (int) (keys[idx] - base) : 0x7fffffff;
+    int o = 0;
+    while (pos + o < k1) {
+      if (o + kNB > 32 && pos + 32 < k1) break;   // the batch may extend beyond this chunk: reload from pos + o
+      const int zlo = __shfl_sync(kFull, u, o) & ~1;
+      const bool member = lane >= o && lane < o + kNB && u <= zlo + 2;
+      const int nb = __popc(__ballot_sync(kFull, member));
+      if (FILL && lane == 0) {
+        const unsigned last = (pos + o + nb >= k1) ? 1u : 0u;
+        table[out + nbat] = make_uint2((uint32_t) (pos + o), (unsigned) zlo | ((unsigned) nb << 24) | (last << 28));
+      }
+      nbat++;
+      o += nb;
+    }
+    pos += o;
+  }
+  if (!FILL && lane == 0) counts[unit] = nbat;
+}
+
+// exclusive scan of counts[0..n) into out[0..n], single CTA
+__global__ void mma_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ out, long long n) {
+  __shared__ uint32_t part[1024];
+  const int t = threadIdx.x;
+  const long long chunk = (n + 1023) / 1024;
+  const long long lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+  uint32_t s = 0;
+  for (long long i = lo; i < hi; i++) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = t > 0 ? part[t - 1] : 0;
+  for (long long i = lo; i < hi; i++) { out[i] = run; run += counts[i]; }
+  if (t == 1023) out[n] = part[1023];
+}
+
 // ---- mbarrier helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -114,143 +182,123 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, int parity) {
-  uint32_t done;
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-  return done != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
-  while (!mbar_test(bar, parity)) {}
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
 // ---- shared memory ----------------------------------------------------------------------------------------
-// A ring of kStages operand blocks filled by the producer warpgroup and consumed by the MMA warpgroup.
+// A ring of kStages operand blocks; producer warp w fills the stages of batches j = w (mod 4).
 // ops[v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
 // (spreading), 2: psi2 in circular window slots, 3: psi1*f.im (spreading only)
-constexpr int kStages = 4;
-constexpr int kMmaRegs = 208, kProdRegs = 48;   // setmaxnreg: 128 * (208 + 48) = 2 CTAs per SM
-
-struct Meta {
-  long long kb;   // first node of the batch (tile order)
-  int nb;         // nodes in the batch, 1..8
-  int zlo;        // window base (even, in [0, n2))
-  int last;       // no batch follows
-  int pad;
-};
+constexpr int kStages = 8;
+constexpr int kMmaRegs = 200, kProdRegs = 56;   // setmaxnreg: 128 * (200 + 56) = 2 CTAs per SM
 
 template <int W, bool SPREAD>
 struct Shared {
   double ops[kStages][SPREAD ? 4 : 3][kF][kNB];
   double red[kStages][4][2 * kNB];   // interpolation: per-MMA-warp partial sums of the batch
-  Meta meta[kStages];
+  uint2 meta[kStages];               // batch table entry of the stage's batch
   uint64_t full[kStages], empty[kStages];
   double coef[3 * (kKbPolyDeg + 1) * W];
   unsigned rowoff[kF * kF];
 };
 
-struct Batch {
-  long long kb;
-  int nb;
-  int zlo;
-};
-
-// Producer thread p (0..127) holds the coordinates of node kb + (p & 7) of the batch; this evaluates the
-// batch's extent (uniform across the warpgroup) and the thread's 3 (4) entries of the operand block.
-template <int W, bool SPREAD>
-__device__ __forceinline__ Batch prepare_batch(Shared<W, SPREAD> &S, int st, long long kb, long long k1,
-                                               const double (&xn)[3], double fr, double fi, int a, int bt,
-                                               const MmaParams &P, int p) {
-  const int i = p & 7, q = p >> 3;
-  const int c0 = __double2int_rd(__dmul_rn(xn[0], (double) P.n0));
-  const int c1 = __double2int_rd(__dmul_rn(xn[1], (double) P.n1));
-  const int c2 = __double2int_rd(__dmul_rn(xn[2], (double) P.n2));
-  const int u0 = wrapi(c0 - P.m, P.n0), u1 = wrapi(c1 - P.m, P.n1), u2 = wrapi(c2 - P.m, P.n2);
-  Batch B;
-  B.kb = kb;
-  B.zlo = __shfl_sync(kFull, u2, 0) & ~1;
-  const bool valid = (kb + i < k1) && (u2 <= B.zlo + 2);
-  B.nb = __popc(__ballot_sync(kFull, valid) & 0xffu);   // nodes are sorted by u2: the valid ones are a prefix
-  const bool live = i < B.nb;
-  const double y0 = 2.0 * (xn[0] * (double) P.n0 - (double) c0) - 1.0;
-  const double y1 = 2.0 * (xn[1] * (double) P.n1 - (double) c1) - 1.0;
-  const double y2 = 2.0 * (xn[2] * (double) P.n2 - (double) c2) - 1.0;
-  const int l0 = q - (u0 - P.T * a), l1 = q - (u1 - P.T * bt), l2 = (q - u2) & (kF - 1);
-  const bool ok0 = live && l0 >= 0 && l0 < W, ok1 = live && l1 >= 0 && l1 < W, ok2 = live && l2 < W;
-  const double *cf0 = S.coef + (ok0 ? l0 : 0);
-  const double *cf1 = S.coef + (kKbPolyDeg + 1) * W + (ok1 ? l1 : 0);
-  const double *cf2 = S.coef + 2 * (kKbPolyDeg + 1) * W + (ok2 ? l2 : 0);
-  double v0 = cf0[P.deg * W], v1 = cf1[P.deg * W], v2 = cf2[P.deg * W];
-#pragma unroll 4
-  for (int k = P.deg - 1; k >= 0; k--) {
-    v0 = fma(v0, y0, cf0[k * W]);
-    v1 = fma(v1, y1, cf1[k * W]);
-    v2 = fma(v2, y2, cf2[k * W]);
-  }
-  S.ops[st][0][q][i] = ok0 ? v0 : 0.0;
-  S.ops[st][2][q][i] = ok2 ? v2 : 0.0;
-  if (SPREAD) {
-    S.ops[st][1][q][i] = ok1 ? v1 * fr : 0.0;
-    S.ops[st][SPREAD ? 3 : 0][q][i] = ok1 ? v1 * fi : 0.0;
-  } else {
-    S.ops[st][1][q][i] = ok1 ? v1 : 0.0;
-  }
-  return B;
-}
-
-// The producer warpgroup (threads 128..255): walks the unit's nodes, forms the batches, fills the ring and --
-// for interpolation -- finishes the batches the MMA warps have released (cross-warp sum, scatter to f).
+// Producer warp pw (0..3) of the CTA: batches j = pw, pw+4, ... of the unit.  Lane = (node i = lane & 7,
+// slot quarter qg = lane >> 3): 4 slots x 3 dimensions = 12 independent Horner chains per lane.
 template <int W, bool SPREAD>
 __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double *__restrict__ xt,
                                               const double2 *__restrict__ ft, const uint32_t *__restrict__ perm,
-                                              double *__restrict__ f, long long k0, long long k1, int a, int bt,
-                                              const MmaParams &P, int p) {
-  auto load_node = [&](long long kb, double (&xn)[3], double &fr, double &fi) {
-    const long long k = kb + (p & 7);
-    fr = fi = 0.0;
-    if (k < k1) {
-      xn[0] = xt[3 * k]; xn[1] = xt[3 * k + 1]; xn[2] = xt[3 * k + 2];
-      if (SPREAD) { const double2 v = ft[k]; fr = v.x; fi = v.y; }
-    } else { xn[0] = xn[1] = xn[2] = 0.0; }
-  };
-  auto finalize = [&](int st) {   // interpolation: batch in stage st has been released by all MMA warps
-    if (!SPREAD && p < 2 * kNB) {
-      const Meta mt = S.meta[st];
-      if ((p >> 1) < mt.nb) {
-        const double v = S.red[st][0][p] + S.red[st][1][p] + S.red[st][2][p] + S.red[st][3][p];
-        f[2 * (size_t) perm[mt.kb + (p >> 1)] + (p & 1)] = v;
+                                              double *__restrict__ f, const uint2 *__restrict__ table,
+                                              int nbat, int a, int bt, const MmaParams &P, int pw, int lane) {
+  const int i = lane & 7, qg = lane >> 3;
+  auto finalize = [&](int st) {   // interpolation: the batch in stage st has been released by all MMA warps
+    if (!SPREAD) {
+      const uint2 mt = S.meta[st];
+      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) {
+        const double v = S.red[st][0][lane] + S.red[st][1][lane] + S.red[st][2][lane] + S.red[st][3][lane];
+        f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = v;
       }
+      __syncwarp();
     }
-    __syncwarp();
   };
-  double xn[3], fr, fi;
-  load_node(k0, xn, fr, fi);
-  long long kb = k0;
-  int j = 0;
-  for (;; j++) {
+  auto load_nodes = [&](uint2 mt, double &xv, double &fv) {
+    const int nb = bt_nb(mt);
+    xv = (lane < 3 * nb) ? xt[3 * (size_t) mt.x + lane] : 0.0;
+    if (SPREAD) fv = (lane < 2 * nb) ? reinterpret_cast<const double *>(ft)[2 * (size_t) mt.x + lane] : 0.0;
+  };
+  if (pw >= nbat) return;
+  uint2 mt = table[pw], mt_next = make_uint2(0, 0);
+  double xv, fv = 0.0, xv_next = 0.0, fv_next = 0.0;
+  load_nodes(mt, xv, fv);
+  if (pw + 4 < nbat) mt_next = table[pw + 4];
+  for (int j = pw; j < nbat; j += 4) {
     const int st = j % kStages;
+    // prefetch: nodes of this warp's next batch, table entry of the one after
+    uint2 mt_next2 = make_uint2(0, 0);
+    if (j + 4 < nbat) load_nodes(mt_next, xv_next, fv_next);
+    if (j + 8 < nbat) mt_next2 = table[j + 8];
     if (j >= kStages) {
       mbar_wait(&S.empty[st], ((j / kStages) - 1) & 1);
       finalize(st);
     }
-    const Batch B = prepare_batch<W, SPREAD>(S, st, kb, k1, xn, fr, fi, a, bt, P, p);
-    kb = B.kb + B.nb;
-    const bool more = kb < k1;
-    if (p == 0) {
-      Meta mt;
-      mt.kb = B.kb; mt.nb = B.nb; mt.zlo = B.zlo; mt.last = more ? 0 : 1; mt.pad = 0;
-      S.meta[st] = mt;
+    const int nb = bt_nb(mt);
+    const bool live = i < nb;
+    double fr = 0.0, fi = 0.0;
+    if (SPREAD) { fr = __shfl_sync(kFull, fv, 2 * i); fi = __shfl_sync(kFull, fv, 2 * i + 1); }
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const double x = __shfl_sync(kFull, xv, 3 * i + t);
+      const int nt = t == 0 ? P.n0 : t == 1 ? P.n1 : P.n2;
+      const int c = __double2int_rd(__dmul_rn(x, (double) nt));
+      const int u = wrapi(c - P.m, nt);
+      const double y = 2.0 * (x * (double) nt - (double) c) - 1.0;
+      const int lo = t == 0 ? u - P.T * a : t == 1 ? u - P.T * bt : u;   // psi_t[l] goes to slot (lo + l) & 15
+      const double *cft = S.coef + t * (kKbPolyDeg + 1) * W;
+      double v[4];
+      int off[4];
+      unsigned okm = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int l = (4 * qg + r - lo) & (kF - 1);
+        const bool ok = live && l < W;
+        okm |= (ok ? 1u : 0u) << r;
+        off[r] = ok ? l : 0;
+        v[r] = cft[P.deg * W + off[r]];
+      }
+#pragma unroll 2
+      for (int k = P.deg - 1; k >= 0; k--) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) v[r] = fma(v[r], y, cft[k * W + off[r]]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int q = 4 * qg + r;
+        const double val = ((okm >> r) & 1u) ? v[r] : 0.0;
+        if (SPREAD && t == 1) {
+          S.ops[st][1][q][i] = val * fr;
+          S.ops[st][SPREAD ? 3 : 0][q][i] = val * fi;
+        } else {
+          S.ops[st][t][q][i] = val;
+        }
+      }
     }
-    if (more) load_node(kb, xn, fr, fi);
-    mbar_arrive(&S.full[st]);
-    if (!more) break;
+    if (lane == 0) S.meta[st] = mt;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.full[st]);
+    mt = mt_next; mt_next = mt_next2;
+    xv = xv_next; fv = fv_next;
   }
   if (!SPREAD) {
-    for (int jj = (j >= kStages ? j - kStages + 1 : 0); jj <= j; jj++) {
+    for (int jj = pw; jj < nbat; jj += 4) {
+      if (jj + kStages < nbat) continue;   // finished in the loop, when the stage was refilled
       const int st = jj % kStages;
       mbar_wait(&S.empty[st], (jj / kStages) & 1);
       finalize(st);
@@ -265,8 +313,10 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   const int tid = threadIdx.x;                                                                        \
   const int n2 = P.n2;                                                                                \
   const long long unit = blockIdx.x;                                                                  \
-  const long long k0 = unit_start[unit], k1 = unit_start[unit + 1];                                   \
-  if (k0 == k1) return;                                                                               \
+  const uint32_t b0 = batch_start[unit];                                                              \
+  const int nbat = (int) (batch_start[unit + 1] - b0);                                                \
+  if (nbat == 0) return;                                                                              \
+  table += b0;                                                                                        \
   const int tile = (int) (unit / P.zseg);                                                             \
   const int a = tile / P.NT1, bt = tile - a * P.NT1;                                                  \
   for (int i = tid; i < 3 * (kKbPolyDeg + 1) * W; i += 256) S.coef[i] = poly[i];                      \
@@ -275,13 +325,13 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
     S.rowoff[tid] = (unsigned) ((wrapi(T * a + l0, P.n0) * (long long) P.n1 + wrapi(T * bt + l1, P.n1)) * n2); \
   }                                                                                                   \
   if (tid == 0) {                                                                                     \
-    for (int st = 0; st < kStages; st++) { mbar_init(&S.full[st], 128); mbar_init(&S.empty[st], 4); } \
+    for (int st = 0; st < kStages; st++) { mbar_init(&S.full[st], 1); mbar_init(&S.empty[st], 4); }   \
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                                \
   }                                                                                                   \
   __syncthreads();                                                                                    \
   if (tid >= 128) {                                                                                   \
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));                             \
-    producer_loop<W, SPREADV>(S, xt, ft, perm, f, k0, k1, a, bt, P, tid - 128);                       \
+    producer_loop<W, SPREADV>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31);   \
     return;                                                                                           \
   }                                                                                                   \
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
@@ -296,7 +346,8 @@ template <int W>
 __global__ void __launch_bounds__(256, 2)
 interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
                   const uint32_t *__restrict__ perm, double *__restrict__ f,
-                  const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+                  const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                  const double *__restrict__ poly, MmaParams P) {
   const double2 *const ft = nullptr;
   NFFTCU_MMA_PROLOGUE(false)
 
@@ -344,11 +395,13 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
     }
   };
 
-  for (int j = 0;; j++) {
+  uint2 e_next = table[0];
+  for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
-    mbar_wait(&S.full[st], (j / kStages) & 1);
-    const int zlo = S.meta[st].zlo, last = S.meta[st].last;
+    const int zlo = bt_zlo(e_next);
+    if (j + 1 < nbat) e_next = table[j + 1];   // lands during this batch: the next window base
     if (zlo != zwin) advance_to(zlo);
+    mbar_wait(&S.full[st], (j / kStages) & 1);
 
     // ---- T = G * psi2, weighted row sums
     double bf[4];
@@ -377,15 +430,9 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
       accr0 = fma(wb0, c[1][0][0], accr0); accr1 = fma(wb1, c[1][0][1], accr1);
       acci0 = fma(wb0, c[1][1][0], acci0); acci1 = fma(wb1, c[1][1][1], acci1);
     }
-    // the window registers are free again: if the next batch is already in the ring, slide the window
-    // now, so that the refill loads fly while this batch is being reduced
-    if (!last) {
-      const int s1 = (j + 1) % kStages;
-      if (mbar_test(&S.full[s1], ((j + 1) / kStages) & 1)) {
-        const int z1 = S.meta[s1].zlo;
-        if (z1 != zwin) advance_to(z1);
-      }
-    }
+    // the window registers are free again: slide the window to the next batch now, so that the refill
+    // loads fly while this batch is being reduced
+    if (j + 1 < nbat && bt_zlo(e_next) != zwin) advance_to(bt_zlo(e_next));
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
       accr0 += __shfl_xor_sync(kFull, accr0, o);
@@ -399,7 +446,6 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.empty[st]);
-    if (last) break;
   }
 }
 
@@ -411,14 +457,14 @@ constexpr int kStgRow = 9;   // staging row pitch in 16-byte cells: 8 cells + 1 
 template <int W, int FLUSH>
 __global__ void __launch_bounds__(256, 2)
 spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const double2 *__restrict__ ft,
-                  const uint32_t *__restrict__ unit_start, const double *__restrict__ poly, MmaParams P) {
+                  const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                  const double *__restrict__ poly, MmaParams P) {
   const uint32_t *const perm = nullptr;
   double *const f = nullptr;
   NFFTCU_MMA_PROLOGUE(true)
   // staging: [buffer][warp][64 rows][kStgRow] double2 behind the Shared block
   double2 *const stg_base = reinterpret_cast<double2 *>(smem_raw + ((sizeof(Shared<W, true>) + 127) & ~(size_t) 127));
-  double2 *const stg_w = stg_base + (size_t) warp * 64 * kStgRow;   // + buf * 4*64*kStgRow
-  constexpr int kStgBuf = 4 * 64 * kStgRow;
+  double2 *const stg_w = stg_base + (size_t) warp * 64 * kStgRow;
 
   double C[8][2][2][2];   // [group][re/im][n-tile][col]: accumulator of pencil (group, nr), slot 8*nt + 2*kq + col
 #pragma unroll
@@ -431,12 +477,17 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
   // staging state (uniform across the warp)
   int sblk = -1;      // 8-cell block (wrapped z >> 3) being staged, -1: none
   int snext = 0;      // next pair position (0,2,4,6) of the block that has not been written
-  int sbuf = 0;
+  bool sbusy = false; // the TMA unit may still be reading the staging rows (last flush not waited for)
   double *const Gd = reinterpret_cast<double *>(G);
 
   auto stage_store = [&](int pos, bool zero, int nt) {   // pair position pos (even) of the staged block
+    if (sbusy) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      sbusy = false;
+    }
     if (kq == (pos >> 1)) {
-      double2 *dst = stg_w + (size_t) sbuf * kStgBuf + (size_t) nr * kStgRow + pos;
+      double2 *dst = stg_w + (size_t) nr * kStgRow + pos;
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         double2 v0 = make_double2(0.0, 0.0), v1 = v0;
@@ -458,16 +509,13 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
       const int row = 2 * lane + rr;   // warp-local row = g*8 + pencil
       const int g = row >> 3, pn = row & 7;
       const unsigned off = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + pn];
-      const double2 *src = stg_w + (size_t) sbuf * kStgBuf + (size_t) row * kStgRow;
+      const double2 *src = stg_w + (size_t) row * kStgRow;
       double2 *dst = G + off + 8 * sblk;
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;"
                    ::"l"(dst), "r"(smem_addr(src)) : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    sbuf ^= 1;
-    // the buffer we switch to was handed over two flushes ago: wait until the TMA unit has read it
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
+    sbusy = true;   // waited for before the rows are written again, normally a batch or more later
     sblk = -1;
     snext = 0;
   };
@@ -508,10 +556,11 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
   };
 
   int zwin = -1;
-  for (int j = 0;; j++) {
+  uint2 e_next = table[0];
+  for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
-    mbar_wait(&S.full[st], (j / kStages) & 1);
-    const int zlo = S.meta[st].zlo, last = S.meta[st].last;
+    const int zlo = bt_zlo(e_next);
+    if (j + 1 < nbat) e_next = table[j + 1];
     // ---- slide the window to zlo: the cells below it are final
     if (zwin < 0) zwin = zlo;
     if (zlo != zwin) {
@@ -520,6 +569,7 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
       zwin = zlo;
     }
     // ---- G += (psi0 psi1 f) * psi2
+    mbar_wait(&S.full[st], (j / kStages) & 1);
     double bf[2][2];   // [n-tile][k-step]
 #pragma unroll
     for (int nt = 0; nt < 2; nt++)
@@ -557,7 +607,6 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
         }
       }
     }
-    if (last) break;
   }
   for (int zp = zwin; zp < zwin + kF; zp += 2) retire_pair(zp);
   if (FLUSH == 1) {
@@ -588,7 +637,7 @@ MmaParams make_params(const nfftcu_ctx *c) {
 template <int W, int FLUSH>
 size_t spread_smem() {
   size_t b = (sizeof(Shared<W, true>) + 127) & ~(size_t) 127;
-  if (FLUSH == 1) b += sizeof(double2) * 2 * 4 * 64 * kStgRow;
+  if (FLUSH == 1) b += sizeof(double2) * 4 * 64 * kStgRow;
   return b;
 }
 
@@ -601,7 +650,8 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     const size_t smem = sizeof(Shared<W, false>);
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     interp_mma_kernel<W><<<grid, 256, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
-                                                         (double *) f_out, c->bin_start, poly, P);
+                                                         (double *) f_out, c->mma_batch_start,
+                                                         (const uint2 *) c->mma_batches, poly, P);
     c->launches++;
   } else {
     const int kb = 256;
@@ -612,12 +662,14 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
       const size_t smem = spread_smem<W, 1>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       spread_mma_kernel<W, 1><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
-                                                              c->bin_start, poly, P);
+                                                              c->mma_batch_start, (const uint2 *) c->mma_batches,
+                                                              poly, P);
     } else {
       const size_t smem = spread_smem<W, 0>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       spread_mma_kernel<W, 0><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
-                                                              c->bin_start, poly, P);
+                                                              c->mma_batch_start, (const uint2 *) c->mma_batches,
+                                                              poly, P);
     }
     c->launches += 2;
   }
@@ -682,6 +734,31 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   mma_unit_bounds_kernel<<<(unsigned) ((units + 1 + kb - 1) / kb), kb, 0, c->stream>>>(
       (const uint64_t *) c->tile_keys, c->bin_start, units, M, P);
   c->launches++;
+  // batch table: count per unit, scan, fill
+  if (c->mma_units != units) {
+    if (c->mma_batch_start) cudaFree(c->mma_batch_start);
+    if (c->mma_counts) cudaFree(c->mma_counts);
+    c->mma_batch_start = c->mma_counts = nullptr;
+    NFFTCU_CUDA(cudaMalloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    NFFTCU_CUDA(cudaMalloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
+    c->mma_units = units;
+  }
+  const unsigned wgrid = (unsigned) ((units * 32 + kb - 1) / kb);
+  mma_batches_kernel<false><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, c->mma_counts,
+                                                         nullptr, nullptr, units, P);
+  mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_batch_start, units);
+  uint32_t total = 0;
+  NFFTCU_CUDA(cudaMemcpyAsync(&total, c->mma_batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  if ((long long) total > c->mma_batch_cap) {
+    if (c->mma_batches) cudaFree(c->mma_batches);
+    c->mma_batches = nullptr;
+    c->mma_batch_cap = (long long) total + total / 8 + 1024;
+    NFFTCU_CUDA(cudaMalloc(&c->mma_batches, sizeof(uint2) * (size_t) c->mma_batch_cap));
+  }
+  mma_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
+                                                        c->mma_batch_start, (uint2 *) c->mma_batches, units, P);
+  c->launches += 3;
   NFFTCU_CUDA(cudaGetLastError());
   c->mma_ready = true;
   return NFFTCU_OK;
