@@ -70,8 +70,10 @@ __device__ __forceinline__ int wrapi(int v, int n) {
   return v;
 }
 
+// volatile: keeps the issue order written in the kernels (independent accumulators interleaved; ptxas
+// otherwise schedules the k-steps of one accumulator back to back and waits out the 26-cycle latency)
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
@@ -199,6 +201,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
 // ops[v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
 // (spreading), 2: psi2 in circular window slots, 3: psi1*f.im (spreading only)
 constexpr int kStages = 8;
+constexpr int kCoefK = kKbPolyDeg + 2;   // powers 0..17 per tap: rows of 144 bytes, (even, odd) pairs 16-byte aligned
 constexpr int kMmaRegs = 200, kProdRegs = 56;   // setmaxnreg: 128 * (200 + 56) = 2 CTAs per SM
 
 template <int W, bool SPREAD>
@@ -207,7 +210,7 @@ struct Shared {
   double red[kStages][4][2 * kNB];   // interpolation: per-MMA-warp partial sums of the batch
   uint2 meta[kStages];               // batch table entry of the stage's batch
   uint64_t full[kStages], empty[kStages];
-  double coef[3 * (kKbPolyDeg + 1) * W];
+  double coef[3 * W * kCoefK];       // [t][tap][power], powers padded with zeros to kCoefK
   unsigned rowoff[kF * kF];
 };
 
@@ -261,23 +264,35 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
       const int u = wrapi(c - P.m, nt);
       const double y = 2.0 * (x * (double) nt - (double) c) - 1.0;
       const int lo = t == 0 ? u - P.T * a : t == 1 ? u - P.T * bt : u;   // psi_t[l] goes to slot (lo + l) & 15
-      const double *cft = S.coef + t * (kKbPolyDeg + 1) * W;
-      double v[4];
+      // p(y) = E(y^2) + y O(y^2): two half-length Horner chains per entry, one 16-byte load per step
+      const double2 *cft = reinterpret_cast<const double2 *>(S.coef + t * W * kCoefK);
+      const double y2 = y * y;
+      double E[4], O[4];
       int off[4];
       unsigned okm = 0;
+      const int ptop = P.deg >> 1;
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int l = (4 * qg + r - lo) & (kF - 1);
         const bool ok = live && l < W;
         okm |= (ok ? 1u : 0u) << r;
-        off[r] = ok ? l : 0;
-        v[r] = cft[P.deg * W + off[r]];
+        off[r] = (ok ? l : 0) * (kCoefK / 2);
+        const double2 c = cft[off[r] + ptop];
+        E[r] = c.x;
+        O[r] = c.y;
       }
 #pragma unroll 2
-      for (int k = P.deg - 1; k >= 0; k--) {
+      for (int p = ptop - 1; p >= 0; p--) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) v[r] = fma(v[r], y, cft[k * W + off[r]]);
+        for (int r = 0; r < 4; r++) {
+          const double2 c = cft[off[r] + p];
+          E[r] = fma(E[r], y2, c.x);
+          O[r] = fma(O[r], y2, c.y);
+        }
       }
+      double v[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) v[r] = fma(O[r], y, E[r]);
 #pragma unroll
       for (int r = 0; r < 4; r++) {
         const int q = 4 * qg + r;
@@ -319,7 +334,10 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   table += b0;                                                                                        \
   const int tile = (int) (unit / P.zseg);                                                             \
   const int a = tile / P.NT1, bt = tile - a * P.NT1;                                                  \
-  for (int i = tid; i < 3 * (kKbPolyDeg + 1) * W; i += 256) S.coef[i] = poly[i];                      \
+  for (int i = tid; i < 3 * W * kCoefK; i += 256) {                                                   \
+    const int t = i / (W * kCoefK), l = (i / kCoefK) % W, k = i % kCoefK;                             \
+    S.coef[i] = k <= kKbPolyDeg ? poly[(t * (kKbPolyDeg + 1) + k) * W + l] : 0.0;                     \
+  }                                                                                                   \
   {                                                                                                   \
     const int l0 = tid >> 4, l1 = tid & 15;                                                           \
     S.rowoff[tid] = (unsigned) ((wrapi(T * a + l0, P.n0) * (long long) P.n1 + wrapi(T * bt + l1, P.n1)) * n2); \
