@@ -196,6 +196,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
       "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
+// producer-side wait: the producers run up to kStages batches ahead and mostly wait; back off between polls
+// so that the polling loop does not take issue slots from the MMA warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, int parity) {
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+
 // ---- shared memory ----------------------------------------------------------------------------------------
 // A ring of kStages operand blocks; producer warp w fills the stages of batches j = w (mod 4).
 // ops[v][slot][node]: v = 0: psi0 placed in the footprint, 1: psi1 (interpolation) or psi1*f.re
@@ -207,7 +223,7 @@ constexpr int kMmaRegs = 200, kProdRegs = 56;   // setmaxnreg: 128 * (200 + 56) 
 template <int W, bool SPREAD>
 struct Shared {
   double ops[kStages][SPREAD ? 4 : 3][kF][kNB];
-  double red[kStages][4][2 * kNB];   // interpolation: per-MMA-warp partial sums of the batch
+  double red[kStages][SPREAD ? 1 : 4][8][4][4];   // interpolation: [MMA warp][nr][kq][re0, im0, re1, im1] partial sums
   uint2 meta[kStages];               // batch table entry of the stage's batch
   uint64_t full[kStages], empty[kStages];
   double coef[3 * W * kCoefK];       // [t][tap][power], powers padded with zeros to kCoefK
@@ -224,11 +240,16 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   const int i = lane & 7, qg = lane >> 3;
   auto finalize = [&](int st) {   // interpolation: the batch in stage st has been released by all MMA warps
     if (!SPREAD) {
+      // output o = 2*node + comp lives at [w][nr][node >> 1][2*(node & 1) + comp] = 16 consecutive doubles per
+      // (w, nr); lanes o and o+16 each sum 16 of the 32 partials
       const uint2 mt = S.meta[st];
-      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) {
-        const double v = S.red[st][0][lane] + S.red[st][1][lane] + S.red[st][2][lane] + S.red[st][3][lane];
-        f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = v;
-      }
+      const double *rp = &S.red[st][0][0][0][0] + (lane & 15) + (lane >> 4) * 16 * 16;
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; q += 2) { v0 += rp[q * 16]; v1 += rp[(q + 1) * 16]; }
+      v0 += v1;
+      v0 += __shfl_xor_sync(kFull, v0, 16);
+      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = v0;
       __syncwarp();
     }
   };
@@ -249,7 +270,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
     if (j + 4 < nbat) load_nodes(mt_next, xv_next, fv_next);
     if (j + 8 < nbat) mt_next2 = table[j + 8];
     if (j >= kStages) {
-      mbar_wait(&S.empty[st], ((j / kStages) - 1) & 1);
+      mbar_wait_sleep(&S.empty[st], ((j / kStages) - 1) & 1);
       finalize(st);
     }
     const int nb = bt_nb(mt);
@@ -264,19 +285,18 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
       const int u = wrapi(c - P.m, nt);
       const double y = 2.0 * (x * (double) nt - (double) c) - 1.0;
       const int lo = t == 0 ? u - P.T * a : t == 1 ? u - P.T * bt : u;   // psi_t[l] goes to slot (lo + l) & 15
-      // p(y) = E(y^2) + y O(y^2): two half-length Horner chains per entry, one 16-byte load per step
+      // p_l(y) = E_l(y^2) + y O_l(y^2): two half-length Horner chains, one 16-byte load per step.  The window is
+      // even, so the mirrored tap is p_{W-1-l}(y) = p_l(-y) = E_l - y O_l: a lane evaluates taps l = 2qg, 2qg+1
+      // (< W/2) and writes both; the lanes whose l >= W/2 write the 16-W zero slots behind the taps.
       const double2 *cft = reinterpret_cast<const double2 *>(S.coef + t * W * kCoefK);
       const double y2 = y * y;
-      double E[4], O[4];
-      int off[4];
-      unsigned okm = 0;
+      double E[2], O[2];
+      int off[2];
       const int ptop = P.deg >> 1;
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int l = (4 * qg + r - lo) & (kF - 1);
-        const bool ok = live && l < W;
-        okm |= (ok ? 1u : 0u) << r;
-        off[r] = (ok ? l : 0) * (kCoefK / 2);
+      for (int r = 0; r < 2; r++) {
+        const int l = 2 * qg + r;
+        off[r] = (l < W / 2 ? l : 0) * (kCoefK / 2);
         const double2 c = cft[off[r] + ptop];
         E[r] = c.x;
         O[r] = c.y;
@@ -284,24 +304,30 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
 #pragma unroll 2
       for (int p = ptop - 1; p >= 0; p--) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 2; r++) {
           const double2 c = cft[off[r] + p];
           E[r] = fma(E[r], y2, c.x);
           O[r] = fma(O[r], y2, c.y);
         }
       }
-      double v[4];
 #pragma unroll
-      for (int r = 0; r < 4; r++) v[r] = fma(O[r], y, E[r]);
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int q = 4 * qg + r;
-        const double val = ((okm >> r) & 1u) ? v[r] : 0.0;
+      for (int r = 0; r < 2; r++) {
+        const int l = 2 * qg + r;
+        const bool tap = l < W / 2;
+        const int zz = l - W / 2;
+        if (!tap && 2 * zz >= kF - W) continue;
+        const int sa = (tap ? lo + l : lo + W + 2 * zz) & (kF - 1);
+        const int sb = (tap ? lo + W - 1 - l : lo + W + 2 * zz + 1) & (kF - 1);
+        const double yo = y * O[r];
+        const double va = (tap && live) ? E[r] + yo : 0.0, vb = (tap && live) ? E[r] - yo : 0.0;
         if (SPREAD && t == 1) {
-          S.ops[st][1][q][i] = val * fr;
-          S.ops[st][SPREAD ? 3 : 0][q][i] = val * fi;
+          S.ops[st][1][sa][i] = va * fr;
+          S.ops[st][1][sb][i] = vb * fr;
+          S.ops[st][SPREAD ? 3 : 0][sa][i] = va * fi;
+          S.ops[st][SPREAD ? 3 : 0][sb][i] = vb * fi;
         } else {
-          S.ops[st][t][q][i] = val;
+          S.ops[st][t][sa][i] = va;
+          S.ops[st][t][sb][i] = vb;
         }
       }
     }
@@ -315,7 +341,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
     for (int jj = pw; jj < nbat; jj += 4) {
       if (jj + kStages < nbat) continue;   // finished in the loop, when the stage was refilled
       const int st = jj % kStages;
-      mbar_wait(&S.empty[st], (jj / kStages) & 1);
+      mbar_wait_sleep(&S.empty[st], (jj / kStages) & 1);
       finalize(st);
     }
   }
@@ -355,9 +381,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
   const int lane = tid & 31, warp = tid >> 5;                                                         \
   const int kq = lane & 3, nr = lane >> 2;                                                            \
-  unsigned rowoff[8];                                                                                 \
-  _Pragma("unroll") for (int g = 0; g < 8; g++)                                                       \
-    rowoff[g] = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + nr];
+  const unsigned *const rowoff_s = S.rowoff + 4 * warp * kF + nr;   /* group g: [(g >> 1) * kF + 8 * (g & 1)] */
 
 // ---- interpolation ------------------------------------------------------------------------------------
 template <int W>
@@ -379,7 +403,7 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
       if (z >= n2) z -= n2;
 #pragma unroll
       for (int g = 0; g < 8; g++) {
-        const double2 v = G[rowoff[g] + z];
+        const double2 v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
         A[g][0][s] = v.x;
         A[g][1][s] = v.y;
       }
@@ -394,7 +418,7 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
 #define NFFTCU_LOADPAIR(SL)                                                                     \
         case SL:                                                                                \
           _Pragma("unroll") for (int g = 0; g < 8; g++) {                                       \
-            const double2 v = G[rowoff[g] + z];                                                 \
+            const double2 v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];                                                 \
             A[g][0][SL] = v.x;                                                                  \
             A[g][1][SL] = v.y;                                                                  \
           }                                                                                     \
@@ -451,17 +475,9 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
     // the window registers are free again: slide the window to the next batch now, so that the refill
     // loads fly while this batch is being reduced
     if (j + 1 < nbat && bt_zlo(e_next) != zwin) advance_to(bt_zlo(e_next));
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      accr0 += __shfl_xor_sync(kFull, accr0, o);
-      accr1 += __shfl_xor_sync(kFull, accr1, o);
-      acci0 += __shfl_xor_sync(kFull, acci0, o);
-      acci1 += __shfl_xor_sync(kFull, acci1, o);
-    }
-    if (nr == 0) {
-      *reinterpret_cast<double2 *>(&S.red[st][warp][4 * kq]) = make_double2(accr0, acci0);
-      *reinterpret_cast<double2 *>(&S.red[st][warp][4 * kq + 2]) = make_double2(accr1, acci1);
-    }
+    // per-lane partial sums go to the ring; the producer warp that refills the stage adds them up
+    *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][0]) = make_double2(accr0, acci0);
+    *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][2]) = make_double2(accr1, acci1);
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.empty[st]);
   }
@@ -558,7 +574,7 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         if (FLUSH == 0) {
-          double *dst = Gd + 2 * ((size_t) rowoff[g] + zw);
+          double *dst = Gd + 2 * ((size_t) rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw);
           if (nt == 0) {
             atomicAdd(dst, C[g][0][0][0]); atomicAdd(dst + 1, C[g][1][0][0]);
             atomicAdd(dst + 2, C[g][0][0][1]); atomicAdd(dst + 3, C[g][1][0][1]);
@@ -675,7 +691,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     const int kb = 256;
     mma_gather_f_kernel<<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
         (const double2 *) f_in, c->tile_perm, (double2 *) c->f_tile, c->M);
-    const bool bulk = (P.n2 % 8 == 0) && c->opt_b_flush != 1;
+    const bool bulk = (P.n2 % 8 == 0) && c->opt_b_flush == 2;
     if (bulk) {
       const size_t smem = spread_smem<W, 1>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

@@ -411,7 +411,7 @@ def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
     variants = [("tile", 0, 0, 0), ("pencil", 2, 0, 0), ("pencil+table", 2, 1, 0), ("generic", 1, 0, 0),
                 ("generic+table", 1, 1, 0)]
     if precision == "double":
-        variants += [("mma", 3, 0, 0), ("mma+red", 3, 0, 1)]
+        variants += [("mma", 3, 0, 0), ("mma+red", 3, 0, 1), ("mma+tma", 3, 0, 2)]
     for label, kernel, table, flush in variants:
         eng = cabi.Engine(N, n, m, M, precision=precision)
         eng.set_option(cabi.OPT_B_KERNEL, kernel)
