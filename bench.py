@@ -41,6 +41,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# FP64 tensor-core (DMMA) rate of this pool's B200s, measured with tools/microbench4.cu
+# (profiles/r01w_microbench_dmma.txt: 36.9 TFLOP/s = 64 FMA/clk/SM at 1.965 GHz, same pipe as DFMA).
+# MEASURED_PEAKS.json carries only HBM GB/s and bf16 TF/s; a key "fp64_tflops" there would override this.
+FP64_TENSOR_TFLOPS = 36.9
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        v = json.load(open(p)).get("fp64_tflops")
+        if v:
+            return float(v), "measured (MEASURED_PEAKS.json fp64_tflops)"
+    return FP64_TENSOR_TFLOPS, ("FP64 DMMA rate measured with tools/microbench4.cu on this pool's B200 "
+                                "(profiles/r01w_microbench_dmma.txt); MEASURED_PEAKS.json has no FP64 entry")
+
+
 def byte_model(cfg, csize):
     """SURVEY 8d model v1.  C = complex bytes, R = C/2."""
     Cb, Rb, d = csize, csize // 2, cfg["d"]
@@ -213,14 +229,17 @@ def run_ours(args, rank, world, local_rank):
     t_nodes = time.perf_counter() - t0
 
     stage = np.zeros((2, 3))
+    kern = np.zeros(2)    # main B / B^T kernel launch durations (CUDA events on the plan's stream)
 
     def step(record):
         sp.trafo(fh_d, f_out)
         if record:
             stage[0] += eng.stage_times()
+            kern[0] += eng.b_kernel_time()
         sp.adjoint(f_d, fh_out)
         if record:
             stage[1] += eng.stage_times()
+            kern[1] += eng.b_kernel_time()
 
     for _ in range(args.warmup):
         step(False)
@@ -249,6 +268,7 @@ def run_ours(args, rank, world, local_rank):
     ms_step = float(t.item()) / args.steps
     value = world * cfg["M"] / (ms_step * 1e-3)
     stage /= args.steps
+    kern /= args.steps
 
     # ---- e2e: reference-facing plan API on pinned host buffers (H2D/D2H inside the timed region) ----
     eng.set_option(cabi.OPT_TIMING, 0)
@@ -302,15 +322,35 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = peaks()
         bm = byte_model(cfg, csize)
-        t_spread, t_interp = stage[1][2], stage[0][2]
-        dom = "spread (B^T)" if t_spread >= t_interp else "interp (B)"
+        # dominant kernel: the B or B^T launch itself (stage time minus memset / gather when the kernel timer ran)
+        t_spread = kern[1] if kern[1] > 0 else stage[1][2]
+        t_interp = kern[0] if kern[0] > 0 else stage[0][2]
+        spread_dom = t_spread >= t_interp
         t_dom = max(t_spread, t_interp)
-        a_dom = bm["spread"] if t_spread >= t_interp else bm["interp"]
-        achieved = a_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else None
+        a_dom = bm["spread"] if spread_dom else bm["interp"]
+        hbm_ach = a_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("spread" if t_spread >= t_interp else "interp")
+            traffic = json.load(open(tp)).get("%s:%d" % (prec, cfg["M"]), {}).get("spread" if spread_dom else "interp")
+        dmma = prec == "double" and args.b_kernel in (0, 3) and cfg["m"] <= 6
+        taps = (2 * cfg["m"] + 2) ** cfg["d"]
+        flops = 4.0 * taps * cfg["M"]      # per tap: complex value x real weight = 2 FMA = 4 flops
+        if dmma:
+            pk, pk_src = fp64_peak()
+            tf = flops / (t_dom * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": ("spread_mma_kernel (B^T)" if spread_dom else "interp_mma_kernel (B)"),
+                    "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk, "traffic": traffic,
+                    "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": a_dom,
+                    "launch_ms": t_dom, "peak_source": pk_src,
+                    "note": "FP64 tensor cores (DMMA m8n8k4): useful flops only, zero padding of the 16^3 window "
+                            "(67 % lane efficiency) not counted",
+                    "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak,
+                            "peak_source": peak_src}}
+        else:
+            roof = {"bound": "hbm", "kernel": "spread (B^T)" if spread_dom else "interp (B)", "achieved": hbm_ach,
+                    "peak": peak, "unit": "GB/s", "frac": (hbm_ach / peak) if hbm_ach else None, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": a_dom, "launch_ms": t_dom, "peak_source": peak_src}
         pipe_ach = bm["pair"] / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
@@ -323,9 +363,8 @@ def run_ours(args, rank, world, local_rank):
                        "nodes_setup_s": t_nodes},
             "stage_ms": {"trafo": {"D": stage[0][0], "F": stage[0][1], "B": stage[0][2]},
                          "adjoint": {"DT": stage[1][0], "F": stage[1][1], "BT": stage[1][2]}},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": a_dom, "launch_ms": t_dom, "peak_source": peak_src},
+            "kernel_ms": {"B": float(kern[0]), "BT": float(kern[1])},
+            "roofline": roof,
             "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s",
                                   "frac": pipe_ach / peak, "algorithmic_bytes_per_step": bm["pair"]},
             "e2e": {"value": world * cfg["M"] / te, "unit": "points/s", "h2d_bytes_per_step": h2d,

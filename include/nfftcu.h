@@ -125,6 +125,9 @@ int nfftcu_sync(nfftcu_ctx *ctx);
 /* milliseconds of the last transform's D, F, B(^T) stages -> plan member MEASURE_TIME_t
  * (include/nfft3.h:139); valid when NFFTCU_OPT_TIMING is on */
 int nfftcu_stage_times(nfftcu_ctx *ctx, float ms[3]);
+/* duration of the main interpolation / spreading kernel launch of the last transform (CUDA events on the
+ * plan's stream; 0 when NFFTCU_OPT_TIMING is off or the generic kernels ran): the roofline numerator of bench.py */
+int nfftcu_b_kernel_time(nfftcu_ctx *ctx, float *ms);
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 int64_t nfftcu_launch_count(nfftcu_ctx *ctx);
 

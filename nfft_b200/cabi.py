@@ -26,7 +26,7 @@ SYMBOLS = (
     "nfftcu_trafo_direct", "nfftcu_adjoint_direct", "nfftcu_trafo_dev", "nfftcu_adjoint_dev",
     "nfftcu_trafo_direct_dev", "nfftcu_adjoint_direct_dev", "nfftcu_stage_D", "nfftcu_stage_F",
     "nfftcu_stage_B", "nfftcu_stage_BT", "nfftcu_stage_DT", "nfftcu_grid_ptr", "nfftcu_set_option",
-    "nfftcu_set_stream", "nfftcu_get_stream", "nfftcu_sync", "nfftcu_stage_times",
+    "nfftcu_set_stream", "nfftcu_get_stream", "nfftcu_sync", "nfftcu_stage_times", "nfftcu_b_kernel_time",
     "nfftcu_launch_count", "nfftcu_malloc_device", "nfftcu_free_device", "nfftcu_malloc_pinned",
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
 )
@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         L.nfftcu_get_stream.restype = vp
         L.nfftcu_sync.argtypes = [vp]
         L.nfftcu_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
+        L.nfftcu_b_kernel_time.argtypes = [vp, C.POINTER(C.c_float)]
         L.nfftcu_launch_count.argtypes = [vp]
         L.nfftcu_launch_count.restype = i64
         L.nfftcu_malloc_device.argtypes = [C.POINTER(vp), C.c_size_t, ci]
@@ -148,6 +149,11 @@ class Engine:
         ms = (C.c_float * 3)()
         _ck(self.L.nfftcu_stage_times(self.ctx, ms))
         return [float(v) for v in ms]
+
+    def b_kernel_time(self) -> float:
+        ms = C.c_float(0)
+        _ck(self.L.nfftcu_b_kernel_time(self.ctx, C.byref(ms)))
+        return float(ms.value)
 
     # ---- nodes ----
     def set_nodes(self, x: np.ndarray):

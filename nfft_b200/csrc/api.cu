@@ -73,6 +73,8 @@ struct StageTimer {
     c->stage_ms[s0] = a;
     c->stage_ms[s1] = b;
     c->stage_ms[s2] = d;
+    c->bkernel_ms = 0.f;
+    if (cudaEventQuery(c->evk[1]) == cudaSuccess) cudaEventElapsedTime(&c->bkernel_ms, c->evk[0], c->evk[1]);
   }
 };
 
@@ -246,6 +248,7 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
   NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   for (int i = 0; i < 4; i++) NFFTCU_CUDA(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 2; i++) NFFTCU_CUDA(cudaEventCreate(&c->evk[i]));
 
   // c_t[k+N/2] = 1/I0(m sqrt(b^2 - (2 pi k/n)^2)), k = -N/2..  (precompute_phi_hut, nfft.c:5754-5770)
   const long double two_pi = 6.283185307179586476925286766559005768394L;
@@ -294,6 +297,8 @@ int nfftcu_destroy(nfftcu_ctx *c) {
     if (p) cudaFree(p);
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (c->evk[i]) cudaEventDestroy(c->evk[i]);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return NFFTCU_OK;
@@ -513,6 +518,12 @@ int nfftcu_sync(nfftcu_ctx *c) {
 int nfftcu_stage_times(nfftcu_ctx *c, float ms[3]) {
   NFFTCU_TRY(check_ctx(c));
   for (int i = 0; i < 3; i++) ms[i] = c->stage_ms[i];
+  return NFFTCU_OK;
+}
+
+int nfftcu_b_kernel_time(nfftcu_ctx *c, float *ms) {
+  NFFTCU_TRY(check_ctx(c));
+  *ms = c->bkernel_ms;
   return NFFTCU_OK;
 }
 

@@ -105,6 +105,8 @@ struct nfftcu_ctx_s {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evk[2] = {nullptr, nullptr};   // around the main B / B^T kernel launch (opt_timing)
+  float bkernel_ms = 0.f;
   float stage_ms[3] = {0.f, 0.f, 0.f};
   int64_t launches = 0;
 

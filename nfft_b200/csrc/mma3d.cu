@@ -683,15 +683,18 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   if (!spread) {
     const size_t smem = sizeof(Shared<W, false>);
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     interp_mma_kernel<W><<<grid, 256, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
                                                          (double *) f_out, c->mma_batch_start,
                                                          (const uint2 *) c->mma_batches, poly, P);
+    if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
     c->launches++;
   } else {
     const int kb = 256;
     mma_gather_f_kernel<<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
         (const double2 *) f_in, c->tile_perm, (double2 *) c->f_tile, c->M);
     const bool bulk = (P.n2 % 8 == 0) && c->opt_b_flush == 2;
+    if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     if (bulk) {
       const size_t smem = spread_smem<W, 1>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -705,6 +708,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
                                                               c->mma_batch_start, (const uint2 *) c->mma_batches,
                                                               poly, P);
     }
+    if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
     c->launches += 2;
   }
   NFFTCU_CUDA(cudaGetLastError());

@@ -683,8 +683,10 @@ int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   const size_t smem = Smem<T, W, true>::bytes();
   NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
   spread_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
+  if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
@@ -698,8 +700,10 @@ int launch_interp(nfftcu_ctx *c, void *f_dev, const TileParams &P) {
   const size_t smem = Smem<T, W, false>::bytes();
   NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
   interp_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (const C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
+  if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
   const int kb = 256;
   scatter_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
       (const C *) c->f_tile, c->tile_perm, (C *) f_dev, c->M);
