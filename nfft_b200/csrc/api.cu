@@ -74,7 +74,8 @@ struct StageTimer {
     c->stage_ms[s1] = b;
     c->stage_ms[s2] = d;
     c->bkernel_ms = 0.f;
-    if (cudaEventQuery(c->evk[1]) == cudaSuccess) cudaEventElapsedTime(&c->bkernel_ms, c->evk[0], c->evk[1]);
+    if (c->evk_recorded) cudaEventElapsedTime(&c->bkernel_ms, c->evk[0], c->evk[1]);
+    c->evk_recorded = false;
   }
 };
 

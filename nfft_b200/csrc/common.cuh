@@ -107,6 +107,7 @@ struct nfftcu_ctx_s {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evk[2] = {nullptr, nullptr};   // around the main B / B^T kernel launch (opt_timing)
   float bkernel_ms = 0.f;
+  bool evk_recorded = false;
   float stage_ms[3] = {0.f, 0.f, 0.f};
   int64_t launches = 0;
 

@@ -687,7 +687,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     interp_mma_kernel<W><<<grid, 256, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
                                                          (double *) f_out, c->mma_batch_start,
                                                          (const uint2 *) c->mma_batches, poly, P);
-    if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
+    if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches++;
   } else {
     const int kb = 256;
@@ -708,7 +708,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
                                                               c->mma_batch_start, (const uint2 *) c->mma_batches,
                                                               poly, P);
     }
-    if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
+    if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches += 2;
   }
   NFFTCU_CUDA(cudaGetLastError());

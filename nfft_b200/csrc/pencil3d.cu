@@ -686,7 +686,7 @@ int launch_spread(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
   spread_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
-  if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
+  if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
@@ -703,7 +703,7 @@ int launch_interp(nfftcu_ctx *c, void *f_dev, const TileParams &P) {
   if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
   interp_tile_kernel<T, W><<<grid, CF::CT, smem, c->stream>>>(
       (const C *) c->grid, (const T *) c->tile_psi, (C *) c->f_tile, c->bin_start, P);
-  if (c->opt_timing) cudaEventRecord(c->evk[1], c->stream);
+  if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
   const int kb = 256;
   scatter_f_kernel<C><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
       (const C *) c->f_tile, c->tile_perm, (C *) f_dev, c->M);

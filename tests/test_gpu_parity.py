@@ -318,10 +318,10 @@ def test_pointer_swap_and_node_refresh():
     other_f = np.zeros(M, dtype=np.complex128)
     p.x[:] = x1
     p.f_hat[:] = fh
-    own_f = p.c.f
+    own_f = C.cast(p.c.f, C.c_void_p).value                    # the address: a ctypes field read aliases the field
     p.c.f = other_f.ctypes.data_as(C.POINTER(C.c_double))      # CSWAP
     p.trafo()
-    p.c.f = own_f
+    p.c.f = C.cast(C.c_void_p(own_f), C.POINTER(C.c_double))
     assert rel_l2(other_f, o.trafo(N, n, m, x1, fh)) <= 1e-12
     v1 = np.array(p.index_x[:, 1])
     p.x[:] = x2                                                 # silent node change
