@@ -94,6 +94,13 @@ int nfftcu_get_index_x(nfftcu_ctx *ctx, int64_t *index_x_host);
  * the exact NDFT kernels when any N_t <= m or n_t <= 2m+2, as the reference does (5658-5664). */
 int nfftcu_trafo(nfftcu_ctx *ctx, const void *f_hat_host, void *f_host);
 int nfftcu_adjoint(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);
+/* The same with an unannounced node refresh, for plans without a psi flag, where the reference re-reads
+ * x on every call (nfft.c:4889, 5351): x_host is uploaded and compared with the resident nodes on a side
+ * stream while the transform already runs with the resident nodes; only when they differ are the nodes
+ * re-sorted and the transform repeated.  *changed (may be NULL) reports whether that happened, i.e.
+ * whether index_x has to be fetched again. */
+int nfftcu_trafo_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_hat_host, void *f_host, int *changed);
+int nfftcu_adjoint_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_host, void *f_hat_host, int *changed);
 /* nfft_trafo_direct / nfft_adjoint_direct (nfft.c:145-297): exact NDFT */
 int nfftcu_trafo_direct(nfftcu_ctx *ctx, const void *f_hat_host, void *f_host);
 int nfftcu_adjoint_direct(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);

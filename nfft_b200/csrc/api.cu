@@ -300,6 +300,9 @@ int nfftcu_destroy(nfftcu_ctx *c) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; i++)
     if (c->evk[i]) cudaEventDestroy(c->evk[i]);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return NFFTCU_OK;
@@ -405,6 +408,76 @@ static int host_transform(nfftcu_ctx *c, const void *in_host, void *out_host, in
   if (out_bytes) NFFTCU_CUDA(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
   return NFFTCU_OK;
+}
+
+// Transform with an unannounced node refresh (plans without a psi flag: the reference re-reads x on
+// every call, nfft.c:4889, 5351).  The upload of x and its comparison with the resident nodes run on a
+// side stream WHILE the transform runs with the resident nodes; only if the comparison reports a change
+// are the nodes re-sorted and the transform repeated.  Unchanged nodes -- every call of a solver loop --
+// cost no serial PCIe time.
+static int host_transform_refresh(nfftcu_ctx *c, const void *x_host, const void *in_host, void *out_host,
+                                  int which, int *changed_out) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  if (changed_out) *changed_out = 0;
+  const size_t xbytes = real_size(c) * (size_t) c->M * c->d;
+  if (!c->have_nodes || xbytes == 0 || c->direct_only) {
+    const int64_t before = c->nodes_version;
+    NFFTCU_TRY(nfftcu_set_nodes(c, x_host));
+    if (changed_out) *changed_out = c->nodes_version != before;
+    return host_transform(c, in_host, out_host, which);
+  }
+  if (!x_host) {
+    set_error("transform: x is NULL");
+    return NFFTCU_EINVAL;
+  }
+  NFFTCU_TRY(ensure_staging(c));
+  if (!c->side_stream) NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  if (!c->h_flag) NFFTCU_CUDA(cudaMallocHost((void **) &c->h_flag, sizeof(int)));
+  if (!c->x_stage) NFFTCU_CUDA(cudaMalloc(&c->x_stage, xbytes));
+  if (!c->diff_flag) NFFTCU_CUDA(cudaMalloc((void **) &c->diff_flag, sizeof(int)));
+  const bool forward = which == 0;
+  const size_t in_bytes = forward ? cbytes(c, c->N_total) : cbytes(c, c->M);
+  const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
+  void *in_dev = forward ? c->fhat_dev : c->f_dev;
+  void *out_dev = forward ? c->f_dev : c->fhat_dev;
+  // the side stream must not start before earlier work on the plan's stream that may still read x_stage
+  if (!c->ev_side) NFFTCU_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  NFFTCU_CUDA(cudaEventRecord(c->ev_side, c->stream));
+  NFFTCU_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
+  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->side_stream));
+  NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->side_stream));
+  {
+    const long long words = (long long) (xbytes / 4);
+    long long blocks = (words + 255) / 256;
+    if (blocks > (long long) c->sm_count * 16) blocks = (long long) c->sm_count * 16;
+    differs_kernel<<<(unsigned) blocks, 256, 0, c->side_stream>>>((const uint32_t *) c->x_stage,
+                                                                (const uint32_t *) c->x_dev, words, c->diff_flag);
+    c->launches++;
+  }
+  NFFTCU_CUDA(cudaMemcpyAsync(c->h_flag, c->diff_flag, sizeof(int), cudaMemcpyDeviceToHost, c->side_stream));
+  int r = forward ? trafo_dev_impl(c, in_dev, out_dev) : adjoint_dev_impl(c, in_dev, out_dev);
+  if (r != NFFTCU_OK) return r;
+  NFFTCU_CUDA(cudaStreamSynchronize(c->side_stream));
+  if (*c->h_flag) {   // the nodes did change: adopt them and redo the transform (its input is still on the device)
+    NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+    void *t = c->x_dev; c->x_dev = c->x_stage; c->x_stage = t;
+    NFFTCU_TRY(nodes_ready(c));
+    if (changed_out) *changed_out = 1;
+    r = forward ? trafo_dev_impl(c, in_dev, out_dev) : adjoint_dev_impl(c, in_dev, out_dev);
+    if (r != NFFTCU_OK) return r;
+  }
+  if (out_bytes) NFFTCU_CUDA(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  return NFFTCU_OK;
+}
+
+int nfftcu_trafo_refresh(nfftcu_ctx *c, const void *x_host, const void *f_hat_host, void *f_host, int *changed) {
+  return host_transform_refresh(c, x_host, f_hat_host, f_host, 0, changed);
+}
+int nfftcu_adjoint_refresh(nfftcu_ctx *c, const void *x_host, const void *f_host, void *f_hat_host, int *changed) {
+  return host_transform_refresh(c, x_host, f_host, f_hat_host, 1, changed);
 }
 
 int nfftcu_trafo(nfftcu_ctx *c, const void *f_hat_host, void *f_host) {

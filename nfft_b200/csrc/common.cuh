@@ -103,6 +103,9 @@ struct nfftcu_ctx_s {
   void *f_dev = nullptr;
 
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // node refresh overlapped with a transform (api.cu: host_transform_refresh)
+  int *h_flag = nullptr;                // pinned: result of the on-device node comparison
+  cudaEvent_t ev_side = nullptr;
   bool own_stream = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evk[2] = {nullptr, nullptr};   // around the main B / B^T kernel launch (opt_timing)

@@ -305,16 +305,37 @@ void X(precompute_one_psi)(X(plan) *ths)
 void X(trafo)(X(plan) *ths)
 {
   if (!ths->f_hat || !ths->f) X(die)("nfft_trafo: f_hat or f is NULL");
-  nodes_for_transform(ths);
-  check_cu(nfftcu_trafo(ctx_of(ths), ths->f_hat, ths->f));
+  if (!(ths->flags & NODE_BOUND_FLAGS))
+  {
+    /* no psi flag: x may have changed without notice; refresh it overlapped with the transform */
+    int changed = 0;
+    if (ths->M_total > 0 && !ths->x) X(die)("Member x not initialized.");
+    check_cu(nfftcu_trafo_refresh(ctx_of(ths), ths->x, ths->f_hat, ths->f, &changed));
+    if (changed) refresh_index_x(ths);
+  }
+  else
+  {
+    nodes_for_transform(ths);
+    check_cu(nfftcu_trafo(ctx_of(ths), ths->f_hat, ths->f));
+  }
   store_times(ths);
 }
 
 void X(adjoint)(X(plan) *ths)
 {
   if (!ths->f_hat || !ths->f) X(die)("nfft_adjoint: f_hat or f is NULL");
-  nodes_for_transform(ths);
-  check_cu(nfftcu_adjoint(ctx_of(ths), ths->f, ths->f_hat));
+  if (!(ths->flags & NODE_BOUND_FLAGS))
+  {
+    int changed = 0;
+    if (ths->M_total > 0 && !ths->x) X(die)("Member x not initialized.");
+    check_cu(nfftcu_adjoint_refresh(ctx_of(ths), ths->x, ths->f, ths->f_hat, &changed));
+    if (changed) refresh_index_x(ths);
+  }
+  else
+  {
+    nodes_for_transform(ths);
+    check_cu(nfftcu_adjoint(ctx_of(ths), ths->f, ths->f_hat));
+  }
   store_times(ths);
 }
 
