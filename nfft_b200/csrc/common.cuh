@@ -119,6 +119,7 @@ struct nfftcu_ctx_s {
   int opt_b_kernel = 0;
   int opt_node_order = 0;
   int opt_b_flush = 0;
+  int opt_fft_prune = 1;            // band-pruned FFT passes + D without zero padding inside trafo / adjoint
   int sm_count = 148;
 };
 
@@ -140,11 +141,11 @@ bool mma3d_supported(const nfftcu_ctx *c);                          // mma3d.cu
 int mma3d_bin_nodes(nfftcu_ctx *c);                                 // mma3d.cu
 int mma3d_interp(nfftcu_ctx *c, void *f_dev);                       // mma3d.cu
 int mma3d_spread(nfftcu_ctx *c, const void *f_dev);                 // mma3d.cu
-int stage_D(nfftcu_ctx *c, const void *f_hat_dev);                  // deconv.cu
+int stage_D(nfftcu_ctx *c, const void *f_hat_dev, bool band_only = false);   // deconv.cu
 int stage_DT(nfftcu_ctx *c, void *f_hat_dev);                       // deconv.cu
 int fft_plan_axes(nfftcu_ctx *c);                                   // fft.cu
 void fft_free_axes(nfftcu_ctx *c);                                  // fft.cu
-int stage_F(nfftcu_ctx *c, int sign);                               // fft.cu
+int stage_F(nfftcu_ctx *c, int sign, bool pruned = false);          // fft.cu
 int stage_B(nfftcu_ctx *c, void *f_dev);                            // interp.cu
 int stage_BT(nfftcu_ctx *c, const void *f_dev);                     // spread.cu
 int build_psi_table(nfftcu_ctx *c);                                 // interp.cu

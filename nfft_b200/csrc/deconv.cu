@@ -83,8 +83,36 @@ __global__ void deconv_crop_kernel(const typename Cplx<T>::type *__restrict__ g,
   }
 }
 
+// D without the zero padding: writes only the band of the grid (the pruned FFT passes of fft.cu never
+// read anything else).  Input-driven, the mirror image of deconv_crop_kernel.
 template <typename T>
-int run(nfftcu_ctx *c, const void *f_hat_in, void *f_hat_out, bool transposed) {
+__global__ void deconv_band_kernel(const typename Cplx<T>::type *__restrict__ f_hat,
+                                   typename Cplx<T>::type *__restrict__ g, DGeom geo, CPtrs<T> cp,
+                                   long long N_total) {
+  typedef typename Cplx<T>::type C;
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long kl = (long long) blockIdx.x * blockDim.x + threadIdx.x; kl < N_total; kl += stride) {
+    long long rem = kl;
+    long long ks[NFFTCU_MAX_D];
+#pragma unroll 1
+    for (int t = geo.d - 1; t >= 0; t--) {
+      ks[t] = rem % geo.N[t];
+      rem /= geo.N[t];
+    }
+    long long gi = 0;
+    T w = (T) 1;
+    for (int t = 0; t < geo.d; t++) {
+      const long long k = ks[t] - geo.N[t] / 2;
+      gi = gi * geo.n[t] + (k >= 0 ? k : geo.n[t] + k);
+      w = (t == 0) ? cp.c[0][ks[0]] : w * cp.c[t][ks[t]];
+    }
+    const C v = f_hat[kl];
+    g[gi] = make_c<T>(v.x * w, v.y * w);
+  }
+}
+
+template <typename T>
+int run(nfftcu_ctx *c, const void *f_hat_in, void *f_hat_out, bool transposed, bool band_only = false) {
   typedef typename Cplx<T>::type C;
   DGeom geo;
   CPtrs<T> cp;
@@ -95,12 +123,16 @@ int run(nfftcu_ctx *c, const void *f_hat_in, void *f_hat_out, bool transposed) {
     cp.c[t] = (const T *) c->c_dev[t];
   }
   const int threads = 256;
-  const long long work = transposed ? c->N_total : c->n_total;
+  const long long work = (transposed || band_only) ? c->N_total : c->n_total;
   long long blocks = (work + threads - 1) / threads;
   const long long cap = (long long) c->sm_count * 16;   // grid-stride above 16 resident CTAs/SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (!transposed)
+  if (!transposed && band_only)
+    deconv_band_kernel<T><<<(unsigned) blocks, threads, 0, c->stream>>>((const C *) f_hat_in,
+                                                                       (C *) c->grid, geo, cp,
+                                                                       c->N_total);
+  else if (!transposed)
     deconv_pad_kernel<T><<<(unsigned) blocks, threads, 0, c->stream>>>((const C *) f_hat_in,
                                                                       (C *) c->grid, geo, cp,
                                                                       c->n_total);
@@ -115,9 +147,9 @@ int run(nfftcu_ctx *c, const void *f_hat_in, void *f_hat_out, bool transposed) {
 
 }  // namespace
 
-int stage_D(nfftcu_ctx *c, const void *f_hat_dev) {
-  return c->prec == NFFTCU_DOUBLE ? run<double>(c, f_hat_dev, nullptr, false)
-                                  : run<float>(c, f_hat_dev, nullptr, false);
+int stage_D(nfftcu_ctx *c, const void *f_hat_dev, bool band_only) {
+  return c->prec == NFFTCU_DOUBLE ? run<double>(c, f_hat_dev, nullptr, false, band_only)
+                                  : run<float>(c, f_hat_dev, nullptr, false, band_only);
 }
 
 int stage_DT(nfftcu_ctx *c, void *f_hat_dev) {

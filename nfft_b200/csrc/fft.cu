@@ -11,6 +11,15 @@
 // Lengths that are not a power of two use an O(len^2) table DFT in shared memory (correct for
 // any length that fits; mixed radix / Bluestein are the planned replacement).
 // HBM-bound: algorithmic bytes 2 * C * n_total per axis pass.
+//
+// Pruned passes.  Inside a transform the oversampled spectrum is non-zero (trafo: after D) or needed
+// (adjoint: before D^T) only in the band k_t in [-N_t/2, N_t/2), i.e. at indices [0, N_t - N_t/2) and
+// [n_t - N_t/2, n_t) of every axis.  The forward transform therefore runs the axes last to first, and the
+// pass over axis t (a) only visits lines whose coordinates in the axes before t lie in the band -- all
+// other lines are still zero -- and (b) loads only the band elements of a line, taking the rest as zero
+// WITHOUT reading them, so D never has to write the zero padding.  The backward transform runs first to
+// last, visits the same lines and stores only the band elements.  At sigma = 2 in 3-D this is
+// (1/4 + 1/2 + 1)/3 of the lines and 2.5x less HBM traffic for D + F.
 #include "common.cuh"
 
 #include <math.h>
@@ -38,7 +47,27 @@ struct LineGeom {
   int bundle;         // lines per CTA
   long long bundles_inner;  // ceil(inner / bundle) when inner > 1
   int pitch;          // shared-memory pitch of one line (complex elements)
+  // pruning (see the header): 0 none | 1 forward: band lines, band loads | 2 backward: band lines, band stores
+  int prune;
+  int nouter;                       // axes before this one
+  long long oN[NFFTCU_MAX_D];       // their band sizes N_s
+  long long olow[NFFTCU_MAX_D];     // ... of which the first olow[s] map to l = c, the rest to l = c + n_s - N_s
+  long long on[NFFTCU_MAX_D];       // ... and full lengths n_s
+  long long elow, ehigh;            // band of this axis: e < elow || e >= ehigh
 };
+
+// compact (band) index over the axes before t -> row-major index over their full lengths
+__device__ __forceinline__ long long map_outer(const LineGeom &g, long long oc) {
+  if (g.prune == 0) return oc;
+  long long o = 0, mul = 1;
+  for (int s = g.nouter - 1; s >= 0; s--) {
+    const long long dgt = oc % g.oN[s];
+    oc /= g.oN[s];
+    o += (dgt < g.olow[s] ? dgt : dgt + (g.on[s] - g.oN[s])) * mul;
+    mul *= g.on[s];
+  }
+  return o;
+}
 
 // global <-> shared staging shared by both kernels.  Line c of bundle b:
 //   inner == 1 : line index q = b*bundle + c,              element e at q*len + e
@@ -48,24 +77,29 @@ template <typename C, bool STORE>
 __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict__ sm,
                                             const LineGeom &g, long long b) {
   const int L = (int) g.len;
+  const bool band_only = STORE ? g.prune == 2 : g.prune == 1;
+  __shared__ long long line_base[64];
   if (g.inner == 1) {
     const long long q0 = b * g.bundle;
     const int cnt = (int) min((long long) g.bundle, g.lines - q0);
-    C *base = data + q0 * g.len;
+    if (threadIdx.x < cnt) line_base[threadIdx.x] = map_outer(g, q0 + threadIdx.x) * g.len;
+    __syncthreads();
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int cl = i / L, e = i - cl * L;
-      if (STORE) base[i] = sm[cl * g.pitch + e];
-      else sm[cl * g.pitch + e] = base[i];
+      const bool in_band = !band_only || e < g.elow || e >= g.ehigh;
+      if (STORE) { if (in_band) data[line_base[cl] + e] = sm[cl * g.pitch + e]; }
+      else sm[cl * g.pitch + e] = in_band ? data[line_base[cl] + e] : C{0, 0};
     }
   } else {
-    const long long o = b / g.bundles_inner;
-    const long long i0 = (b - o * g.bundles_inner) * g.bundle;
+    const long long oc = b / g.bundles_inner;
+    const long long i0 = (b - oc * g.bundles_inner) * g.bundle;
     const int cnt = (int) min((long long) g.bundle, g.inner - i0);
-    C *base = data + o * g.len * g.inner + i0;
+    C *base = data + map_outer(g, oc) * g.len * g.inner + i0;
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int e = i / cnt, cl = i - e * cnt;
-      if (STORE) base[(long long) e * g.inner + cl] = sm[cl * g.pitch + e];
-      else sm[cl * g.pitch + e] = base[(long long) e * g.inner + cl];
+      const bool in_band = !band_only || e < g.elow || e >= g.ehigh;
+      if (STORE) { if (in_band) base[(long long) e * g.inner + cl] = sm[cl * g.pitch + e]; }
+      else sm[cl * g.pitch + e] = in_band ? base[(long long) e * g.inner + cl] : C{0, 0};
     }
   }
 }
@@ -183,7 +217,7 @@ int ilog2_exact(long long v) {
 }
 
 template <typename T>
-int run_axis(nfftcu_ctx *c, int t, int sign) {
+int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
   typedef typename Cplx<T>::type C;
   const FftAxis &ax = c->fft[t];
   if (ax.kind == 0) return NFFTCU_OK;
@@ -192,6 +226,18 @@ int run_axis(nfftcu_ctx *c, int t, int sign) {
   g.inner = 1;
   for (int t2 = t + 1; t2 < c->d; t2++) g.inner *= c->n[t2];
   g.lines = c->n_total / ax.len;
+  g.prune = pruned ? (sign < 0 ? 1 : 2) : 0;
+  g.nouter = t;
+  long long outer = 1;
+  for (int s2 = 0; s2 < t; s2++) {
+    g.oN[s2] = pruned ? c->N[s2] : c->n[s2];
+    g.olow[s2] = pruned ? c->N[s2] - c->N[s2] / 2 : c->n[s2];
+    g.on[s2] = c->n[s2];
+    outer *= g.oN[s2];
+  }
+  g.elow = c->N[t] - c->N[t] / 2;
+  g.ehigh = c->n[t] - c->N[t] / 2;
+  g.lines = outer * g.inner;
   const int pad = 1;
   g.pitch = (int) ax.len + pad;
   const size_t line_bytes = 2 * (size_t) g.pitch * sizeof(C);   // two buffers
@@ -205,6 +251,7 @@ int run_axis(nfftcu_ctx *c, int t, int sign) {
   g.bundle = pref < fit ? pref : fit;
   if (g.inner > 1 && (long long) g.bundle > g.inner) g.bundle = (int) g.inner;
   g.bundles_inner = g.inner == 1 ? 1 : (g.inner + g.bundle - 1) / g.bundle;
+  if (g.bundle > 64) g.bundle = 64;   // line_base[] of stage_lines
   const long long nb = g.inner == 1 ? (g.lines + g.bundle - 1) / g.bundle
                                     : (g.lines / g.inner) * g.bundles_inner;
   const size_t smem = line_bytes * g.bundle;
@@ -259,11 +306,15 @@ void fft_free_axes(nfftcu_ctx *c) {
   }
 }
 
-int stage_F(nfftcu_ctx *c, int sign) {
-  // last axis first: it is the contiguous one, so the grid is touched in the order it was written
-  for (int t = c->d - 1; t >= 0; t--) {
-    if (c->prec == NFFTCU_DOUBLE) NFFTCU_TRY(run_axis<double>(c, t, sign));
-    else NFFTCU_TRY(run_axis<float>(c, t, sign));
+// pruned: the caller guarantees the band structure described in the header (trafo: grid written by the
+// sparse D; adjoint: only the band of the result is read by D^T)
+int stage_F(nfftcu_ctx *c, int sign, bool pruned) {
+  // forward (and every unpruned transform): last axis first; pruned backward: first axis first
+  const bool last_first = !(pruned && sign > 0);
+  for (int i = 0; i < c->d; i++) {
+    const int t = last_first ? c->d - 1 - i : i;
+    if (c->prec == NFFTCU_DOUBLE) NFFTCU_TRY(run_axis<double>(c, t, sign, pruned));
+    else NFFTCU_TRY(run_axis<float>(c, t, sign, pruned));
   }
   return NFFTCU_OK;
 }

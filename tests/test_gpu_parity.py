@@ -428,6 +428,37 @@ def test_tile3d_vs_generic_and_oracle(N, n, m, M, precision):
         assert rel_l2(outs[label][1], outs["generic"][1]) <= tight, label
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("N,n,m,M", [
+    ([64], [128], 6, 500), ([20], [50], 4, 300),
+    ([32, 16], [64, 32], 6, 2000), ([20, 30], [50, 72], 5, 1500),
+    ([16, 16, 16], [32, 32, 32], 6, 3000), ([12, 10, 14], [30, 24, 36], 4, 2500), ([8, 6], [16, 18], 3, 200),
+])
+def test_pruned_fft_matches_full_passes(N, n, m, M, precision):
+    """trafo/adjoint with the band-pruned FFT passes and the D that skips the zero padding (default) against
+    full passes over a zero-padded grid, and both against the oracle."""
+    rng = np.random.default_rng(77)
+    o = oracle(precision)
+    d = len(N)
+    x = (rng.random((M, d)) - 0.5).astype(o.real)
+    NN = int(np.prod(N))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    outs = []
+    for prune in (1, 0):
+        eng = cabi.Engine(N, n, m, M, precision=precision)
+        eng.set_option(cabi.OPT_FFT_PRUNE, prune)
+        eng.set_nodes(x)
+        outs.append((eng.trafo(fh), eng.adjoint(f), eng.trafo(fh)))   # trafo again: the grid holds adjoint leftovers
+        eng.close()
+    assert rel_l2(outs[0][0], o.trafo(N, n, m, x, fh)) <= TOL[precision]
+    assert rel_l2(outs[0][1], o.adjoint(N, n, m, x, f)) <= TOL[precision]
+    tight = 1e-14 if precision == "double" else 1e-6
+    for a, b in zip(outs[0], outs[1]):
+        assert rel_l2(a, b) <= tight
+    assert np.array_equal(outs[0][0], outs[0][2])
+
+
 def test_tile3d_z_segments_small_grid_many_nodes():
     """few tiles -> the sweep is split into z segments; every segment flushes / preloads its window."""
     rng = np.random.default_rng(32)
