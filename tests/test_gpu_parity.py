@@ -7,6 +7,7 @@ Tolerances: fp64 rel-l2 <= 1e-12, fp32 rel-l2 <= 1e-5 against the reference's ow
 reference's own bound (tests/nfft.c:217-284).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -472,3 +473,48 @@ def test_tile3d_z_segments_small_grid_many_nodes():
     assert rel_l2(eng.trafo(fh), o.trafo(N, n, m, x, fh)) <= 1e-12
     assert rel_l2(eng.adjoint(f), o.adjoint(N, n, m, x, f)) <= 1e-12
     eng.close()
+
+
+# ---- (10) the reference's own solver, unmodified, on top of the engine ------------------------------------
+@pytest.mark.parametrize("d,N,n,M,solver", [
+    (2, [32, 32], [64, 64], 3000, "cgnr_damp"),
+    (2, [32, 32], [64, 64], 800, "cgne_weight"),
+    (3, [16, 16, 16], [32, 32, 32], 6000, "cgnr_damp"),      # d = 3, m = 6: the DMMA kernels
+    (1, [128], [256], 400, "cgnr"),
+])
+def test_reference_solver_runs_on_the_engine(d, N, n, M, solver):
+    """kernel/solver/solver.c (CGNR 232-296, CGNE 298-344) compiled from the reference tree, unmodified, and
+    linked against libnfft3_b200.so (oracle/refbuild: libsolver_b200.so) against the same driver on the
+    reference's own nfft.c (libsolver_ref.so): 12 iterations, iterate and residual norms must agree."""
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    so_ref, so_b200 = os.path.join(ref_dir, "libsolver_ref.so"), os.path.join(ref_dir, "libsolver_b200.so")
+    if not (os.path.exists(so_ref) and os.path.exists(so_b200)):
+        pytest.skip("oracle/_ref/libsolver_*.so not built (needs /root/reference at build time)")
+    LANDWEBER, STEEPEST, CGNR, CGNE, NORMS, PRE_W, PRE_D = (1 << i for i in range(7))
+    sflags = {"cgnr": CGNR, "cgnr_damp": CGNR | PRE_D, "cgne_weight": CGNE | PRE_W}[solver]
+    rng = np.random.default_rng(5)
+    m, iters = 6, 12
+    x = np.ascontiguousarray(rng.random((M, d)) - 0.5)
+    NN = int(np.prod(N))
+    y = np.ascontiguousarray(rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5))
+    w = np.ascontiguousarray(0.5 + rng.random(M))
+    k = np.stack(np.meshgrid(*[np.arange(-v // 2, v // 2) / v for v in N], indexing="ij"), -1)
+    w_hat = np.ascontiguousarray((np.sqrt((k ** 2).sum(-1)) <= 0.5).astype(np.float64).ravel())   # disc mask, mri2d style
+    nfft_flags = (abi.PRE_PHI_HUT | abi.PRE_PSI | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+                  | abi.FFT_OUT_OF_PLACE)
+    outs = []
+    for so in (so_ref, so_b200):
+        L = C.CDLL(so, mode=os.RTLD_LOCAL)
+        fn = L.solver_driver_run
+        fn.restype = C.c_int
+        f_hat = np.zeros(NN, dtype=np.complex128)
+        dots = np.zeros(iters)
+        ia = lambda a: (C.c_int * len(a))(*a)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = fn(C.c_int(d), ia(N), C.c_int(M), ia(n), C.c_int(m), C.c_uint(nfft_flags), C.c_uint(sflags),
+                p(x), p(y), p(w), p(w_hat), C.c_int(iters), p(f_hat), p(dots))
+        assert rc == 0
+        outs.append((f_hat, dots))
+    assert np.all(np.isfinite(outs[1][0]))
+    assert rel_l2(outs[1][0], outs[0][0]) <= 1e-9
+    assert np.allclose(outs[1][1], outs[0][1], rtol=1e-8, atol=0)
