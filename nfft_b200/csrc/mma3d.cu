@@ -79,8 +79,18 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
+// c = floor(x * n) in the PLAN's precision (the binning keys use cell_of of common.cuh: same rounding);
+// x is carried as a double that holds the stored value exactly
+template <typename TS> __device__ __forceinline__ int cell_int(double x, int n);
+template <> __device__ __forceinline__ int cell_int<double>(double x, int n) { return __double2int_rd(__dmul_rn(x, (double) n)); }
+template <> __device__ __forceinline__ int cell_int<float>(double x, int n) { return __float2int_rd(__fmul_rn((float) x, (float) n)); }
+
+__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(float *p, double v) { atomicAdd(p, (float) v); }
+
 // ---- binning ---------------------------------------------------------------------------------------------
-__global__ void mma_keys_kernel(const double *__restrict__ x, uint64_t *__restrict__ keys,
+template <typename TS>
+__global__ void mma_keys_kernel(const TS *__restrict__ x, uint64_t *__restrict__ keys,
                                 uint32_t *__restrict__ vals, long long M, MmaParams P) {
   const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
@@ -108,8 +118,9 @@ __global__ void mma_unit_bounds_kernel(const uint64_t *__restrict__ keys, uint32
   unit_start[u] = (uint32_t) lo;
 }
 
-__global__ void mma_gather_f_kernel(const double2 *__restrict__ f, const uint32_t *__restrict__ perm,
-                                    double2 *__restrict__ ft, long long M) {
+template <typename C2>
+__global__ void mma_gather_f_kernel(const C2 *__restrict__ f, const uint32_t *__restrict__ perm,
+                                    C2 *__restrict__ ft, long long M) {
   const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (k < M) ft[k] = f[perm[k]];
 }
@@ -232,10 +243,11 @@ struct Shared {
 
 // Producer warp pw (0..3) of the CTA: batches j = pw, pw+4, ... of the unit.  Lane = (node i = lane & 7,
 // slot quarter qg = lane >> 3): 4 slots x 3 dimensions = 12 independent Horner chains per lane.
-template <int W, bool SPREAD>
-__device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double *__restrict__ xt,
-                                              const double2 *__restrict__ ft, const uint32_t *__restrict__ perm,
-                                              double *__restrict__ f, const uint2 *__restrict__ table,
+template <typename TS, int W, bool SPREAD>
+__device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__restrict__ xt,
+                                              const typename Cplx<TS>::type *__restrict__ ft,
+                                              const uint32_t *__restrict__ perm,
+                                              TS *__restrict__ f, const uint2 *__restrict__ table,
                                               int nbat, int a, int bt, const MmaParams &P, int pw, int lane) {
   const int i = lane & 7, qg = lane >> 3;
   auto finalize = [&](int st) {   // interpolation: the batch in stage st has been released by all MMA warps
@@ -249,14 +261,14 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
       for (int q = 0; q < 16; q += 2) { v0 += rp[q * 16]; v1 += rp[(q + 1) * 16]; }
       v0 += v1;
       v0 += __shfl_xor_sync(kFull, v0, 16);
-      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = v0;
+      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = (TS) v0;
       __syncwarp();
     }
   };
   auto load_nodes = [&](uint2 mt, double &xv, double &fv) {
     const int nb = bt_nb(mt);
-    xv = (lane < 3 * nb) ? xt[3 * (size_t) mt.x + lane] : 0.0;
-    if (SPREAD) fv = (lane < 2 * nb) ? reinterpret_cast<const double *>(ft)[2 * (size_t) mt.x + lane] : 0.0;
+    xv = (lane < 3 * nb) ? (double) xt[3 * (size_t) mt.x + lane] : 0.0;
+    if (SPREAD) fv = (lane < 2 * nb) ? (double) reinterpret_cast<const TS *>(ft)[2 * (size_t) mt.x + lane] : 0.0;
   };
   if (pw >= nbat) return;
   uint2 mt = table[pw], mt_next = make_uint2(0, 0);
@@ -281,7 +293,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
     for (int t = 0; t < 3; t++) {
       const double x = __shfl_sync(kFull, xv, 3 * i + t);
       const int nt = t == 0 ? P.n0 : t == 1 ? P.n1 : P.n2;
-      const int c = __double2int_rd(__dmul_rn(x, (double) nt));
+      const int c = cell_int<TS>(x, nt);
       const int u = wrapi(c - P.m, nt);
       const double y = 2.0 * (x * (double) nt - (double) c) - 1.0;
       const int lo = t == 0 ? u - P.T * a : t == 1 ? u - P.T * bt : u;   // psi_t[l] goes to slot (lo + l) & 15
@@ -375,7 +387,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   __syncthreads();                                                                                    \
   if (tid >= 128) {                                                                                   \
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));                             \
-    producer_loop<W, SPREADV>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31);   \
+    producer_loop<TS, W, SPREADV>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31); \
     return;                                                                                           \
   }                                                                                                   \
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
@@ -384,13 +396,13 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const double
   const unsigned *const rowoff_s = S.rowoff + 4 * warp * kF + nr;   /* group g: [(g >> 1) * kF + 8 * (g & 1)] */
 
 // ---- interpolation ------------------------------------------------------------------------------------
-template <int W>
+template <typename TS, int W>
 __global__ void __launch_bounds__(256, 2)
-interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
-                  const uint32_t *__restrict__ perm, double *__restrict__ f,
+interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
+                  const uint32_t *__restrict__ perm, TS *__restrict__ f,
                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
                   const double *__restrict__ poly, MmaParams P) {
-  const double2 *const ft = nullptr;
+  const typename Cplx<TS>::type *const ft = nullptr;
   NFFTCU_MMA_PROLOGUE(false)
 
   double A[8][2][4];   // [group][re/im][slot]: grid value of pencil (group, nr) at the cell of slot 4*s+kq
@@ -403,9 +415,9 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
       if (z >= n2) z -= n2;
 #pragma unroll
       for (int g = 0; g < 8; g++) {
-        const double2 v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
-        A[g][0][s] = v.x;
-        A[g][1][s] = v.y;
+        const typename Cplx<TS>::type v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
+        A[g][0][s] = (double) v.x;
+        A[g][1][s] = (double) v.y;
       }
     }
   };
@@ -418,9 +430,9 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
 #define NFFTCU_LOADPAIR(SL)                                                                     \
         case SL:                                                                                \
           _Pragma("unroll") for (int g = 0; g < 8; g++) {                                       \
-            const double2 v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];                                                 \
-            A[g][0][SL] = v.x;                                                                  \
-            A[g][1][SL] = v.y;                                                                  \
+            const typename Cplx<TS>::type v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];     \
+            A[g][0][SL] = (double) v.x;                                                         \
+            A[g][1][SL] = (double) v.y;                                                         \
           }                                                                                     \
           break;
         NFFTCU_LOADPAIR(0) NFFTCU_LOADPAIR(1) NFFTCU_LOADPAIR(2) NFFTCU_LOADPAIR(3)
@@ -488,13 +500,14 @@ interp_mma_kernel(const double2 *__restrict__ G, const double *__restrict__ xt,
 // FLUSH = 1: staged per warp in shared memory as 128-byte runs and reduced into the grid by the TMA unit
 constexpr int kStgRow = 9;   // staging row pitch in 16-byte cells: 8 cells + 1 pad (bank-conflict-free, 16-byte aligned)
 
-template <int W, int FLUSH>
+template <typename TS, int W, int FLUSH>
 __global__ void __launch_bounds__(256, 2)
-spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const double2 *__restrict__ ft,
+spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
+                  const typename Cplx<TS>::type *__restrict__ ft,
                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
                   const double *__restrict__ poly, MmaParams P) {
   const uint32_t *const perm = nullptr;
-  double *const f = nullptr;
+  TS *const f = nullptr;
   NFFTCU_MMA_PROLOGUE(true)
   // staging: [buffer][warp][64 rows][kStgRow] double2 behind the Shared block
   double2 *const stg_base = reinterpret_cast<double2 *>(smem_raw + ((sizeof(Shared<W, true>) + 127) & ~(size_t) 127));
@@ -512,7 +525,7 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
   int sblk = -1;      // 8-cell block (wrapped z >> 3) being staged, -1: none
   int snext = 0;      // next pair position (0,2,4,6) of the block that has not been written
   bool sbusy = false; // the TMA unit may still be reading the staging rows (last flush not waited for)
-  double *const Gd = reinterpret_cast<double *>(G);
+  TS *const Gd = reinterpret_cast<TS *>(G);
 
   auto stage_store = [&](int pos, bool zero, int nt) {   // pair position pos (even) of the staged block
     if (sbusy) {
@@ -544,7 +557,7 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
       const int g = row >> 3, pn = row & 7;
       const unsigned off = S.rowoff[(4 * warp + (g >> 1)) * kF + 8 * (g & 1) + pn];
       const double2 *src = stg_w + (size_t) row * kStgRow;
-      double2 *dst = G + off + 8 * sblk;
+      void *dst = G + off + 8 * sblk;   // FLUSH = 1 is instantiated for TS = double only
       asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 128;"
                    ::"l"(dst), "r"(smem_addr(src)) : "memory");
     }
@@ -574,13 +587,13 @@ spread_mma_kernel(double2 *__restrict__ G, const double *__restrict__ xt, const 
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         if (FLUSH == 0) {
-          double *dst = Gd + 2 * ((size_t) rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw);
+          TS *dst = Gd + 2 * ((size_t) rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw);
           if (nt == 0) {
-            atomicAdd(dst, C[g][0][0][0]); atomicAdd(dst + 1, C[g][1][0][0]);
-            atomicAdd(dst + 2, C[g][0][0][1]); atomicAdd(dst + 3, C[g][1][0][1]);
+            red_add(dst, C[g][0][0][0]); red_add(dst + 1, C[g][1][0][0]);
+            red_add(dst + 2, C[g][0][0][1]); red_add(dst + 3, C[g][1][0][1]);
           } else {
-            atomicAdd(dst, C[g][0][1][0]); atomicAdd(dst + 1, C[g][1][1][0]);
-            atomicAdd(dst + 2, C[g][0][1][1]); atomicAdd(dst + 3, C[g][1][1][1]);
+            red_add(dst, C[g][0][1][0]); red_add(dst + 1, C[g][1][1][0]);
+            red_add(dst + 2, C[g][0][1][1]); red_add(dst + 3, C[g][1][1][1]);
           }
         }
         if (nt == 0) { C[g][0][0][0] = C[g][1][0][0] = C[g][0][0][1] = C[g][1][0][1] = 0.0; }
@@ -675,38 +688,37 @@ size_t spread_smem() {
   return b;
 }
 
-template <int W>
+template <typename TS, int W>
 int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
+  typedef typename Cplx<TS>::type C2;
   const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
-  const double *xt = (const double *) c->tile_x;
+  const TS *xt = (const TS *) c->tile_x;
   const double *poly = (const double *) c->kbpoly_dev;
+  const uint2 *table = (const uint2 *) c->mma_batches;
   if (!spread) {
     const size_t smem = sizeof(Shared<W, false>);
-    NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<TS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
-    interp_mma_kernel<W><<<grid, 256, smem, c->stream>>>((const double2 *) c->grid, xt, c->tile_perm,
-                                                         (double *) f_out, c->mma_batch_start,
-                                                         (const uint2 *) c->mma_batches, poly, P);
+    interp_mma_kernel<TS, W><<<grid, 256, smem, c->stream>>>((const C2 *) c->grid, xt, c->tile_perm, (TS *) f_out,
+                                                             c->mma_batch_start, table, poly, P);
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches++;
   } else {
     const int kb = 256;
-    mma_gather_f_kernel<<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
-        (const double2 *) f_in, c->tile_perm, (double2 *) c->f_tile, c->M);
-    const bool bulk = (P.n2 % 8 == 0) && c->opt_b_flush == 2;
+    mma_gather_f_kernel<C2><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+        (const C2 *) f_in, c->tile_perm, (C2 *) c->f_tile, c->M);
+    const bool bulk = sizeof(TS) == 8 && (P.n2 % 8 == 0) && c->opt_b_flush == 2;
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     if (bulk) {
       const size_t smem = spread_smem<W, 1>();
-      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<W, 1><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
-                                                              c->mma_batch_start, (const uint2 *) c->mma_batches,
-                                                              poly, P);
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<double, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<double, W, 1><<<grid, 256, smem, c->stream>>>(
+          (double2 *) c->grid, (const double *) c->tile_x, (const double2 *) c->f_tile, c->mma_batch_start, table, poly, P);
     } else {
       const size_t smem = spread_smem<W, 0>();
-      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<W, 0><<<grid, 256, smem, c->stream>>>((double2 *) c->grid, xt, (const double2 *) c->f_tile,
-                                                              c->mma_batch_start, (const uint2 *) c->mma_batches,
-                                                              poly, P);
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<TS, W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<TS, W, 0><<<grid, 256, smem, c->stream>>>((C2 *) c->grid, xt, (const C2 *) c->f_tile,
+                                                                  c->mma_batch_start, table, poly, P);
     }
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches += 2;
@@ -715,14 +727,15 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   return NFFTCU_OK;
 }
 
+template <typename TS>
 int dispatch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
   const MmaParams P = make_params(c);
   switch (2 * (int) c->m + 2) {
-    case 6: return launch<6>(c, f_in, f_out, spread, P);
-    case 8: return launch<8>(c, f_in, f_out, spread, P);
-    case 10: return launch<10>(c, f_in, f_out, spread, P);
-    case 12: return launch<12>(c, f_in, f_out, spread, P);
-    case 14: return launch<14>(c, f_in, f_out, spread, P);
+    case 6: return launch<TS, 6>(c, f_in, f_out, spread, P);
+    case 8: return launch<TS, 8>(c, f_in, f_out, spread, P);
+    case 10: return launch<TS, 10>(c, f_in, f_out, spread, P);
+    case 12: return launch<TS, 12>(c, f_in, f_out, spread, P);
+    case 14: return launch<TS, 14>(c, f_in, f_out, spread, P);
     default: break;
   }
   set_error("mma3d: unsupported window cut-off m=%lld", (long long) c->m);
@@ -732,7 +745,7 @@ int dispatch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
 }  // namespace
 
 bool mma3d_supported(const nfftcu_ctx *c) {
-  if (c->d != 3 || c->direct_only || c->prec != NFFTCU_DOUBLE) return false;
+  if (c->d != 3 || c->direct_only) return false;
   if (c->m < 2 || c->m > 6 || c->kbpoly_fit < 0) return false;
   for (int t = 0; t < 3; t++)
     if (c->n[t] < kF || c->n[t] > 0x3fffff) return false;
@@ -753,8 +766,8 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   const long long nkeys = (long long) P.NT0 * P.NT1 * P.n2;
   if (!c->tile_keys) NFFTCU_CUDA(cudaMalloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
   if (!c->tile_perm) NFFTCU_CUDA(cudaMalloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
-  if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, sizeof(double) * (size_t) M * 3));
-  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, sizeof(double2) * (size_t) M));
+  if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, real_size(c) * (size_t) M * 3));
+  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
   if (!c->bin_start || c->tile_nbins != units) {
     if (c->bin_start) cudaFree(c->bin_start);
     c->bin_start = nullptr;
@@ -762,8 +775,12 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
     c->tile_nbins = units;
   }
   const int kb = 256;
-  mma_keys_kernel<<<(unsigned) ((M + kb - 1) / kb), kb, 0, c->stream>>>(
-      (const double *) c->x_dev, (uint64_t *) c->tile_keys, c->tile_perm, M, P);
+  if (c->prec == NFFTCU_DOUBLE)
+    mma_keys_kernel<double><<<(unsigned) ((M + kb - 1) / kb), kb, 0, c->stream>>>(
+        (const double *) c->x_dev, (uint64_t *) c->tile_keys, c->tile_perm, M, P);
+  else
+    mma_keys_kernel<float><<<(unsigned) ((M + kb - 1) / kb), kb, 0, c->stream>>>(
+        (const float *) c->x_dev, (uint64_t *) c->tile_keys, c->tile_perm, M, P);
   c->launches++;
   int bits = 0;
   while ((1ll << bits) < nkeys && bits < 62) bits++;
@@ -802,8 +819,12 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   return NFFTCU_OK;
 }
 
-int mma3d_interp(nfftcu_ctx *c, void *f_dev) { return dispatch(c, nullptr, f_dev, false); }
+int mma3d_interp(nfftcu_ctx *c, void *f_dev) {
+  return c->prec == NFFTCU_DOUBLE ? dispatch<double>(c, nullptr, f_dev, false) : dispatch<float>(c, nullptr, f_dev, false);
+}
 
-int mma3d_spread(nfftcu_ctx *c, const void *f_dev) { return dispatch(c, f_dev, nullptr, true); }
+int mma3d_spread(nfftcu_ctx *c, const void *f_dev) {
+  return c->prec == NFFTCU_DOUBLE ? dispatch<double>(c, f_dev, nullptr, true) : dispatch<float>(c, f_dev, nullptr, true);
+}
 
 }  // namespace nfftcu
