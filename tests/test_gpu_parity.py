@@ -518,3 +518,147 @@ def test_reference_solver_runs_on_the_engine(d, N, n, M, solver):
     assert np.all(np.isfinite(outs[1][0]))
     assert rel_l2(outs[1][0], outs[0][0]) <= 1e-9
     assert np.allclose(outs[1][1], outs[0][1], rtol=1e-8, atol=0)
+
+
+# ---- (11) the reference's kernel/mri and applications/fastsum, unmodified, on top of the engine -----------
+def _apps_libs():
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    so_ref, so_b200 = os.path.join(ref_dir, "libapps_ref.so"), os.path.join(ref_dir, "libapps_b200.so")
+    if not (os.path.exists(so_ref) and os.path.exists(so_b200)):
+        pytest.skip("oracle/_ref/libapps_*.so not built (needs /root/reference at build time)")
+    return [C.CDLL(so, mode=os.RTLD_LOCAL) for so in (so_ref, so_b200)]
+
+
+_ia = lambda a: (C.c_int * len(a))(*a)            # noqa: E731
+_vp = lambda a: a.ctypes.data_as(C.c_void_p)      # noqa: E731
+
+
+@pytest.mark.parametrize("variant", ["2d1d", "3d"])
+@pytest.mark.parametrize("N0,N3,m,sigma,M", [(32, 12, 2, 1.25, 900), (64, 16, 4, 2.0, 5000)])
+def test_reference_mri_inh_runs_on_the_engine(variant, N0, N3, m, sigma, M):
+    """kernel/mri/mri.c:58-330 (mri_inh_2d1d_* loops 2 N3/2+1 NFFTs with host-side PHI / PHI_HUT scaling and
+    swaps the plan's f / f_hat buffers with nfft_free + its own; mri_inh_3d_* wraps one 3-D NFFT), compiled from
+    the reference tree and linked against libnfft3_b200.so, vs the same code on the reference's nfft.c."""
+    libs = _apps_libs()
+    rng = np.random.default_rng(31)
+    NN = N0 * N0
+    x = np.ascontiguousarray(rng.random((M, 2)) - 0.5)
+    t = np.ascontiguousarray((rng.random(M) - 0.5) * (1 - 2 * m / N3) * 0.99)
+    w = np.ascontiguousarray((rng.random(NN) - 0.5) * 0.5)
+    fh = np.ascontiguousarray(rng.random(NN) + 1j * rng.random(NN))
+    f = np.ascontiguousarray(rng.random(M) + 1j * rng.random(M))
+    flags = abi.PRE_PHI_HUT | abi.PRE_PSI | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+    n2 = int(np.ceil(N0 * sigma))
+    outs = []
+    for L in libs:
+        fo, fho = np.zeros(M, complex), np.zeros(NN, complex)
+        if variant == "2d1d":
+            rc = L.apps_mri_inh_2d1d(_ia([N0, N0, N3]), M, _ia([n2, n2, N3]), m, C.c_double(sigma), C.c_uint(flags),
+                                     _vp(x), _vp(t), _vp(w), _vp(fh), _vp(f), _vp(fo), _vp(fho))
+        else:
+            x3 = np.ascontiguousarray(np.concatenate([x, t[:, None]], 1))
+            n3 = int(np.ceil(N3 * sigma / 2)) * 2
+            rc = L.apps_mri_inh_3d(_ia([N0, N0, N3]), M, _ia([n2, n2, n3]), m, C.c_double(sigma), C.c_uint(flags),
+                                   _vp(x3), _vp(w), _vp(fh), _vp(f), _vp(fo), _vp(fho))
+        assert rc == 0
+        outs.append((fo, fho))
+    assert np.all(np.isfinite(outs[1][0])) and np.all(np.isfinite(outs[1][1]))
+    assert rel_l2(outs[1][0], outs[0][0]) <= 1e-12
+    assert rel_l2(outs[1][1], outs[0][1]) <= 1e-12
+
+
+@pytest.mark.parametrize("d,Ns,Mt,nn,m,p,kern,fs_flags", [
+    (2, 4000, 3000, 64, 4, 3, 1, 0),         # multiquadric, search-tree near field
+    (2, 4000, 3000, 64, 6, 5, 0, 2),         # gaussian, NEARFIELD_BOXES
+    (3, 3000, 3000, 32, 4, 3, 3, 0),         # inverse multiquadric, d = 3: the DMMA kernels
+    (1, 2000, 2000, 128, 5, 4, 2, 0),        # 1/x (complex-valued regularisation), d = 1
+])
+def test_reference_fastsum_runs_on_the_engine(d, Ns, Mt, nn, m, p, kern, fs_flags):
+    """applications/fastsum/fastsum.c (fastsum_init_guru 1062-1068: two NFFT plans without MALLOC_* whose
+    x / f / f_hat are assigned after init 919-921, 981-983; fastsum_trafo 1170-1260: adjoint -> multiply by b ->
+    trafo -> near field) compiled from the reference tree and linked against libnfft3_b200.so, vs the same code
+    on the reference's nfft.c; also against the direct sum to the accuracy the reference itself reaches."""
+    libs = _apps_libs()
+    rng = np.random.default_rng(41)
+    c = 1.0 / np.sqrt(float(nn)) if kern != 2 else 0.0
+    eps_I, eps_B = p / nn, 1.0 / 16
+
+    def ball(K):
+        r = 0.25 - eps_B / 2
+        v = (rng.random((4 * K + 64, d)) * 2 - 1) * r
+        v = v[(v ** 2).sum(1) < r * r][:K]
+        assert len(v) == K
+        return np.ascontiguousarray(v)
+
+    xs, ys = ball(Ns), ball(Mt)
+    al = np.ascontiguousarray(rng.random(Ns) + 1j * rng.random(Ns))
+    outs = []
+    for i, L in enumerate(libs):
+        L.apps_fastsum.argtypes = [C.c_int] * 7 + [C.c_double] * 3 + [C.c_uint] + [C.c_void_p] * 5
+        fo = np.zeros(Mt, complex)
+        fe = np.zeros(Mt, complex)
+        rc = L.apps_fastsum(d, Ns, Mt, nn, m, p, kern, c, eps_I, eps_B, fs_flags, _vp(xs), _vp(al), _vp(ys),
+                            _vp(fo), _vp(fe) if i == 0 else None)
+        assert rc == 0
+        outs.append((fo, fe))
+    ref_f, exact = outs[0]
+    got = outs[1][0]
+    assert np.all(np.isfinite(got))
+    assert rel_l2(got, ref_f) <= 1e-11
+    # the approximation error of the fast sum itself is the same on both NFFT back ends
+    scale = np.abs(al).sum()
+    assert abs(np.abs(got - exact).max() - np.abs(ref_f - exact).max()) <= 1e-10 * scale
+
+
+# ---- (12) BASELINE configs[1]: 2-D N=512^2, M=512^2 MRI-style trajectories, PRE_PSI, full size vs the oracle ---
+def _mri_knots(kind, M, N):
+    """applications/mri/mri2d/construct_knots_spiral.m:20-33 (one arm) and construct_knots_radial.m:18-31."""
+    if kind == "spiral":
+        A, w = 0.5, N / 64 * 50
+        t = np.sqrt(np.arange(M) / M)
+        x = np.stack([A * t * np.cos(2 * np.pi * w * t), A * t * np.sin(2 * np.pi * w * t)], 1)
+    else:
+        Z = int(np.sqrt(M))
+        i, j = np.meshgrid(np.arange(Z), np.arange(Z), indexing="ij")
+        r = (j.ravel() - Z / 2) / Z
+        phi = np.pi * i.ravel() / Z
+        x = np.stack([r * np.cos(phi), r * np.sin(phi)], 1)
+    return np.ascontiguousarray(np.clip(x, -0.5, np.nextafter(0.5, 0.0)))
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("kind", ["spiral", "radial"])
+def test_cfg2_mri_trajectories_vs_oracle(kind, precision):
+    N, n, m, M = [512, 512], [1024, 1024], 6, 512 * 512
+    spec = dict(d=2, N=N, n=n, m=m, M=M, seed=20260102,
+                flags=BASE | abi.PRE_PSI)   # reconstruct_data_2d.c:47-55
+    _, fh, f = make_case(spec, precision)
+    x = _mri_knots(kind, M, 512)
+    if precision == "float":
+        x = np.minimum(x.astype(np.float32), np.nextafter(np.float32(0.5), np.float32(0)))
+    o = oracle(precision)
+    out_f, out_fh, _ = run_plan(spec, precision, x, fh, f)
+    assert rel_l2(out_f, o.trafo(N, n, m, x, fh)) <= TOL[precision]
+    assert rel_l2(out_fh, o.adjoint(N, n, m, x, f, True)) <= TOL[precision]
+
+
+# ---- (13) BASELINE configs[3] grid: 3-D N=256^3, n=512^3 (one GPU's share of the node-sharded run) --------------
+def test_cfg4_grid_subsample_and_adjointness():
+    """N=256^3, n=512^3, m=6, M=4*10^6 nodes: a 2000-node subsample of trafo against the oracle's B step fed with
+    the device grid (D and F are covered at sizes the oracle can run in full), and <A u, v> == <u, A^H v>."""
+    rng = np.random.default_rng(777)
+    N, n, m, M = [256] * 3, [512] * 3, 6, 4_000_000
+    NN = 256 ** 3
+    x = rng.random((M, 3)) - 0.5
+    u = rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)
+    v = rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)
+    eng = cabi.Engine(N, n, m, M, precision="double")
+    eng.set_nodes(x)
+    Au = eng.trafo(u)
+    g = eng.grid_to_host()
+    AHv = eng.adjoint(v)
+    eng.close()
+    sel = rng.choice(M, 2000, replace=False)
+    assert rel_l2(Au[sel], oracle("double").stage_B(N, n, m, x[sel], g)) <= 1e-12
+    lhs, rhs = np.vdot(v, Au), np.vdot(AHv, u)
+    assert abs(lhs - rhs) / (np.linalg.norm(v) * np.linalg.norm(Au)) <= 1e-12
