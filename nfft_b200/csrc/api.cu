@@ -92,9 +92,9 @@ int trafo_dev_impl(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
   if (c->direct_only) return ndft_trafo(c, f_hat_dev, f_dev);
   StageTimer tm(c);
   tm.mark(0);
-  NFFTCU_TRY(stage_D(c, f_hat_dev, c->opt_fft_prune != 0));
+  NFFTCU_TRY(stage_D(c, f_hat_dev, c->opt_fft_prune != 0 && !c->fft_no_prune));
   tm.mark(1);
-  NFFTCU_TRY(stage_F(c, -1, c->opt_fft_prune != 0));
+  NFFTCU_TRY(stage_F(c, -1, c->opt_fft_prune != 0 && !c->fft_no_prune));
   tm.mark(2);
   NFFTCU_TRY(stage_B(c, f_dev));
   tm.mark(3);
@@ -109,7 +109,7 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
   tm.mark(0);
   NFFTCU_TRY(stage_BT(c, f_dev));
   tm.mark(1);
-  NFFTCU_TRY(stage_F(c, +1, c->opt_fft_prune != 0));
+  NFFTCU_TRY(stage_F(c, +1, c->opt_fft_prune != 0 && !c->fft_no_prune));
   tm.mark(2);
   NFFTCU_TRY(stage_DT(c, f_hat_dev));
   tm.mark(3);

@@ -41,10 +41,20 @@ template <> __host__ __device__ inline double2 make_c<double>(double re, double 
 template <> __host__ __device__ inline float2 make_c<float>(float re, float im) { return make_float2(re, im); }
 
 // ---- plan context -----------------------------------------------------------------------------
-struct FftAxis {
+// one shared-memory transform length
+struct FftLine {
   int64_t len = 0;
   void *tw = nullptr;   // len complex (plan precision): exp(-2 pi i q / len)
-  int kind = 0;         // 0: len==1, 1: shared-memory Stockham (power of two), 2: O(len^2) table DFT
+  int kind = 0;         // 0: len==1, 1: radix-4/2 Stockham (power of two), 2: O(len^2) table DFT, 3: mixed radix
+  int nst = 0;          // kind 3: radix per stage
+  int radix[24] = {0};
+};
+struct FftAxis {
+  int64_t len = 0;
+  bool split = false;   // four-step: len = sub1.len * sub2.len, twiddle W_len^q = twA[q >> tw_shift] * twB[q & mask]
+  FftLine whole, sub1, sub2;
+  void *twA = nullptr, *twB = nullptr;
+  int tw_shift = 0;
 };
 
 }  // namespace nfftcu
@@ -61,6 +71,8 @@ struct nfftcu_ctx_s {
   std::vector<double> c_host[NFFTCU_MAX_D];   // c_phi_inv in double
   void *c_dev[NFFTCU_MAX_D] = {nullptr};      // c_phi_inv in plan precision
   void *grid = nullptr;                       // n_total complex
+  void *grid2 = nullptr;                      // second buffer, only for plans with a split (four-step) FFT axis
+  bool fft_no_prune = false;                  // a split axis runs unpruned passes
   nfftcu::FftAxis fft[NFFTCU_MAX_D];
 
   // nodes

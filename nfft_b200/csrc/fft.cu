@@ -8,8 +8,12 @@
 // and writes the lines back.  For strided axes the bundle is a run of neighbouring lines so that
 // every global access is a contiguous segment of bundle*sizeof(complex) bytes.
 // Twiddles come from a per-axis table exp(-2 pi i q/len) computed on the host in long double.
-// Lengths that are not a power of two use an O(len^2) table DFT in shared memory (correct for
-// any length that fits; mixed radix / Bluestein are the planned replacement).
+// Lengths that are not a power of two run a mixed-radix Stockham (radix 4, 2, 3, 5, 7 in registers, any
+// other prime factor <= 61 as a direct r-point stage); a length with a larger prime factor uses the O(len^2)
+// table DFT in shared memory.  An axis too long for one CTA's shared memory is split len = L1 * L2
+// (four-step): L1-point transforms down the columns with the twiddle W_len^(l2 k1) fused into their store
+// (two-level table, one extra complex multiply), then L2-point transforms along the rows whose store
+// transposes into a second grid buffer; the two buffers are swapped afterwards.
 // HBM-bound: algorithmic bytes 2 * C * n_total per axis pass.
 //
 // Pruned passes.  Inside a transform the oversampled spectrum is non-zero (trafo: after D) or needed
@@ -23,6 +27,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <string.h>
 
 namespace nfftcu {
 
@@ -54,6 +59,19 @@ struct LineGeom {
   long long olow[NFFTCU_MAX_D];     // ... of which the first olow[s] map to l = c, the rest to l = c + n_s - N_s
   long long on[NFFTCU_MAX_D];       // ... and full lengths n_s
   long long elow, ehigh;            // band of this axis: e < elow || e >= ehigh
+  // four-step split of a long axis (see the header).  twist: this pass is the column pass, element e (= k1) of
+  // the line with inner index i is multiplied by W_Ltot^((i / tw_I) * e) = twA[q >> tw_shift] * twB[q & mask]
+  // at the store.  tstore: this pass is the row pass over [o][k1][e = k2][i], stored as [o][k2][k1][i].
+  int twist, tstore;
+  int tw_shift;
+  long long tw_I;
+  const void *twA, *twB;
+  long long tL1, tL2, tI;
+};
+
+struct RadixPlan {
+  int nst;
+  int radix[24];
 };
 
 // compact (band) index over the axes before t -> row-major index over their full lengths
@@ -73,12 +91,44 @@ __device__ __forceinline__ long long map_outer(const LineGeom &g, long long oc) 
 //   inner == 1 : line index q = b*bundle + c,              element e at q*len + e
 //   inner  > 1 : (o, i) = (b / bundles_inner, (b % bundles_inner)*bundle + c),
 //                element e at (o*len + e)*inner + i
+template <typename C>
+__device__ __forceinline__ C twist_factor(const LineGeom &g, long long l2, int e, int sign) {
+  const long long q = l2 * e;
+  const C a = reinterpret_cast<const C *>(g.twA)[q >> g.tw_shift];
+  const C bq = reinterpret_cast<const C *>(g.twB)[q & ((1ll << g.tw_shift) - 1)];
+  C w = cmul(a, bq);
+  if (sign > 0) w.y = -w.y;
+  return w;
+}
+
 template <typename C, bool STORE>
 __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict__ sm,
-                                            const LineGeom &g, long long b) {
+                                            const LineGeom &g, long long b, int sign = 0) {
   const int L = (int) g.len;
   const bool band_only = STORE ? g.prune == 2 : g.prune == 1;
   __shared__ long long line_base[64];
+  if (STORE && g.tstore) {
+    // row pass of a split axis: line (oc = o * L1 + k1, i), element e = k2 -> [o][k2][k1][i]; the bundle runs
+    // along k1 (inner == 1) or i (inner > 1), so consecutive cl are consecutive addresses either way
+    long long oc, i0;
+    int cnt;
+    if (g.inner == 1) {
+      oc = b * g.bundle; i0 = 0;
+      cnt = (int) min((long long) g.bundle, g.lines - oc);
+    } else {
+      oc = b / g.bundles_inner;
+      i0 = (b - oc * g.bundles_inner) * g.bundle;
+      cnt = (int) min((long long) g.bundle, g.inner - i0);
+    }
+    for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
+      const int e = i / cnt, cl = i - e * cnt;
+      const long long ocl = g.inner == 1 ? oc + cl : oc;
+      const long long o = ocl / g.tL1, k1 = ocl - o * g.tL1;
+      const long long ii = g.inner == 1 ? 0 : i0 + cl;
+      data[((o * g.tL2 + e) * g.tL1 + k1) * g.tI + ii] = sm[cl * g.pitch + e];
+    }
+    return;
+  }
   if (g.inner == 1) {
     const long long q0 = b * g.bundle;
     const int cnt = (int) min((long long) g.bundle, g.lines - q0);
@@ -98,7 +148,11 @@ __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict_
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int e = i / cnt, cl = i - e * cnt;
       const bool in_band = !band_only || e < g.elow || e >= g.ehigh;
-      if (STORE) { if (in_band) base[(long long) e * g.inner + cl] = sm[cl * g.pitch + e]; }
+      if (STORE) {
+        C v = sm[cl * g.pitch + e];
+        if (g.twist && e) v = cmul(v, twist_factor<C>(g, (i0 + cl) / g.tw_I, e, sign));
+        if (in_band) base[(long long) e * g.inner + cl] = v;
+      }
       else sm[cl * g.pitch + e] = in_band ? base[(long long) e * g.inner + cl] : C{0, 0};
     }
   }
@@ -114,7 +168,7 @@ __device__ __forceinline__ int bundle_count(const LineGeom &g, long long b) {
 // ---- power-of-two lengths: Stockham autosort in shared memory -----------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kFftThreads)
-fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data,
+fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::type *__restrict__ out_data,
                     const typename Cplx<T>::type *__restrict__ tw, LineGeom g, int sign,
                     int log2len) {
   typedef typename Cplx<T>::type C;
@@ -170,13 +224,107 @@ fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data,
     __syncthreads();
     C *t = src; src = dst; dst = t;
   }
-  stage_lines<C, true>(data, src, g, b);
+  stage_lines<C, true>(out_data, src, g, b, sign);
+}
+
+// ---- any length with prime factors <= 61: mixed-radix Stockham in shared memory ------------------
+// Stage with radix R after Ns = product of the earlier radices: butterfly j in [0, L/R), k = j mod Ns,
+//   v[q] = src[j + q L/R] * W_L^(q k L/(Ns R)),  dst[(j - k) R + k + p Ns] = sum_q v[q] W_R^(p q).
+template <typename T, int R>
+__device__ __forceinline__ void radix_stage(const typename Cplx<T>::type *__restrict__ src,
+                                            typename Cplx<T>::type *__restrict__ dst,
+                                            const typename Cplx<T>::type *__restrict__ tw, int L, int Ns, int cnt,
+                                            int pitch, int sign) {
+  typedef typename Cplx<T>::type C;
+  const int sub = L / R, tstep = L / (Ns * R), rstep = L / R;
+  for (int w = threadIdx.x; w < cnt * sub; w += blockDim.x) {
+    const int cl = w / sub, j = w - cl * sub;
+    const int k = j % Ns;
+    C v[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      v[q] = src[cl * pitch + j + q * sub];
+      if (q && k) {
+        C wq = tw[q * k * tstep];
+        if (sign > 0) wq.y = -wq.y;
+        v[q] = cmul(v[q], wq);
+      }
+    }
+    C *out = dst + cl * pitch + (j - k) * R + k;
+#pragma unroll
+    for (int pq = 0; pq < R; pq++) {
+      C acc = v[0];
+#pragma unroll
+      for (int q = 1; q < R; q++) {
+        C wr = tw[((pq * q) % R) * rstep];
+        if (sign > 0) wr.y = -wr.y;
+        acc = cadd(acc, cmul(v[q], wr));
+      }
+      out[pq * Ns] = acc;
+    }
+  }
+}
+
+// any other (odd prime) radix: one output per inner iteration, inputs re-read from shared memory
+template <typename T>
+__device__ __forceinline__ void radix_stage_any(const typename Cplx<T>::type *__restrict__ src,
+                                                typename Cplx<T>::type *__restrict__ dst,
+                                                const typename Cplx<T>::type *__restrict__ tw, int L, int R, int Ns,
+                                                int cnt, int pitch, int sign) {
+  typedef typename Cplx<T>::type C;
+  const int sub = L / R, tstep = L / (Ns * R), rstep = L / R;
+  for (int w = threadIdx.x; w < cnt * sub * R; w += blockDim.x) {
+    const int pq = w % R, rest = w / R;
+    const int cl = rest / sub, j = rest - cl * sub;
+    const int k = j % Ns;
+    C acc = src[cl * pitch + j];
+    for (int q = 1; q < R; q++) {
+      // W_L^(q k tstep) * W_R^(pq q): both exponents are < L, their sum is reduced once
+      int e = q * k * tstep + ((pq * q) % R) * rstep;
+      if (e >= L) e -= L;
+      C wv = tw[e];
+      if (sign > 0) wv.y = -wv.y;
+      acc = cadd(acc, cmul(src[cl * pitch + j + q * sub], wv));
+    }
+    dst[cl * pitch + (j - k) * R + k + pq * Ns] = acc;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads)
+fft_mixed_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::type *__restrict__ out_data,
+                 const typename Cplx<T>::type *__restrict__ tw, LineGeom g, int sign, RadixPlan rp) {
+  typedef typename Cplx<T>::type C;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C *src = reinterpret_cast<C *>(smem_raw);
+  C *dst = src + (size_t) g.bundle * g.pitch;
+  const int L = (int) g.len;
+  const long long b = blockIdx.x;
+  const int cnt = bundle_count<C>(g, b);
+  stage_lines<C, false>(data, src, g, b);
+  __syncthreads();
+  int Ns = 1;
+  for (int st = 0; st < rp.nst; st++) {
+    const int R = rp.radix[st];
+    switch (R) {
+      case 2: radix_stage<T, 2>(src, dst, tw, L, Ns, cnt, g.pitch, sign); break;
+      case 3: radix_stage<T, 3>(src, dst, tw, L, Ns, cnt, g.pitch, sign); break;
+      case 4: radix_stage<T, 4>(src, dst, tw, L, Ns, cnt, g.pitch, sign); break;
+      case 5: radix_stage<T, 5>(src, dst, tw, L, Ns, cnt, g.pitch, sign); break;
+      case 7: radix_stage<T, 7>(src, dst, tw, L, Ns, cnt, g.pitch, sign); break;
+      default: radix_stage_any<T>(src, dst, tw, L, R, Ns, cnt, g.pitch, sign); break;
+    }
+    __syncthreads();
+    C *t = src; src = dst; dst = t;
+    Ns *= R;
+  }
+  stage_lines<C, true>(out_data, src, g, b, sign);
 }
 
 // ---- any length that fits: O(len^2) DFT from the twiddle table ---------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kFftThreads)
-dft_table_kernel(typename Cplx<T>::type *__restrict__ data,
+dft_table_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::type *__restrict__ out_data,
                  const typename Cplx<T>::type *__restrict__ tw, LineGeom g, int sign) {
   typedef typename Cplx<T>::type C;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -207,7 +355,7 @@ dft_table_kernel(typename Cplx<T>::type *__restrict__ data,
     buf1[cl * g.pitch + k] = o;
   }
   __syncthreads();
-  stage_lines<C, true>(data, buf1, g, b);
+  stage_lines<C, true>(out_data, buf1, g, b, sign);
 }
 
 int ilog2_exact(long long v) {
@@ -216,16 +364,139 @@ int ilog2_exact(long long v) {
   return ((1ll << l) == v) ? l : -1;
 }
 
+constexpr int kMaxPrimeRadix = 61;
+
+// len = 4^a * 2^b * odd primes <= kMaxPrimeRadix ?
+bool factorize(long long len, FftLine &ln) {
+  ln.nst = 0;
+  while (len % 4 == 0 && ln.nst < 24) { ln.radix[ln.nst++] = 4; len /= 4; }
+  if (len % 2 == 0 && ln.nst < 24) { ln.radix[ln.nst++] = 2; len /= 2; }
+  for (int p = 3; p <= kMaxPrimeRadix; p += 2)
+    while (len % p == 0) {
+      if (ln.nst >= 24) return false;
+      ln.radix[ln.nst++] = p;
+      len /= p;
+    }
+  return len == 1;
+}
+
+// longest line whose two shared-memory buffers (pitch len + 1) fit one CTA
+long long max_line_len(const nfftcu_ctx *c) { return (long long) (kSmemBudget / (2 * 2 * real_size(c))) - 1; }
+
+int upload_twiddles(const nfftcu_ctx *c, long long count, long long num_stride, long long den, void **out) {
+  // table[q] = exp(-2 pi i q * num_stride / den), q < count, in long double -> plan precision
+  const long double two_pi = 6.283185307179586476925286766559005768394L;
+  const size_t esz = 2 * real_size(c);
+  std::vector<unsigned char> host(esz * (size_t) count);
+  for (long long q = 0; q < count; q++) {
+    const long long r = (long long) (((__int128) q * num_stride) % den);
+    const long double ang = two_pi * (long double) r / (long double) den;
+    const long double cr = cosl(ang), ci = -sinl(ang);
+    if (c->prec == NFFTCU_DOUBLE) {
+      ((double *) host.data())[2 * q] = (double) cr;
+      ((double *) host.data())[2 * q + 1] = (double) ci;
+    } else {
+      ((float *) host.data())[2 * q] = (float) cr;
+      ((float *) host.data())[2 * q + 1] = (float) ci;
+    }
+  }
+  NFFTCU_CUDA(cudaMalloc(out, host.size()));
+  NFFTCU_CUDA(cudaMemcpy(*out, host.data(), host.size(), cudaMemcpyHostToDevice));
+  return NFFTCU_OK;
+}
+
+int plan_line(const nfftcu_ctx *c, long long len, FftLine &ln) {
+  ln.len = len;
+  if (len == 1) { ln.kind = 0; return NFFTCU_OK; }
+  if (ilog2_exact(len) >= 0) ln.kind = 1;
+  else ln.kind = factorize(len, ln) ? 3 : 2;
+  return upload_twiddles(c, len, 1, len, &ln.tw);
+}
+
+// one pass of shared-memory transforms of length ln.len over lines described by g (bundle etc. filled in here)
+template <typename T>
+int run_pass(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *src, void *dst) {
+  typedef typename Cplx<T>::type C;
+  const int pad = 1;
+  g.len = ln.len;
+  g.pitch = (int) ln.len + pad;
+  const size_t line_bytes = 2 * (size_t) g.pitch * sizeof(C);   // two buffers
+  int pref = (int) (128 / sizeof(C));                           // 128-byte global segments
+  if (g.inner == 1) pref = (int) max(1ll, min(8ll, 2048ll / ln.len));
+  if (g.inner == 1 && g.tstore) pref = (int) (128 / sizeof(C));  // the transposed store runs along the bundle
+  int fit = (int) (kSmemBudget / line_bytes);
+  if (fit < 1) {
+    set_error("FFT: length %lld does not fit the shared-memory kernel", (long long) ln.len);
+    return NFFTCU_EINVAL;
+  }
+  g.bundle = pref < fit ? pref : fit;
+  if (g.inner > 1 && (long long) g.bundle > g.inner) g.bundle = (int) g.inner;
+  g.bundles_inner = g.inner == 1 ? 1 : (g.inner + g.bundle - 1) / g.bundle;
+  if (g.bundle > 64) g.bundle = 64;   // line_base[] of stage_lines
+  const long long nb = g.inner == 1 ? (g.lines + g.bundle - 1) / g.bundle
+                                    : (g.lines / g.inner) * g.bundles_inner;
+  if (nb > 0x7fffffffll) {
+    set_error("FFT: too many line bundles (%lld)", nb);
+    return NFFTCU_EINVAL;
+  }
+  const size_t smem = line_bytes * g.bundle;
+  if (ln.kind == 1) {
+    NFFTCU_CUDA(cudaFuncSetAttribute(fft_stockham_kernel<T>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    fft_stockham_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>(
+        (C *) src, (C *) dst, (const C *) ln.tw, g, sign, ilog2_exact(ln.len));
+  } else if (ln.kind == 3) {
+    RadixPlan rp;
+    rp.nst = ln.nst;
+    for (int i = 0; i < 24; i++) rp.radix[i] = ln.radix[i];
+    NFFTCU_CUDA(cudaFuncSetAttribute(fft_mixed_kernel<T>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    fft_mixed_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>((C *) src, (C *) dst, (const C *) ln.tw, g,
+                                                                         sign, rp);
+  } else {
+    NFFTCU_CUDA(cudaFuncSetAttribute(dft_table_kernel<T>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    dft_table_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>((C *) src, (C *) dst, (const C *) ln.tw, g,
+                                                                         sign);
+  }
+  c->launches++;
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
 template <typename T>
 int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
-  typedef typename Cplx<T>::type C;
   const FftAxis &ax = c->fft[t];
-  if (ax.kind == 0) return NFFTCU_OK;
+  if (ax.len == 1) return NFFTCU_OK;
   LineGeom g;
-  g.len = ax.len;
-  g.inner = 1;
-  for (int t2 = t + 1; t2 < c->d; t2++) g.inner *= c->n[t2];
-  g.lines = c->n_total / ax.len;
+  memset(&g, 0, sizeof(g));
+  long long inner = 1, outer_full = 1;
+  for (int t2 = t + 1; t2 < c->d; t2++) inner *= c->n[t2];
+  for (int s2 = 0; s2 < t; s2++) outer_full *= c->n[s2];
+  if (ax.split) {
+    // column pass: [outer][L1][L2 * inner], transform over L1, twiddle at the store, in place
+    const long long L1 = ax.sub1.len, L2 = ax.sub2.len;
+    g.inner = L2 * inner;
+    g.lines = outer_full * g.inner;
+    g.twist = 1;
+    g.tw_I = inner;
+    g.twA = ax.twA;
+    g.twB = ax.twB;
+    g.tw_shift = ax.tw_shift;
+    NFFTCU_TRY(run_pass<T>(c, ax.sub1, g, sign, c->grid, c->grid));
+    // row pass: [outer * L1][L2][inner], transform over L2, transposed store into the second buffer
+    memset(&g, 0, sizeof(g));
+    g.inner = inner;
+    g.lines = outer_full * L1 * inner;
+    g.tstore = 1;
+    g.tL1 = L1;
+    g.tL2 = L2;
+    g.tI = inner;
+    NFFTCU_TRY(run_pass<T>(c, ax.sub2, g, sign, c->grid, c->grid2));
+    void *tmp = c->grid; c->grid = c->grid2; c->grid2 = tmp;
+    return NFFTCU_OK;
+  }
+  g.inner = inner;
   g.prune = pruned ? (sign < 0 ? 1 : 2) : 0;
   g.nouter = t;
   long long outer = 1;
@@ -238,77 +509,62 @@ int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
   g.elow = c->N[t] - c->N[t] / 2;
   g.ehigh = c->n[t] - c->N[t] / 2;
   g.lines = outer * g.inner;
-  const int pad = 1;
-  g.pitch = (int) ax.len + pad;
-  const size_t line_bytes = 2 * (size_t) g.pitch * sizeof(C);   // two buffers
-  int pref = (int) (128 / sizeof(C));                           // 128-byte global segments
-  if (g.inner == 1) pref = (int) max(1ll, min(8ll, 2048ll / ax.len));
-  int fit = (int) (kSmemBudget / line_bytes);
-  if (fit < 1) {
-    set_error("FFT axis %d: length %lld does not fit the shared-memory kernel", t, (long long) ax.len);
-    return NFFTCU_EINVAL;
-  }
-  g.bundle = pref < fit ? pref : fit;
-  if (g.inner > 1 && (long long) g.bundle > g.inner) g.bundle = (int) g.inner;
-  g.bundles_inner = g.inner == 1 ? 1 : (g.inner + g.bundle - 1) / g.bundle;
-  if (g.bundle > 64) g.bundle = 64;   // line_base[] of stage_lines
-  const long long nb = g.inner == 1 ? (g.lines + g.bundle - 1) / g.bundle
-                                    : (g.lines / g.inner) * g.bundles_inner;
-  const size_t smem = line_bytes * g.bundle;
-  if (ax.kind == 1) {
-    NFFTCU_CUDA(cudaFuncSetAttribute(fft_stockham_kernel<T>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
-    fft_stockham_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>(
-        (C *) c->grid, (const C *) ax.tw, g, sign, ilog2_exact(ax.len));
-  } else {
-    NFFTCU_CUDA(cudaFuncSetAttribute(dft_table_kernel<T>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
-    dft_table_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>((C *) c->grid,
-                                                                         (const C *) ax.tw, g, sign);
-  }
-  c->launches++;
-  NFFTCU_CUDA(cudaGetLastError());
-  return NFFTCU_OK;
+  return run_pass<T>(c, ax.whole, g, sign, c->grid, c->grid);
 }
 
 }  // namespace
 
 int fft_plan_axes(nfftcu_ctx *c) {
-  const long double two_pi = 6.283185307179586476925286766559005768394L;
+  const long long fit = max_line_len(c);
   for (int t = 0; t < c->d; t++) {
     FftAxis &ax = c->fft[t];
     ax.len = c->n[t];
-    if (ax.len == 1) { ax.kind = 0; continue; }
-    ax.kind = ilog2_exact(ax.len) >= 0 ? 1 : 2;
-    const size_t esz = 2 * real_size(c);
-    std::vector<unsigned char> host(esz * (size_t) ax.len);
-    for (long long q = 0; q < ax.len; q++) {
-      const long double ang = two_pi * (long double) q / (long double) ax.len;
-      const long double cr = cosl(ang), ci = -sinl(ang);
-      if (c->prec == NFFTCU_DOUBLE) {
-        ((double *) host.data())[2 * q] = (double) cr;
-        ((double *) host.data())[2 * q + 1] = (double) ci;
-      } else {
-        ((float *) host.data())[2 * q] = (float) cr;
-        ((float *) host.data())[2 * q + 1] = (float) ci;
-      }
+    ax.split = false;
+    if (ax.len <= fit) {
+      NFFTCU_TRY(plan_line(c, ax.len, ax.whole));
+      continue;
     }
-    NFFTCU_CUDA(cudaMalloc(&ax.tw, host.size()));
-    NFFTCU_CUDA(cudaMemcpy(ax.tw, host.data(), host.size(), cudaMemcpyHostToDevice));
+    // four-step: the divisor pair (L1, L2) closest to sqrt(len) with both factors fitting one CTA
+    long long best = 0;
+    for (long long a = 2; a * a <= ax.len; a++)
+      if (ax.len % a == 0 && ax.len / a <= fit) best = a;   // a <= sqrt(len) <= len / a
+    if (!best) {
+      set_error("FFT axis %d: length %lld neither fits shared memory (max %lld) nor splits into two such factors",
+                t, (long long) ax.len, fit);
+      return NFFTCU_EINVAL;
+    }
+    ax.split = true;
+    NFFTCU_TRY(plan_line(c, best, ax.sub1));
+    NFFTCU_TRY(plan_line(c, ax.len / best, ax.sub2));
+    // W_len^q, q < len, as twA[q >> s] * twB[q & (2^s - 1)]
+    int s = 0;
+    while ((1ll << (2 * s)) < ax.len) s++;
+    ax.tw_shift = s;
+    NFFTCU_TRY(upload_twiddles(c, (ax.len >> s) + 1, 1ll << s, ax.len, &ax.twA));
+    NFFTCU_TRY(upload_twiddles(c, 1ll << s, 1, ax.len, &ax.twB));
+    c->fft_no_prune = true;
+    if (!c->grid2) NFFTCU_CUDA(cudaMalloc(&c->grid2, 2 * real_size(c) * (size_t) c->n_total));
   }
   return NFFTCU_OK;
 }
 
 void fft_free_axes(nfftcu_ctx *c) {
   for (int t = 0; t < c->d; t++) {
-    if (c->fft[t].tw) cudaFree(c->fft[t].tw);
-    c->fft[t].tw = nullptr;
+    FftAxis &ax = c->fft[t];
+    void **ptrs[] = {&ax.whole.tw, &ax.sub1.tw, &ax.sub2.tw, &ax.twA, &ax.twB};
+    for (void **p : ptrs) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+    }
   }
+  if (c->grid2) cudaFree(c->grid2);
+  c->grid2 = nullptr;
 }
 
 // pruned: the caller guarantees the band structure described in the header (trafo: grid written by the
 // sparse D; adjoint: only the band of the result is read by D^T)
 int stage_F(nfftcu_ctx *c, int sign, bool pruned) {
+  if (c->fft_no_prune) pruned = false;
   // forward (and every unpruned transform): last axis first; pruned backward: first axis first
   const bool last_first = !(pruned && sign > 0);
   for (int i = 0; i < c->d; i++) {
