@@ -118,6 +118,56 @@ typedef ptrdiff_t NFFT_INT;
 NFFT_B200_DEFINE_API(NFFT_B200_MANGLE_DOUBLE, double, nfft_b200_cdouble)
 NFFT_B200_DEFINE_API(NFFT_B200_MANGLE_FLOAT, float, nfft_b200_cfloat)
 
+/* ---- inverse-NFFT solver (layout of include/nfft3.h:758-786, SOLVER_DEFINE_API, complex variant) ------------
+ * solver_*_complex / solverf_*_complex of libnfft3_b200.so run the iteration on the device (include/nfftcu.h,
+ * nfftcu_solver_*) when mv is an NFFT plan of this library; any other mv plan is refused loudly (link the
+ * reference's kernel/solver/solver.c for those -- it runs unmodified on top of nfft_trafo / nfft_adjoint).
+ * Host members: y, w, w_hat and the initial f_hat_iter are read at solver_before_loop; f_hat_iter, r_iter and all
+ * scalar members are current after every call; z_hat_iter, p_hat_iter and v_iter are allocated as in the
+ * reference but only refreshed when the environment variable NFFT_B200_SOLVER_MIRROR_ALL is set. */
+#define NFFT_B200_DEFINE_SOLVER_API(X, Y, R, C)                                                  \
+  typedef struct {                                                                               \
+    Y(mv_plan_complex) *mv;                                                                      \
+    unsigned flags;                                                                              \
+    R *w;                                                                                        \
+    R *w_hat;                                                                                    \
+    C *y;                                                                                        \
+    C *f_hat_iter;                                                                               \
+    C *r_iter;                                                                                   \
+    C *z_hat_iter;                                                                               \
+    C *p_hat_iter;                                                                               \
+    C *v_iter;                                                                                   \
+    R alpha_iter;                                                                                \
+    R beta_iter;                                                                                 \
+    R dot_r_iter;                                                                                \
+    R dot_r_iter_old;                                                                            \
+    R dot_z_hat_iter;                                                                            \
+    R dot_z_hat_iter_old;                                                                        \
+    R dot_p_hat_iter;                                                                            \
+    R dot_v_iter;                                                                                \
+  } X(plan_complex);                                                                             \
+  void X(init_advanced_complex)(X(plan_complex) *ths, Y(mv_plan_complex) *mv, unsigned flags);   \
+  void X(init_complex)(X(plan_complex) *ths, Y(mv_plan_complex) *mv);                            \
+  void X(before_loop_complex)(X(plan_complex) *ths);                                             \
+  void X(loop_one_step_complex)(X(plan_complex) *ths);                                           \
+  void X(finalize_complex)(X(plan_complex) *ths);
+
+#define NFFT_B200_SOLVER_MANGLE_DOUBLE(name) solver_##name
+#define NFFT_B200_SOLVER_MANGLE_FLOAT(name) solverf_##name
+NFFT_B200_DEFINE_SOLVER_API(NFFT_B200_SOLVER_MANGLE_DOUBLE, NFFT_B200_MANGLE_DOUBLE, double, nfft_b200_cdouble)
+NFFT_B200_DEFINE_SOLVER_API(NFFT_B200_SOLVER_MANGLE_FLOAT, NFFT_B200_MANGLE_FLOAT, float, nfft_b200_cfloat)
+
+/* solver flags (values of include/nfft3.h:823-829) */
+#ifndef LANDWEBER
+#define LANDWEBER (1U << 0)
+#define STEEPEST_DESCENT (1U << 1)
+#define CGNR (1U << 2)
+#define CGNE (1U << 3)
+#define NORMS_FOR_LANDWEBER (1U << 4)
+#define PRECOMPUTE_WEIGHT (1U << 5)
+#define PRECOMPUTE_DAMP (1U << 6)
+#endif
+
 /* plan flags (values of include/nfft3.h:195-208) */
 #ifndef PRE_PHI_HUT
 #define PRE_PHI_HUT (1U << 0)

@@ -147,6 +147,35 @@ int nfftcu_free_pinned(void *ptr);
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int nfftcu_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 
+/* ---- device-resident inverse-NFFT iterations --------------------------------------------------------------
+ * Replaces the host loops of kernel/solver/solver.c (solver_before_loop_complex 81-125, solver_loop_one_step_complex
+ * 347-360 with LANDWEBER 128-174, STEEPEST_DESCENT 177-229, CGNR 232-292, CGNE 295-344) and the vector kernels of
+ * kernel/util/vector1.c-vector3.c they call, for an mv plan that is an NFFT plan of this library: all vectors stay
+ * in HBM, alpha / beta are computed on the device, one synchronisation per step.  `flags` are the reference's solver
+ * flags (include/nfft3.h:823-829).  The reference-facing wrappers solver_*_complex / solverf_*_complex of
+ * libnfft3_b200.so sit on top of these. */
+typedef struct nfftcu_solver_s nfftcu_solver;
+#define NFFTCU_SOLVER_Y 0            /* M complex: right-hand side                      (solver_plan_complex.y) */
+#define NFFTCU_SOLVER_W 1            /* M reals, PRECOMPUTE_WEIGHT                      (.w) */
+#define NFFTCU_SOLVER_W_HAT 2        /* N_total reals, PRECOMPUTE_DAMP                  (.w_hat) */
+#define NFFTCU_SOLVER_F_HAT_ITER 3   /* N_total complex: iterate                        (.f_hat_iter) */
+#define NFFTCU_SOLVER_R_ITER 4       /* M complex: residual                             (.r_iter) */
+#define NFFTCU_SOLVER_Z_HAT_ITER 5   /* N_total complex; aliases P_HAT_ITER unless CGNR (.z_hat_iter) */
+#define NFFTCU_SOLVER_P_HAT_ITER 6   /* N_total complex: search direction               (.p_hat_iter) */
+#define NFFTCU_SOLVER_V_ITER 7       /* M complex, CGNR / STEEPEST_DESCENT              (.v_iter) */
+/* scal[8] = alpha_iter, beta_iter, dot_r_iter, dot_r_iter_old, dot_z_hat_iter, dot_z_hat_iter_old, dot_p_hat_iter,
+ * dot_v_iter (the scalar members of solver_plan_complex, include/nfft3.h:772-779), as doubles */
+int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags);
+int nfftcu_solver_destroy(nfftcu_solver *s);
+int nfftcu_solver_upload(nfftcu_solver *s, int which, const void *host);      /* host -> device vector */
+int nfftcu_solver_download(nfftcu_solver *s, int which, void *host);          /* device vector -> host */
+void *nfftcu_solver_vector(nfftcu_solver *s, int which);                      /* device pointer */
+/* r = y - A f_hat_iter, z_hat = A^H (w r), initial norms.  f_hat_iter_host / r_iter_host (may be NULL) receive the
+ * host mirrors of the iterate and the residual; scal receives the scalars. */
+int nfftcu_solver_before_loop(nfftcu_solver *s, void *f_hat_iter_host, void *r_iter_host, double scal[8]);
+/* one iteration.  LANDWEBER reads scal[0] (alpha_iter is set by the caller in the reference too). */
+int nfftcu_solver_step(nfftcu_solver *s, void *f_hat_iter_host, void *r_iter_host, double scal[8]);
+
 #ifdef __cplusplus
 }
 #endif

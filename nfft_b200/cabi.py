@@ -29,6 +29,8 @@ SYMBOLS = (
     "nfftcu_set_stream", "nfftcu_get_stream", "nfftcu_sync", "nfftcu_stage_times", "nfftcu_b_kernel_time", "nfftcu_trafo_refresh", "nfftcu_adjoint_refresh",
     "nfftcu_launch_count", "nfftcu_malloc_device", "nfftcu_free_device", "nfftcu_malloc_pinned",
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
+    "nfftcu_solver_create", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
+    "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
 )
 
 

@@ -125,6 +125,13 @@ static void nodes_for_transform(X(plan) *ths)
     upload_nodes(ths);
 }
 
+/* for solver_host.c: same freshness rule as nfft_trafo, once per solver step */
+__attribute__((visibility("hidden"))) void X(b200_nodes_for_transform)(X(plan) *ths)
+{
+  if (!(ths->flags & NODE_BOUND_FLAGS)) upload_nodes(ths);
+  else nodes_for_transform(ths);
+}
+
 static void store_times(X(plan) *ths)
 {
   float ms[3];

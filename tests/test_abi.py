@@ -43,6 +43,10 @@ def test_host_layer_exports_reference_plan_api():
             assert hasattr(L, prefix + fn), prefix + fn
         for hook in ("malloc_hook", "free_hook", "die_hook"):
             C.c_void_p.in_dll(L, prefix + hook)
+    for prefix in ("solver_", "solverf_"):   # include/nfft3.h:782-786, device-resident (solver_host.c)
+        for fn in ("init_advanced_complex", "init_complex", "before_loop_complex", "loop_one_step_complex",
+                   "finalize_complex"):
+            assert hasattr(L, prefix + fn), prefix + fn
     assert not hasattr(L, "nfftl_trafo")   # long double is deliberately not provided
 
 
@@ -81,6 +85,34 @@ def test_plan_layout_ctypes_matches_our_header():
 def test_plan_layout_matches_reference_header():
     ref = _offsets_from_c(["/root/reference/include", os.path.join(ROOT, "oracle", "refbuild")], "nfft3.h")
     assert ref == _ctypes_offsets()
+
+
+SOLVER_MEMBERS = ("mv", "flags", "w", "w_hat", "y", "f_hat_iter", "r_iter", "z_hat_iter", "p_hat_iter", "v_iter",
+                  "alpha_iter", "beta_iter", "dot_r_iter", "dot_r_iter_old", "dot_z_hat_iter", "dot_z_hat_iter_old",
+                  "dot_p_hat_iter", "dot_v_iter")
+
+
+def _solver_offsets(include_dirs, header):
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include <complex.h>\n#include "%s"\nint main(void){\n' % header
+    for typ in ("solver_plan_complex", "solverf_plan_complex"):
+        src += f'printf("{typ} sizeof %zu\\n", sizeof({typ}));\n'
+        for mname in SOLVER_MEMBERS:
+            src += f'printf("{typ} {mname} %zu\\n", offsetof({typ}, {mname}));\n'
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as td:
+        cfile, exe = os.path.join(td, "o.c"), os.path.join(td, "o")
+        open(cfile, "w").write(src)
+        subprocess.run([GCC, "-std=gnu99", "-w"] + [f"-I{d}" for d in include_dirs] + [cfile, "-o", exe], check=True)
+        return subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/include/nfft3.h"),
+                    reason="reference header only exists in the build container")
+def test_solver_plan_layout_matches_reference_header():
+    """solver_plan_complex of nfft3_b200.h (device-resident solver) vs include/nfft3.h:760-780."""
+    ours = _solver_offsets([os.path.join(ROOT, "include")], "nfft3_b200.h")
+    ref = _solver_offsets(["/root/reference/include", os.path.join(ROOT, "oracle", "refbuild")], "nfft3.h")
+    assert ours == ref and "solverf_plan_complex dot_v_iter" in ours
 
 
 def test_fails_loudly_without_gpu():

@@ -512,12 +512,76 @@ def test_reference_solver_runs_on_the_engine(d, N, n, M, solver):
         ia = lambda a: (C.c_int * len(a))(*a)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = fn(C.c_int(d), ia(N), C.c_int(M), ia(n), C.c_int(m), C.c_uint(nfft_flags), C.c_uint(sflags),
-                p(x), p(y), p(w), p(w_hat), C.c_int(iters), p(f_hat), p(dots))
+                p(x), p(y), p(w), p(w_hat), C.c_int(iters), p(f_hat), p(dots), C.c_double(0.0), None)
         assert rc == 0
         outs.append((f_hat, dots))
     assert np.all(np.isfinite(outs[1][0]))
     assert rel_l2(outs[1][0], outs[0][0]) <= 1e-9
     assert np.allclose(outs[1][1], outs[0][1], rtol=1e-8, atol=0)
+
+
+# ---- (10b) the device-resident solver behind the reference's solver_* API ------------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("d,N,n,M,solver", [
+    (2, [32, 32], [64, 64], 3000, "cgnr_damp"),
+    (2, [32, 32], [64, 64], 3000, "cgnr_weight_damp"),
+    (2, [32, 32], [64, 64], 800, "cgne_weight"),
+    (2, [32, 32], [64, 64], 800, "cgne_damp"),
+    (2, [24, 40], [48, 80], 2500, "steepest_weight_damp"),
+    (2, [24, 40], [48, 80], 2500, "landweber_norms_damp"),
+    (2, [24, 40], [48, 80], 2500, "landweber"),
+    (3, [16, 16, 16], [32, 32, 32], 6000, "cgnr_damp"),
+    (1, [128], [256], 400, "cgnr"),
+])
+def test_device_solver_vs_reference(d, N, n, M, solver, precision):
+    """solver_*_complex / solverf_*_complex of libnfft3_b200.so (device-resident iteration: solver.cu behind
+    solver_host.c) against the reference's kernel/solver/solver.c on the reference's own nfft.c, same driver
+    (oracle/refbuild/solver_driver.c), 10 iterations: iterate, residual vector and residual norms."""
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    so_ref, so_dev = os.path.join(ref_dir, "libsolver_ref.so"), os.path.join(ref_dir, "libsolver_dev_b200.so")
+    if not (os.path.exists(so_ref) and os.path.exists(so_dev)):
+        pytest.skip("oracle/_ref/libsolver_*.so not built (needs /root/reference at build time)")
+    LANDWEBER, STEEPEST, CGNR, CGNE, NORMS, PRE_W, PRE_D = (1 << i for i in range(7))
+    sflags = {"cgnr": CGNR, "cgnr_damp": CGNR | PRE_D, "cgnr_weight_damp": CGNR | PRE_W | PRE_D,
+              "cgne_weight": CGNE | PRE_W, "cgne_damp": CGNE | PRE_D,
+              "steepest_weight_damp": STEEPEST | PRE_W | PRE_D,
+              "landweber_norms_damp": LANDWEBER | NORMS | PRE_D, "landweber": LANDWEBER}[solver]
+    real, cplx, creal = ((np.float64, np.complex128, C.c_double) if precision == "double"
+                         else (np.float32, np.complex64, C.c_float))
+    rng = np.random.default_rng(5)
+    m, iters = 6, 10
+    x = np.ascontiguousarray((rng.random((M, d)) - 0.5).astype(real))
+    if precision == "float":
+        x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
+    NN = int(np.prod(N))
+    y = np.ascontiguousarray((rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(cplx))
+    w = np.ascontiguousarray((0.5 + rng.random(M)).astype(real))
+    k = np.stack(np.meshgrid(*[np.arange(-v // 2, v // 2) / v for v in N], indexing="ij"), -1)
+    w_hat = np.ascontiguousarray((np.sqrt((k ** 2).sum(-1)) <= 0.5).astype(real).ravel())
+    nfft_flags = (abi.PRE_PHI_HUT | abi.PRE_PSI | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+                  | abi.FFT_OUT_OF_PLACE)
+    alpha = 0.5 / M   # Landweber step well inside 2 / ||A||^2
+    outs = []
+    for so in (so_ref, so_dev):
+        L = C.CDLL(so, mode=os.RTLD_LOCAL)
+        fn = L.solver_driver_run if precision == "double" else L.solver_driver_run_f
+        fn.restype = C.c_int
+        f_hat = np.zeros(NN, dtype=cplx)
+        r = np.zeros(M, dtype=cplx)
+        dots = np.zeros(iters, dtype=real)
+        ia = lambda a: (C.c_int * len(a))(*a)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = fn(C.c_int(d), ia(N), C.c_int(M), ia(n), C.c_int(m), C.c_uint(nfft_flags), C.c_uint(sflags),
+                p(x), p(y), p(w), p(w_hat), C.c_int(iters), p(f_hat), p(dots), creal(alpha), p(r))
+        assert rc == 0
+        outs.append((f_hat, dots, r))
+    tol = 1e-9 if precision == "double" else 2e-3
+    assert np.all(np.isfinite(outs[1][0]))
+    assert np.linalg.norm(outs[0][0]) > 0
+    assert rel_l2(outs[1][0], outs[0][0]) <= tol
+    assert rel_l2(outs[1][2], outs[0][2]) <= tol
+    if not (sflags & LANDWEBER) or (sflags & NORMS):
+        assert np.allclose(outs[1][1], outs[0][1], rtol=10 * tol, atol=0)
 
 
 # ---- (11) the reference's kernel/mri and applications/fastsum, unmodified, on top of the engine -----------
