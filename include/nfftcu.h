@@ -51,6 +51,7 @@ typedef struct nfftcu_ctx_s nfftcu_ctx;
 #define NFFTCU_OPT_B_KERNEL 3      /* 0 auto | 1 generic gather/scatter | 2 register pencils | 3 DMMA */
 #define NFFTCU_OPT_B_FLUSH 5       /* DMMA spreading: 0 auto | 1 RED.ADD from registers | 2 staged TMA bulk reductions */
 #define NFFTCU_OPT_FFT_PRUNE 6     /* 1 (default): band-pruned FFT passes and D without zero padding inside trafo/adjoint | 0: full passes */
+#define NFFTCU_OPT_FFT_KERNEL 7    /* 0 auto (register-resident Stockham for 2^k lengths 64..2048) | 1 shared-memory Stockham only */
 #define NFFTCU_OPT_NODE_ORDER 4    /* 0 auto | 1 reference row-major key | 2 tile-binned */
 
 const char *nfftcu_last_error(void);

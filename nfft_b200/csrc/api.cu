@@ -559,6 +559,7 @@ int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
     case NFFTCU_OPT_NODE_ORDER: c->opt_node_order = (int) value; break;
     case NFFTCU_OPT_B_FLUSH: c->opt_b_flush = (int) value; break;
     case NFFTCU_OPT_FFT_PRUNE: c->opt_fft_prune = (int) value; break;
+    case NFFTCU_OPT_FFT_KERNEL: c->opt_fft_kernel = (int) value; break;
     default:
       set_error("nfftcu_set_option: unknown option %d", option);
       return NFFTCU_EINVAL;

@@ -131,6 +131,7 @@ struct nfftcu_ctx_s {
   int opt_b_kernel = 0;
   int opt_node_order = 0;
   int opt_b_flush = 0;
+  int opt_fft_kernel = 0;           // 0 auto | 1 shared-memory Stockham only (fft_stockham_kernel)
   int opt_fft_prune = 1;            // band-pruned FFT passes + D without zero padding inside trafo / adjoint
   int sm_count = 148;
 };

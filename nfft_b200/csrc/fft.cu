@@ -227,6 +227,187 @@ fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>:
   stage_lines<C, true>(out_data, src, g, b, sign);
 }
 
+// ---- power-of-two lengths 64 ... 2048: register-resident Stockham ---------------------------------------
+// A line of L = 16 * TPL points is owned by TPL threads, 16 points per thread in registers for the whole
+// transform.  L = R1 * R2 (* R3) with radices 4, 8, 16: a step with radix R does 16 / R butterflies per thread
+// entirely in registers (DFT8 = 2 x 4, DFT16 = 4 x 4 with constant twiddles), the inter-step twiddles come from the
+// per-axis table, and steps exchange data through ONE shared-memory buffer (one write + one read per element and
+// exchange, against two per radix-4 stage in fft_stockham_kernel).  The Stockham index maps make every thread's
+// global loads (first step) and stores (last step) the elements t + TPL * e, e < 16: for strided axes the lanes run
+// along the bundle of neighbouring lines (128-byte segments), for the contiguous axis along t.
+// Element i of a line sits at i + i / 16 of its shared-memory row (conflict-free 16-byte quarter-warp accesses), rows
+// are pitched to an odd multiple of 16 bytes.
+template <typename C, int SIGN> __device__ __forceinline__ C mul_i(C a) {   // a * (SIGN * i)
+  C r;
+  if (SIGN < 0) { r.x = a.y; r.y = -a.x; } else { r.x = -a.y; r.y = a.x; }
+  return r;
+}
+
+// exp(SIGN * 2 pi i e / 16), e compile-time after unrolling
+template <typename T, int SIGN> __device__ __forceinline__ typename Cplx<T>::type w16(int e) {
+  const T c1 = (T) 0.92387953251128675613, c2 = (T) 0.70710678118654752440, c3 = (T) 0.38268343236508977173;
+  T cr, ci;
+  switch (e & 15) {
+    case 0: cr = 1; ci = 0; break;
+    case 1: cr = c1; ci = c3; break;
+    case 2: cr = c2; ci = c2; break;
+    case 3: cr = c3; ci = c1; break;
+    case 4: cr = 0; ci = 1; break;
+    case 5: cr = -c3; ci = c1; break;
+    case 6: cr = -c2; ci = c2; break;
+    case 7: cr = -c1; ci = c3; break;
+    case 8: cr = -1; ci = 0; break;
+    case 9: cr = -c1; ci = -c3; break;
+    case 10: cr = -c2; ci = -c2; break;
+    case 11: cr = -c3; ci = -c1; break;
+    case 12: cr = 0; ci = -1; break;
+    case 13: cr = c3; ci = -c1; break;
+    case 14: cr = c2; ci = -c2; break;
+    default: cr = c1; ci = -c3; break;
+  }
+  typename Cplx<T>::type r;
+  r.x = cr;
+  r.y = SIGN < 0 ? -ci : ci;
+  return r;
+}
+
+template <typename T, int SIGN> __device__ __forceinline__ void dft4(typename Cplx<T>::type &a, typename Cplx<T>::type &b,
+                                                                     typename Cplx<T>::type &c, typename Cplx<T>::type &d) {
+  typedef typename Cplx<T>::type C;
+  const C t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = mul_i<C, SIGN>(csub(b, d));
+  a = cadd(t0, t2);
+  b = cadd(t1, t3);
+  c = csub(t0, t2);
+  d = csub(t1, t3);
+}
+
+// in-place DFT of x[0..R), natural order in and out
+template <typename T, int SIGN, int R> __device__ __forceinline__ void dft_reg(typename Cplx<T>::type *x) {
+  typedef typename Cplx<T>::type C;
+  if constexpr (R == 4) {
+    dft4<T, SIGN>(x[0], x[1], x[2], x[3]);
+  } else if constexpr (R == 8) {   // n = 4 n1 + n2: DFT2 over n1, twiddle W8^(n2 k1), DFT4 over n2 -> X[k1 + 2 k2]
+    C y[8];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) {
+      y[n2] = cadd(x[n2], x[4 + n2]);
+      C o = csub(x[n2], x[4 + n2]);
+      if (n2 == 1 || n2 == 3) o = cmul(o, w16<T, SIGN>(2 * n2));
+      if (n2 == 2) o = mul_i<C, SIGN>(o);
+      y[4 + n2] = o;
+    }
+    dft4<T, SIGN>(y[0], y[1], y[2], y[3]);
+    dft4<T, SIGN>(y[4], y[5], y[6], y[7]);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) { x[2 * k2] = y[k2]; x[2 * k2 + 1] = y[4 + k2]; }
+  } else {               // R == 16, n = 4 n1 + n2: DFT4 over n1, twiddle W16^(n2 k1), DFT4 over n2 -> X[k1 + 4 k2]
+    C y[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) {
+      C a = x[n2], b = x[4 + n2], c = x[8 + n2], d = x[12 + n2];
+      dft4<T, SIGN>(a, b, c, d);
+      y[n2] = a;   // k1 = 0
+      if (n2 == 0) { y[4] = b; y[8] = c; y[12] = d; }
+      else {
+        y[4 + n2] = cmul(b, w16<T, SIGN>(n2));
+        y[8 + n2] = (2 * n2 == 4) ? mul_i<C, SIGN>(c) : cmul(c, w16<T, SIGN>(2 * n2));
+        y[12 + n2] = cmul(d, w16<T, SIGN>(3 * n2));
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+      dft4<T, SIGN>(y[4 * k1], y[4 * k1 + 1], y[4 * k1 + 2], y[4 * k1 + 3]);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; k2++) x[k1 + 4 * k2] = y[4 * k1 + k2];
+    }
+  }
+}
+
+__device__ __forceinline__ int reg_pad(int i) { return i + (i >> 4); }
+
+// one Stockham step with radix R after NS = product of the earlier radices on the 16 register values of thread t;
+// results go to the shared-memory row (LAST = false) or stay in v in global order t + TPL * e (LAST = true)
+template <typename T, int SIGN, int L, int R, int NS, bool LAST>
+__device__ __forceinline__ void reg_step(typename Cplx<T>::type *v, int t, const typename Cplx<T>::type *__restrict__ tw,
+                                         typename Cplx<T>::type *row) {
+  typedef typename Cplx<T>::type C;
+  constexpr int TPL = L / 16, U = 16 / R;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const int jj = t + TPL * u;
+    const int k = jj & (NS - 1);
+    C x[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      x[q] = v[u + q * U];
+      if (NS > 1 && q > 0) {
+        C wq = tw[q * k * (L / (NS * R))];
+        if (SIGN > 0) wq.y = -wq.y;
+        x[q] = cmul(x[q], wq);
+      }
+    }
+    dft_reg<T, SIGN, R>(x);
+#pragma unroll
+    for (int pq = 0; pq < R; pq++) {
+      if (LAST) v[u + pq * U] = x[pq];   // (jj - k) R + k + pq NS == jj + pq L / R == t + TPL (u + pq U)
+      else row[reg_pad((jj - k) * R + k + pq * NS)] = x[pq];
+    }
+  }
+}
+
+template <typename T, int SIGN, int R1, int R2, int R3>
+__global__ void __launch_bounds__(256)
+fft_reg_kernel(typename Cplx<T>::type *__restrict__ data, const typename Cplx<T>::type *__restrict__ tw, LineGeom g) {
+  typedef typename Cplx<T>::type C;
+  constexpr int L = R1 * R2 * R3, TPL = L / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long b = blockIdx.x;
+  const int cnt = bundle_count<C>(g, b);
+  int cl, t;
+  if (g.inner == 1) { t = threadIdx.x % TPL; cl = threadIdx.x / TPL; }
+  else { cl = threadIdx.x % g.bundle; t = threadIdx.x / g.bundle; }
+  const bool active = cl < cnt;
+  C *row = reinterpret_cast<C *>(smem_raw) + (size_t) cl * g.pitch;
+  C *base = data;
+  long long stride = 1;
+  if (active) {
+    if (g.inner == 1) base += map_outer(g, b * g.bundle + cl) * L;
+    else {
+      const long long oc = b / g.bundles_inner;
+      base += map_outer(g, oc) * L * g.inner + (b - oc * g.bundles_inner) * g.bundle + cl;
+      stride = g.inner;
+    }
+  }
+  C v[16];
+#pragma unroll
+  for (int e = 0; e < 16; e++) {
+    const int i = t + TPL * e;
+    const bool in_band = g.prune != 1 || i < g.elow || i >= g.ehigh;
+    v[e] = (active && in_band) ? base[(long long) i * stride] : C{0, 0};
+  }
+  reg_step<T, SIGN, L, R1, 1, false>(v, t, tw, row);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 16; e++) v[e] = row[reg_pad(t + TPL * e)];
+  if (R3 > 1) {
+    __syncthreads();
+    reg_step<T, SIGN, L, R2, R1, false>(v, t, tw, row);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = row[reg_pad(t + TPL * e)];
+    reg_step<T, SIGN, L, (R3 > 1 ? R3 : 4), R1 * R2, true>(v, t, tw, row);
+  } else {
+    reg_step<T, SIGN, L, R2, R1, true>(v, t, tw, row);
+  }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      const int i = t + TPL * e;
+      if (g.prune != 2 || i < g.elow || i >= g.ehigh) base[(long long) i * stride] = v[e];
+    }
+  }
+}
+
 // ---- any length with prime factors <= 61: mixed-radix Stockham in shared memory ------------------
 // Stage with radix R after Ns = product of the earlier radices: butterfly j in [0, L/R), k = j mod Ns,
 //   v[q] = src[j + q L/R] * W_L^(q k L/(Ns R)),  dst[(j - k) R + k + p Ns] = sum_q v[q] W_R^(p q).
@@ -413,10 +594,63 @@ int plan_line(const nfftcu_ctx *c, long long len, FftLine &ln) {
   return upload_twiddles(c, len, 1, len, &ln.tw);
 }
 
+template <typename T, int R1, int R2, int R3>
+int launch_reg(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *data) {
+  typedef typename Cplx<T>::type C;
+  constexpr int L = R1 * R2 * R3, TPL = L / 16;
+  int bundle = 256 / TPL;                                  // 256 threads per CTA at most
+  const int seg = (int) (128 / sizeof(C));                 // lines per 128-byte segment of a strided axis
+  if (g.inner > 1 && bundle > seg) bundle = seg;
+  if (g.inner == 1 && bundle > 8) bundle = 8;
+  if (g.inner > 1 && (long long) bundle > g.inner) bundle = (int) g.inner;
+  if (bundle < 1) bundle = 1;
+  g.len = L;
+  g.bundle = bundle;
+  g.bundles_inner = g.inner == 1 ? 1 : (g.inner + bundle - 1) / bundle;
+  g.pitch = L + L / 16;
+  while (g.pitch % 8 != 1) g.pitch++;                      // odd multiple of 16 bytes (fp64) between rows
+  const long long nb = g.inner == 1 ? (g.lines + bundle - 1) / bundle : (g.lines / g.inner) * g.bundles_inner;
+  if (nb > 0x7fffffffll) { set_error("FFT: too many line bundles (%lld)", nb); return NFFTCU_EINVAL; }
+  const size_t smem = sizeof(C) * (size_t) g.pitch * bundle;
+  const unsigned threads = (unsigned) (bundle * TPL);
+  if (sign < 0) {
+    NFFTCU_CUDA(cudaFuncSetAttribute(fft_reg_kernel<T, -1, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    fft_reg_kernel<T, -1, R1, R2, R3><<<(unsigned) nb, threads, smem, c->stream>>>((C *) data, (const C *) ln.tw, g);
+  } else {
+    NFFTCU_CUDA(cudaFuncSetAttribute(fft_reg_kernel<T, +1, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    fft_reg_kernel<T, +1, R1, R2, R3><<<(unsigned) nb, threads, smem, c->stream>>>((C *) data, (const C *) ln.tw, g);
+  }
+  c->launches++;
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+// register-resident kernel for this length?  (in place, no twist / transposed store)
+template <typename T>
+int try_reg(nfftcu_ctx *c, const FftLine &ln, const LineGeom &g, int sign, void *data, bool *done) {
+  *done = true;
+  switch (ln.len) {
+    case 64: return launch_reg<T, 8, 8, 1>(c, ln, g, sign, data);
+    case 128: return launch_reg<T, 16, 8, 1>(c, ln, g, sign, data);
+    case 256: return launch_reg<T, 16, 16, 1>(c, ln, g, sign, data);
+    case 512: return launch_reg<T, 8, 8, 8>(c, ln, g, sign, data);
+    case 1024: return launch_reg<T, 16, 16, 4>(c, ln, g, sign, data);
+    case 2048: return launch_reg<T, 16, 16, 8>(c, ln, g, sign, data);
+    default: break;
+  }
+  *done = false;
+  return NFFTCU_OK;
+}
+
 // one pass of shared-memory transforms of length ln.len over lines described by g (bundle etc. filled in here)
 template <typename T>
 int run_pass(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *src, void *dst) {
   typedef typename Cplx<T>::type C;
+  if (ln.kind == 1 && !g.twist && !g.tstore && src == dst && c->opt_fft_kernel != 1) {
+    bool done = false;
+    NFFTCU_TRY(try_reg<T>(c, ln, g, sign, src, &done));
+    if (done) return NFFTCU_OK;
+  }
   const int pad = 1;
   g.len = ln.len;
   g.pitch = (int) ln.len + pad;

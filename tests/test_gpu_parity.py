@@ -460,6 +460,43 @@ def test_pruned_fft_matches_full_passes(N, n, m, M, precision):
     assert np.array_equal(outs[0][0], outs[0][2])
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("prune", [1, 0])
+@pytest.mark.parametrize("N,n,m,M", [
+    ([32], [64], 4, 300), ([64], [128], 6, 500), ([100], [256], 6, 500), ([256], [512], 6, 800),
+    ([512], [1024], 6, 800), ([1024], [2048], 6, 3000),                       # 1-D, contiguous lines: every radix split
+    ([32, 64], [64, 128], 5, 3000), ([128, 30], [256, 64], 4, 3000), ([256, 512], [512, 1024], 4, 8000),
+    ([60, 500], [128, 1024], 3, 4000), ([1000, 20], [2048, 64], 3, 4000),     # strided axis, partial bundles (n1 = 64 ...)
+    ([32, 32, 32], [64, 64, 64], 6, 20000), ([20, 64, 128], [64, 128, 256], 4, 20000),
+    ([128, 128, 128], [256, 256, 256], 6, 50000),                             # the benchmark grid
+])
+def test_register_fft_vs_shared_memory_fft(N, n, m, M, prune, precision):
+    """F with the register-resident Stockham kernel (fft_reg_kernel, default for 2^k lengths 64..2048) against
+    the shared-memory radix-4 Stockham (fft_stockham_kernel, NFFTCU_OPT_FFT_KERNEL = 1), pruned and full passes,
+    both transform directions; the small cases also against the oracle."""
+    rng = np.random.default_rng(78)
+    o = oracle(precision)
+    d = len(N)
+    x = (rng.random((M, d)) - 0.5).astype(o.real)
+    NN = int(np.prod(N))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    outs = []
+    for kernel in (0, 1):
+        eng = cabi.Engine(N, n, m, M, precision=precision)
+        eng.set_option(cabi.OPT_FFT_PRUNE, prune)
+        eng.set_option(cabi.OPT_FFT_KERNEL, kernel)
+        eng.set_nodes(x)
+        outs.append((eng.trafo(fh), eng.adjoint(f)))
+        eng.close()
+    tight = 1e-14 if precision == "double" else 2e-6
+    assert rel_l2(outs[0][0], outs[1][0]) <= tight
+    assert rel_l2(outs[0][1], outs[1][1]) <= tight
+    if int(np.prod(n)) <= 1 << 21:
+        assert rel_l2(outs[0][0], o.trafo(N, n, m, x, fh)) <= TOL[precision]
+        assert rel_l2(outs[0][1], o.adjoint(N, n, m, x, f)) <= TOL[precision]
+
+
 def test_tile3d_z_segments_small_grid_many_nodes():
     """few tiles -> the sweep is split into z segments; every segment flushes / preloads its window."""
     rng = np.random.default_rng(32)
