@@ -72,7 +72,9 @@ int build_kb_poly(nfftcu_ctx *c) {
   c->kbpoly_fit = -1;
   // The device keeps the coefficients of one tap in registers and runs a fixed-length Horner loop, so
   // the table is always stored with kKbPolyDeg+1 coefficients per tap (higher ones zero).
-  for (int p = 10; p <= kKbPolyDeg; p++) {
+  // fp32 plans need the window to ~1e-9 of its peak only (their results carry 1e-7): about half the degree
+  const long double tol = c->prec == NFFTCU_DOUBLE ? 3e-15L : 2e-9L;
+  for (int p = c->prec == NFFTCU_DOUBLE ? 10 : 4; p <= kKbPolyDeg; p++) {
     std::vector<double> coef((size_t) c->d * (kKbPolyDeg + 1) * W, 0.0);
     long double worst = 0;
     for (int t = 0; t < c->d; t++) {
@@ -92,7 +94,7 @@ int build_kb_poly(nfftcu_ctx *c) {
         }
       }
     }
-    if (worst < 3e-15L) {
+    if (worst < tol) {
       c->kbpoly_deg = kKbPolyDeg;   // stored (padded) degree; the fitted degree is p
       c->kbpoly_fit = p;
       c->kbpoly_host = coef;

@@ -243,7 +243,18 @@ struct Shared {
 
 // Producer warp pw (0..3) of the CTA: batches j = pw, pw+4, ... of the unit.  Lane = (node i = lane & 7,
 // slot quarter qg = lane >> 3): 4 slots x 3 dimensions = 12 independent Horner chains per lane.
-template <typename TS, int W, bool SPREAD>
+// TF32 = true (fp32 plans on the TF32 tensor path): the ring entries keep their 8-byte slots but hold fp32 data, so
+// that the conversions happen once per value here and not once per MMA warp: psi2 as the (hi, lo) tf32 pair of the
+// 3xTF32 split, every other operand as one float in the low word.
+__device__ __forceinline__ double pack_tf32_pair(double v) {
+  unsigned hi, lo;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"((float) v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"((float) (v - (double) __uint_as_float(hi))));
+  return __hiloint2double((int) lo, (int) hi);   // low word = hi part, high word = lo part
+}
+__device__ __forceinline__ double pack_f32(double v) { return __hiloint2double(0, __float_as_int((float) v)); }
+
+template <typename TS, int W, bool SPREAD, bool TF32 = false>
 __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__restrict__ xt,
                                               const typename Cplx<TS>::type *__restrict__ ft,
                                               const uint32_t *__restrict__ perm,
@@ -265,14 +276,16 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
       __syncwarp();
     }
   };
-  auto load_nodes = [&](uint2 mt, double &xv, double &fv) {
+  // the prefetched values stay in the storage type until they are used: a conversion right behind the load would
+  // make the warp wait for the load at once
+  auto load_nodes = [&](uint2 mt, TS &xv, TS &fv) {
     const int nb = bt_nb(mt);
-    xv = (lane < 3 * nb) ? (double) xt[3 * (size_t) mt.x + lane] : 0.0;
-    if (SPREAD) fv = (lane < 2 * nb) ? (double) reinterpret_cast<const TS *>(ft)[2 * (size_t) mt.x + lane] : 0.0;
+    xv = (lane < 3 * nb) ? xt[3 * (size_t) mt.x + lane] : (TS) 0;
+    if (SPREAD) fv = (lane < 2 * nb) ? reinterpret_cast<const TS *>(ft)[2 * (size_t) mt.x + lane] : (TS) 0;
   };
   if (pw >= nbat) return;
   uint2 mt = table[pw], mt_next = make_uint2(0, 0);
-  double xv, fv = 0.0, xv_next = 0.0, fv_next = 0.0;
+  TS xv, fv = 0, xv_next = 0, fv_next = 0;
   load_nodes(mt, xv, fv);
   if (pw + 4 < nbat) mt_next = table[pw + 4];
   for (int j = pw; j < nbat; j += 4) {
@@ -288,10 +301,10 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
     const int nb = bt_nb(mt);
     const bool live = i < nb;
     double fr = 0.0, fi = 0.0;
-    if (SPREAD) { fr = __shfl_sync(kFull, fv, 2 * i); fi = __shfl_sync(kFull, fv, 2 * i + 1); }
+    if (SPREAD) { fr = (double) __shfl_sync(kFull, fv, 2 * i); fi = (double) __shfl_sync(kFull, fv, 2 * i + 1); }
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-      const double x = __shfl_sync(kFull, xv, 3 * i + t);
+      const double x = (double) __shfl_sync(kFull, xv, 3 * i + t);
       const int nt = t == 0 ? P.n0 : t == 1 ? P.n1 : P.n2;
       const int c = cell_int<TS>(x, nt);
       const int u = wrapi(c - P.m, nt);
@@ -333,10 +346,13 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
         const double yo = y * O[r];
         const double va = (tap && live) ? E[r] + yo : 0.0, vb = (tap && live) ? E[r] - yo : 0.0;
         if (SPREAD && t == 1) {
-          S.ops[st][1][sa][i] = va * fr;
-          S.ops[st][1][sb][i] = vb * fr;
-          S.ops[st][SPREAD ? 3 : 0][sa][i] = va * fi;
-          S.ops[st][SPREAD ? 3 : 0][sb][i] = vb * fi;
+          S.ops[st][1][sa][i] = TF32 ? pack_f32(va * fr) : va * fr;
+          S.ops[st][1][sb][i] = TF32 ? pack_f32(vb * fr) : vb * fr;
+          S.ops[st][SPREAD ? 3 : 0][sa][i] = TF32 ? pack_f32(va * fi) : va * fi;
+          S.ops[st][SPREAD ? 3 : 0][sb][i] = TF32 ? pack_f32(vb * fi) : vb * fi;
+        } else if (TF32) {
+          S.ops[st][t][sa][i] = t == 2 ? pack_tf32_pair(va) : pack_f32(va);
+          S.ops[st][t][sb][i] = t == 2 ? pack_tf32_pair(vb) : pack_f32(vb);
         } else {
           S.ops[st][t][sa][i] = va;
           S.ops[st][t][sb][i] = vb;
@@ -359,7 +375,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
   }
 }
 
-#define NFFTCU_MMA_PROLOGUE(SPREADV)                                                                  \
+#define NFFTCU_MMA_PROLOGUE(SPREADV, TF32V)                                                                \
   constexpr int T = kF + 1 - W;                                                                       \
   extern __shared__ __align__(128) unsigned char smem_raw[];                                          \
   Shared<W, SPREADV> &S = *reinterpret_cast<Shared<W, SPREADV> *>(smem_raw);                          \
@@ -387,7 +403,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
   __syncthreads();                                                                                    \
   if (tid >= 128) {                                                                                   \
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));                             \
-    producer_loop<TS, W, SPREADV>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31); \
+    producer_loop<TS, W, SPREADV, TF32V>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31); \
     return;                                                                                           \
   }                                                                                                   \
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
@@ -403,7 +419,7 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
                   const double *__restrict__ poly, MmaParams P) {
   const typename Cplx<TS>::type *const ft = nullptr;
-  NFFTCU_MMA_PROLOGUE(false)
+  NFFTCU_MMA_PROLOGUE(false, false)
 
   double A[8][2][4];   // [group][re/im][slot]: grid value of pencil (group, nr) at the cell of slot 4*s+kq
   int zwin = -1000;    // window base (even); the window holds cells [zwin, zwin+16), cell z in slot z mod 16
@@ -508,7 +524,7 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
                   const double *__restrict__ poly, MmaParams P) {
   const uint32_t *const perm = nullptr;
   TS *const f = nullptr;
-  NFFTCU_MMA_PROLOGUE(true)
+  NFFTCU_MMA_PROLOGUE(true, false)
   // staging: [buffer][warp][64 rows][kStgRow] double2 behind the Shared block
   double2 *const stg_base = reinterpret_cast<double2 *>(smem_raw + ((sizeof(Shared<W, true>) + 127) & ~(size_t) 127));
   double2 *const stg_w = stg_base + (size_t) warp * 64 * kStgRow;
@@ -662,6 +678,245 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
   }
 }
 
+// ---- fp32 plans: the same contraction on the TF32 tensor path, split 3 ways ------------------------------------
+// For nfftf_ plans the grid, the samples and the result are fp32, so the FP64 pipe is not needed for the
+// contraction itself: mma.sync.m16n8k8 TF32 with fp32 accumulation runs at 277 TFLOP/s on this part
+// (profiles/r03i_microbench_tf32.txt), 7.4x the DMMA rate.  TF32 keeps 11 significant bits, so every operand is split
+// x = hi + lo (hi = tf32(x), lo = tf32(x - hi): 22 bits) and a product is formed as lo*hi + hi*lo + hi*hi
+// (3 MMAs; the dropped lo*lo term is 2^-22 relative): 1.4e-7 rel-l2 on a 16-term window contraction against
+// fp64, i.e. fp32 accuracy.  One m16n8k8 covers exactly a 2 x 2 block of the m8n8k4 tiles of the fp64 kernels
+// (two pencil groups, two k4 steps), so the register window, the producers (window values still evaluated in
+// double and rounded once), the operand ring and the batch table are shared with them.
+__device__ __forceinline__ unsigned f2tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3,
+                                         unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int W>
+__global__ void __launch_bounds__(256, 2)
+interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
+                   const uint32_t *__restrict__ perm, float *__restrict__ f,
+                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                   const double *__restrict__ poly, MmaParams P) {
+  typedef float TS;
+  const float2 *const ft = nullptr;
+  NFFTCU_MMA_PROLOGUE(false, true)
+
+  unsigned Ah[8][2][4], Al[8][2][4];   // [group][re/im][slot]: tf32 hi / lo of the grid value, layout of interp_mma_kernel
+  int zwin = -1000;
+
+  auto fill_all = [&](int zlo) {
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      int z = zlo + ((4 * s + kq - zlo) & 15);
+      if (z >= n2) z -= n2;
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        const float2 v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
+        split_tf32(v.x, Ah[g][0][s], Al[g][0][s]);
+        split_tf32(v.y, Ah[g][1][s], Al[g][1][s]);
+      }
+    }
+  };
+  // refill loads are parked as raw float2 and split into (hi, lo) only when the next batch starts: a conversion
+  // right behind the load would make the warp wait out the L2 latency at once instead of during the reduction
+  float2 pend[8];
+  int pend_slot = -1;
+  auto commit = [&]() {
+    if (pend_slot < 0) return;
+    switch (pend_slot) {
+#define NFFTCU_COMMIT(SL)                                                                       \
+      case SL:                                                                                  \
+        _Pragma("unroll") for (int g = 0; g < 8; g++) {                                         \
+          split_tf32(pend[g].x, Ah[g][0][SL], Al[g][0][SL]);                                    \
+          split_tf32(pend[g].y, Ah[g][1][SL], Al[g][1][SL]);                                    \
+        }                                                                                       \
+        break;
+      NFFTCU_COMMIT(0) NFFTCU_COMMIT(1) NFFTCU_COMMIT(2) NFFTCU_COMMIT(3)
+#undef NFFTCU_COMMIT
+    }
+    pend_slot = -1;
+  };
+  auto load_pair = [&](int zp) {
+    if ((kq >> 1) == ((zp >> 1) & 1)) {
+      commit();   // a second pair for this lane before the first was used (window moved by more than 4 cells)
+      int z = zp + (kq & 1);
+      if (z >= n2) z -= n2;
+#pragma unroll
+      for (int g = 0; g < 8; g++) pend[g] = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
+      pend_slot = (zp >> 2) & 3;
+    }
+  };
+  auto advance_to = [&](int zlo) {
+    if (zlo - zwin >= kF || zwin < 0) {
+      pend_slot = -1;   // the whole window is replaced
+      fill_all(zlo);
+      zwin = zlo;
+    } else {
+      while (zwin < zlo) { load_pair(zwin + kF); zwin += 2; }
+    }
+  };
+
+  uint2 e_next = table[0];
+  for (int j = 0; j < nbat; j++) {
+    const int st = j % kStages;
+    const int zlo = bt_zlo(e_next);
+    if (j + 1 < nbat) e_next = table[j + 1];
+    if (zlo != zwin) advance_to(zlo);
+    mbar_wait(&S.full[st], (j / kStages) & 1);
+    commit();
+
+    unsigned bh[4], bl[4];   // psi2 at slot 4s+kq of node nr: (hi, lo) packed by the producer
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const uint2 v = *reinterpret_cast<const uint2 *>(&S.ops[st][2][4 * s + kq][nr]);
+      bh[s] = v.x;
+      bl[s] = v.y;
+    }
+    const uint4 q1a = *reinterpret_cast<const uint4 *>(&S.ops[st][1][nr][2 * kq]);        // floats of nodes 2kq, 2kq+1 in .x, .z
+    const uint4 q1b = *reinterpret_cast<const uint4 *>(&S.ops[st][1][8 + nr][2 * kq]);
+    const float p1ax = __uint_as_float(q1a.x), p1ay = __uint_as_float(q1a.z);
+    const float p1bx = __uint_as_float(q1b.x), p1by = __uint_as_float(q1b.z);
+    float accr0 = 0.f, accr1 = 0.f, acci0 = 0.f, acci1 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; h++) {   // footprint row l0 = 4*warp + h: groups 2h (rows 0-7 of the m16 tile) and 2h+1
+      float c[2][4];                // [re/im][group 2h: col0, col1; group 2h+1: col0, col1]
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) c[cc][0] = c[cc][1] = c[cc][2] = c[cc][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          mma_tf32(c[cc], Al[2 * h][cc][2 * kk], Al[2 * h + 1][cc][2 * kk], Al[2 * h][cc][2 * kk + 1], Al[2 * h + 1][cc][2 * kk + 1],
+                   bh[2 * kk], bh[2 * kk + 1]);
+          mma_tf32(c[cc], Ah[2 * h][cc][2 * kk], Ah[2 * h + 1][cc][2 * kk], Ah[2 * h][cc][2 * kk + 1], Ah[2 * h + 1][cc][2 * kk + 1],
+                   bl[2 * kk], bl[2 * kk + 1]);
+          mma_tf32(c[cc], Ah[2 * h][cc][2 * kk], Ah[2 * h + 1][cc][2 * kk], Ah[2 * h][cc][2 * kk + 1], Ah[2 * h + 1][cc][2 * kk + 1],
+                   bh[2 * kk], bh[2 * kk + 1]);
+        }
+      const uint4 q0 = *reinterpret_cast<const uint4 *>(&S.ops[st][0][4 * warp + h][2 * kq]);
+      const float p0x = __uint_as_float(q0.x), p0y = __uint_as_float(q0.z);
+      const float wa0 = p0x * p1ax, wa1 = p0y * p1ay, wb0 = p0x * p1bx, wb1 = p0y * p1by;
+      accr0 = fmaf(wa0, c[0][0], accr0); accr1 = fmaf(wa1, c[0][1], accr1);
+      acci0 = fmaf(wa0, c[1][0], acci0); acci1 = fmaf(wa1, c[1][1], acci1);
+      accr0 = fmaf(wb0, c[0][2], accr0); accr1 = fmaf(wb1, c[0][3], accr1);
+      acci0 = fmaf(wb0, c[1][2], acci0); acci1 = fmaf(wb1, c[1][3], acci1);
+    }
+    if (j + 1 < nbat && bt_zlo(e_next) != zwin) advance_to(bt_zlo(e_next));
+    *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][0]) = make_double2((double) accr0, (double) acci0);
+    *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][2]) = make_double2((double) accr1, (double) acci1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[st]);
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256, 2)
+spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const float2 *__restrict__ ft,
+                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                   const double *__restrict__ poly, MmaParams P) {
+  typedef float TS;
+  const uint32_t *const perm = nullptr;
+  float *const f = nullptr;
+  NFFTCU_MMA_PROLOGUE(true, true)
+
+  float C[4][2][2][4];   // [row pair h][re/im][n-tile][group 2h: col0, col1; group 2h+1: col0, col1], slot 8*nt + 2*kq + col
+#pragma unroll
+  for (int h = 0; h < 4; h++)
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) C[h][cc][nt][0] = C[h][cc][nt][1] = C[h][cc][nt][2] = C[h][cc][nt][3] = 0.f;
+
+  // retire pair (zp, zp+1) of the window (zp even, unwrapped): n-tile (zp>>3)&1, lanes kq == (zp&7)>>1
+  auto retire_pair = [&](int zp) {
+    int zw = zp;
+    if (zw >= n2) zw -= n2;
+    if (kq == ((zp & 7) >> 1)) {
+#define NFFTCU_RETIRE(NT)                                                                                   \
+      _Pragma("unroll") for (int g = 0; g < 8; g++) {                                                       \
+        float2 *dst = G + rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw;                                       \
+        const int o = 2 * (g & 1);                                                                          \
+        atomicAdd(dst, make_float2(C[g >> 1][0][NT][o], C[g >> 1][1][NT][o]));                              \
+        atomicAdd(dst + 1, make_float2(C[g >> 1][0][NT][o + 1], C[g >> 1][1][NT][o + 1]));                  \
+        C[g >> 1][0][NT][o] = C[g >> 1][1][NT][o] = C[g >> 1][0][NT][o + 1] = C[g >> 1][1][NT][o + 1] = 0.f; \
+      }
+      if (((zp >> 3) & 1) == 0) { NFFTCU_RETIRE(0) } else { NFFTCU_RETIRE(1) }
+#undef NFFTCU_RETIRE
+    }
+  };
+
+  int zwin = -1;
+  uint2 e_next = table[0];
+  for (int j = 0; j < nbat; j++) {
+    const int st = j % kStages;
+    const int zlo = bt_zlo(e_next);
+    if (j + 1 < nbat) e_next = table[j + 1];
+    if (zwin < 0) zwin = zlo;
+    if (zlo != zwin) {
+      const int zend = (zlo - zwin >= kF) ? zwin + kF : zlo;
+      for (int zp = zwin; zp < zend; zp += 2) retire_pair(zp);
+      zwin = zlo;
+    }
+    mbar_wait(&S.full[st], (j / kStages) & 1);
+    unsigned bh[2][2], bl[2][2];   // [n-tile][k half]: psi2 of node 4*ks+kq at slot 8*nt+nr
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(&S.ops[st][2][8 * nt + nr][4 * ks + kq]);
+        bh[nt][ks] = v.x;
+        bl[nt][ks] = v.y;
+      }
+    float p1r[2][2], p1i[2][2];    // [half][k half]
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        p1r[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][1][8 * hh + nr][4 * ks + kq])->x);
+        p1i[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][3][8 * hh + nr][4 * ks + kq])->x);
+      }
+    float p0[4][2];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      p0[h][0] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][0][4 * warp + h][kq])->x);
+      p0[h][1] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][0][4 * warp + h][4 + kq])->x);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[st]);   // operands are in registers: the stage can be refilled
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        // A fragment: a0 (group 2h, node kq), a1 (group 2h+1, node kq), a2 (group 2h, node 4+kq), a3 (group 2h+1, node 4+kq)
+        unsigned ah[4], al[4];
+        split_tf32(p0[h][0] * (cc ? p1i[0][0] : p1r[0][0]), ah[0], al[0]);
+        split_tf32(p0[h][0] * (cc ? p1i[1][0] : p1r[1][0]), ah[1], al[1]);
+        split_tf32(p0[h][1] * (cc ? p1i[0][1] : p1r[0][1]), ah[2], al[2]);
+        split_tf32(p0[h][1] * (cc ? p1i[1][1] : p1r[1][1]), ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          mma_tf32(C[h][cc][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+          mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+          mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+        }
+      }
+    }
+  }
+  for (int zp = zwin; zp < zwin + kF; zp += 2) retire_pair(zp);
+}
+
 MmaParams make_params(const nfftcu_ctx *c) {
   MmaParams P;
   P.n0 = (int) c->n[0];
@@ -695,6 +950,30 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   const TS *xt = (const TS *) c->tile_x;
   const double *poly = (const double *) c->kbpoly_dev;
   const uint2 *table = (const uint2 *) c->mma_batches;
+  if (sizeof(TS) == 4 && c->opt_b_kernel != 3) {   // fp32 plans: TF32 tensor path (NFFTCU_OPT_B_KERNEL = 3 forces DMMA)
+    if (!spread) {
+      const size_t smem = sizeof(Shared<W, false>);
+      NFFTCU_CUDA(cudaFuncSetAttribute(interp_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
+      interp_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((const float2 *) c->grid, (const float *) c->tile_x, c->tile_perm,
+                                                            (float *) f_out, c->mma_batch_start, table, poly, P);
+      if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
+      c->launches++;
+    } else {
+      const int kb = 256;
+      mma_gather_f_kernel<float2><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
+          (const float2 *) f_in, c->tile_perm, (float2 *) c->f_tile, c->M);
+      const size_t smem = sizeof(Shared<W, true>);
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
+      spread_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((float2 *) c->grid, (const float *) c->tile_x,
+                                                            (const float2 *) c->f_tile, c->mma_batch_start, table, poly, P);
+      if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
+      c->launches += 2;
+    }
+    NFFTCU_CUDA(cudaGetLastError());
+    return NFFTCU_OK;
+  }
   if (!spread) {
     const size_t smem = sizeof(Shared<W, false>);
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<TS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
