@@ -45,6 +45,8 @@ def peaks():
 # (profiles/r01w_microbench_dmma.txt: 36.9 TFLOP/s = 64 FMA/clk/SM at 1.965 GHz, same pipe as DFMA).
 # MEASURED_PEAKS.json carries only HBM GB/s and bf16 TF/s; a key "fp64_tflops" there would override this.
 FP64_TENSOR_TFLOPS = 36.9
+# legacy tensor path used by the fp32 plans (tools/microbench5.cu, profiles/r03i_microbench_tf32.txt)
+TF32_MMA_SYNC_TFLOPS = 276.7
 
 
 def fp64_peak():
@@ -355,7 +357,8 @@ def run_ours(args, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("%s:%d" % (prec, cfg["M"]), {}).get("spread" if spread_dom else "interp")
-        dmma = args.b_kernel in (0, 3) and cfg["m"] <= 6   # fp32 plans run on the FP64 DMMA kernels too (fp32 storage)
+        dmma = args.b_kernel in (0, 3) and cfg["m"] <= 6 and (prec == "double" or args.b_kernel == 3)
+        tf32 = prec == "float" and args.b_kernel == 0 and cfg["m"] <= 6   # fp32 plans: 3xTF32 mma.sync kernels
         taps = (2 * cfg["m"] + 2) ** cfg["d"]
         flops = 4.0 * taps * cfg["M"]      # per tap: complex value x real weight = 2 FMA = 4 flops
         if dmma:
@@ -367,6 +370,18 @@ def run_ours(args, rank, world, local_rank):
                     "launch_ms": t_dom, "peak_source": pk_src,
                     "note": "FP64 tensor cores (DMMA m8n8k4): useful flops only, zero padding of the 16^3 window "
                             "(67 % lane efficiency) not counted",
+                    "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak,
+                            "peak_source": peak_src}}
+        elif tf32:
+            tf = flops / (t_dom * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": ("spread_tf32_kernel (B^T)" if spread_dom else "interp_tf32_kernel (B)"),
+                    "achieved": 3 * tf, "peak": TF32_MMA_SYNC_TFLOPS, "unit": "TFLOP/s", "frac": 3 * tf / TF32_MMA_SYNC_TFLOPS,
+                    "traffic": traffic, "algorithmic_flops_per_launch": 3 * flops, "algorithmic_bytes_per_launch": a_dom,
+                    "launch_ms": t_dom,
+                    "peak_source": "legacy mma.sync m16n8k8 TF32 rate measured with tools/microbench5.cu on this pool's "
+                                   "B200 (profiles/r03i_microbench_tf32.txt); the register-resident window rules out tcgen05",
+                    "note": "3xTF32 split: three tensor flops per useful flop are counted (useful: %.2f TFLOP/s); zero "
+                            "padding of the 16^3 window not counted; the kernels are issue-bound, see DESIGN.md 4.1c" % tf,
                     "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak,
                             "peak_source": peak_src}}
         else:
