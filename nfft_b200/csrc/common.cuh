@@ -93,6 +93,9 @@ struct nfftcu_ctx_s {
   uint32_t *mma_batch_start = nullptr;   // units+1 offsets into mma_batches
   uint32_t *mma_counts = nullptr;   // scratch: batches per unit
   long long mma_units = 0, mma_batch_cap = 0;
+  uint32_t *mma_chunk_start = nullptr;   // units+1 offsets into mma_chunks
+  void *mma_chunks = nullptr;       // uint4 per CTA: tile, first batch, end batch (runs of <= 384 batches of one unit)
+  long long mma_nchunks = 0, mma_chunk_cap = 0;
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

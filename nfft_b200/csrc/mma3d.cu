@@ -188,6 +188,35 @@ __global__ void mma_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *_
   if (t == 1023) out[n] = part[1023];
 }
 
+// ---- work chunks (plan time) --------------------------------------------------------------------------------
+// A CTA sweeps one chunk = a run of at most kChunkBatches consecutive batches of one work unit (tile, z segment).
+// With evenly spread nodes a unit is one chunk; clustered node sets (radial / spiral trajectories: thousands of
+// batches in the tiles around the centre) are cut into many, so that the load of a CTA is bounded.  A chunk is
+// self-contained: interpolation loads the window of its first batch itself, spreading retires the whole window
+// with reductions at its end.
+constexpr int kChunkBatches = 384;
+
+__global__ void mma_chunk_count_kernel(const uint32_t *__restrict__ batch_start, uint32_t *__restrict__ counts, long long units) {
+  const long long u = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= units) return;
+  const uint32_t nb = batch_start[u + 1] - batch_start[u];
+  counts[u] = (nb + kChunkBatches - 1) / kChunkBatches;
+}
+
+__global__ void mma_chunk_fill_kernel(const uint32_t *__restrict__ batch_start, const uint32_t *__restrict__ chunk_start,
+                                      uint4 *__restrict__ chunks, long long units, int zseg) {
+  const long long u = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= units) return;
+  const uint32_t b0 = batch_start[u], nb = batch_start[u + 1] - b0;
+  const uint32_t cnt = chunk_start[u + 1] - chunk_start[u];
+  if (cnt == 0) return;
+  const uint32_t size = (nb + cnt - 1) / cnt;   // equal shares
+  for (uint32_t k = 0; k < cnt; k++) {
+    const uint32_t lo = b0 + k * size, hi = (k + 1 == cnt) ? b0 + nb : lo + size;
+    chunks[chunk_start[u] + k] = make_uint4((uint32_t) (u / zseg), lo, hi, 0u);
+  }
+}
+
 // ---- mbarrier helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -381,12 +410,12 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
   Shared<W, SPREADV> &S = *reinterpret_cast<Shared<W, SPREADV> *>(smem_raw);                          \
   const int tid = threadIdx.x;                                                                        \
   const int n2 = P.n2;                                                                                \
-  const long long unit = blockIdx.x;                                                                  \
-  const uint32_t b0 = batch_start[unit];                                                              \
-  const int nbat = (int) (batch_start[unit + 1] - b0);                                                \
+  const uint4 chunk = chunks[blockIdx.x];   /* tile, first batch, end batch */                        \
+  const uint32_t b0 = chunk.y;                                                                        \
+  const int nbat = (int) (chunk.z - b0);                                                              \
   if (nbat == 0) return;                                                                              \
   table += b0;                                                                                        \
-  const int tile = (int) (unit / P.zseg);                                                             \
+  const int tile = (int) chunk.x;                                                                     \
   const int a = tile / P.NT1, bt = tile - a * P.NT1;                                                  \
   for (int i = tid; i < 3 * W * kCoefK; i += 256) {                                                   \
     const int t = i / (W * kCoefK), l = (i / kCoefK) % W, k = i % kCoefK;                             \
@@ -416,7 +445,7 @@ template <typename TS, int W>
 __global__ void __launch_bounds__(256, 2)
 interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                   const uint32_t *__restrict__ perm, TS *__restrict__ f,
-                  const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                  const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
                   const double *__restrict__ poly, MmaParams P) {
   const typename Cplx<TS>::type *const ft = nullptr;
   NFFTCU_MMA_PROLOGUE(false, false)
@@ -520,7 +549,7 @@ template <typename TS, int W, int FLUSH>
 __global__ void __launch_bounds__(256, 2)
 spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                   const typename Cplx<TS>::type *__restrict__ ft,
-                  const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                  const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
                   const double *__restrict__ poly, MmaParams P) {
   const uint32_t *const perm = nullptr;
   TS *const f = nullptr;
@@ -707,7 +736,7 @@ template <int W>
 __global__ void __launch_bounds__(256, 2)
 interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
                    const uint32_t *__restrict__ perm, float *__restrict__ f,
-                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                   const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
                    const double *__restrict__ poly, MmaParams P) {
   typedef float TS;
   const float2 *const ft = nullptr;
@@ -824,7 +853,7 @@ interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
 template <int W>
 __global__ void __launch_bounds__(256, 2)
 spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const float2 *__restrict__ ft,
-                   const uint32_t *__restrict__ batch_start, const uint2 *__restrict__ table,
+                   const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
                    const double *__restrict__ poly, MmaParams P) {
   typedef float TS;
   const uint32_t *const perm = nullptr;
@@ -946,7 +975,9 @@ size_t spread_smem() {
 template <typename TS, int W>
 int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
   typedef typename Cplx<TS>::type C2;
-  const unsigned grid = (unsigned) ((long long) P.NT0 * P.NT1 * P.zseg);
+  const unsigned grid = (unsigned) c->mma_nchunks;
+  if (grid == 0) return NFFTCU_OK;
+  const uint4 *chunks = (const uint4 *) c->mma_chunks;
   const TS *xt = (const TS *) c->tile_x;
   const double *poly = (const double *) c->kbpoly_dev;
   const uint2 *table = (const uint2 *) c->mma_batches;
@@ -956,7 +987,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
       NFFTCU_CUDA(cudaFuncSetAttribute(interp_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
       interp_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((const float2 *) c->grid, (const float *) c->tile_x, c->tile_perm,
-                                                            (float *) f_out, c->mma_batch_start, table, poly, P);
+                                                            (float *) f_out, chunks, table, poly, P);
       if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
       c->launches++;
     } else {
@@ -967,7 +998,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
       spread_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((float2 *) c->grid, (const float *) c->tile_x,
-                                                            (const float2 *) c->f_tile, c->mma_batch_start, table, poly, P);
+                                                            (const float2 *) c->f_tile, chunks, table, poly, P);
       if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
       c->launches += 2;
     }
@@ -979,7 +1010,7 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<TS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     interp_mma_kernel<TS, W><<<grid, 256, smem, c->stream>>>((const C2 *) c->grid, xt, c->tile_perm, (TS *) f_out,
-                                                             c->mma_batch_start, table, poly, P);
+                                                             chunks, table, poly, P);
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches++;
   } else {
@@ -992,12 +1023,12 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
       const size_t smem = spread_smem<W, 1>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<double, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       spread_mma_kernel<double, W, 1><<<grid, 256, smem, c->stream>>>(
-          (double2 *) c->grid, (const double *) c->tile_x, (const double2 *) c->f_tile, c->mma_batch_start, table, poly, P);
+          (double2 *) c->grid, (const double *) c->tile_x, (const double2 *) c->f_tile, chunks, table, poly, P);
     } else {
       const size_t smem = spread_smem<W, 0>();
       NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<TS, W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       spread_mma_kernel<TS, W, 0><<<grid, 256, smem, c->stream>>>((C2 *) c->grid, xt, (const C2 *) c->f_tile,
-                                                                  c->mma_batch_start, table, poly, P);
+                                                                  chunks, table, poly, P);
     }
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches += 2;
@@ -1072,7 +1103,8 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   if (c->mma_units != units) {
     if (c->mma_batch_start) cudaFree(c->mma_batch_start);
     if (c->mma_counts) cudaFree(c->mma_counts);
-    c->mma_batch_start = c->mma_counts = nullptr;
+    if (c->mma_chunk_start) cudaFree(c->mma_chunk_start);
+    c->mma_batch_start = c->mma_counts = c->mma_chunk_start = nullptr;
     NFFTCU_CUDA(cudaMalloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
     NFFTCU_CUDA(cudaMalloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
     c->mma_units = units;
@@ -1092,7 +1124,24 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   }
   mma_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
                                                         c->mma_batch_start, (uint2 *) c->mma_batches, units, P);
-  c->launches += 3;
+  // chunks: count per unit (reusing the counts scratch), scan, fill
+  if (!c->mma_chunk_start) NFFTCU_CUDA(cudaMalloc((void **) &c->mma_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
+  const unsigned ugrid = (unsigned) ((units + kb - 1) / kb);
+  mma_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_counts, units);
+  mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_chunk_start, units);
+  uint32_t nchunks = 0;
+  NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, c->mma_chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  if ((long long) nchunks > c->mma_chunk_cap) {
+    if (c->mma_chunks) cudaFree(c->mma_chunks);
+    c->mma_chunks = nullptr;
+    c->mma_chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
+    NFFTCU_CUDA(cudaMalloc(&c->mma_chunks, sizeof(uint4) * (size_t) c->mma_chunk_cap));
+  }
+  mma_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_chunk_start, (uint4 *) c->mma_chunks, units,
+                                                    P.zseg);
+  c->mma_nchunks = nchunks;
+  c->launches += 6;
   NFFTCU_CUDA(cudaGetLastError());
   c->mma_ready = true;
   return NFFTCU_OK;

@@ -497,6 +497,33 @@ def test_register_fft_vs_shared_memory_fft(N, n, m, M, prune, precision):
         assert rel_l2(outs[0][1], o.adjoint(N, n, m, x, f)) <= TOL[precision]
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_tile3d_clustered_nodes_are_cut_into_chunks(precision):
+    """2*10^5 nodes in a ball of radius 0.04 on a 64^3 grid: a handful of tiles hold thousands of batches each, so
+    their work units are cut into many chunks (mma_chunk_fill_kernel); every chunk preloads / retires its own window."""
+    rng = np.random.default_rng(33)
+    o = oracle(precision)
+    N, n, m, M = [32, 32, 32], [64, 64, 64], 6, 200_000
+    v = rng.normal(size=(M, 3))
+    x = (v / np.linalg.norm(v, axis=1, keepdims=True) * (0.04 * rng.random((M, 1)) ** (1 / 3)) + 0.21).astype(o.real)
+    fh = (rng.random(32 ** 3) - 0.5 + 1j * (rng.random(32 ** 3) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    eng = cabi.Engine(N, n, m, M, precision=precision)
+    eng.set_nodes(x)
+    got_f, got_fh = eng.trafo(fh), eng.adjoint(f)
+    eng.close()
+    assert rel_l2(got_f, o.trafo(N, n, m, x, fh)) <= TOL[precision]
+    if precision == "double":
+        assert rel_l2(got_fh, o.adjoint(N, n, m, x, f)) <= TOL[precision]
+    else:
+        # every grid cell of the cluster sums ~10^5 fp32 contributions: two fp32 summation orders (the reference's
+        # and ours) differ by ~sqrt(10^5) eps = 2e-5 here, so the fp32 result is held against the fp64 oracle instead
+        od = oracle("double")
+        want = od.adjoint(N, n, m, x.astype(np.float64), f.astype(np.complex128))
+        assert rel_l2(got_fh, want) <= 5e-5
+        assert rel_l2(got_fh, want) <= 2 * rel_l2(o.adjoint(N, n, m, x, f), want) + 1e-5   # no worse than the fp32 reference
+
+
 def test_tile3d_z_segments_small_grid_many_nodes():
     """few tiles -> the sweep is split into z segments; every segment flushes / preloads its window."""
     rng = np.random.default_rng(32)

@@ -155,6 +155,17 @@ def main():
         x = rng.random((M, 3)) - 0.5
         print(json.dumps(dict(config="cfg4 on ONE GPU: 3-D N=256^3 n=512^3 M=%d m=6 fp64" % M,
                               **pair_times([256] * 3, [512] * 3, 6, x, steps=3, warmup=1))), flush=True)
+    if "cfg3r" in want:
+        # 3-D radial trajectory (applications/mri/mri3d style): M = 10^7 nodes on lines through the origin, density ~ 1/r^2
+        M = 10_000_000
+        lines = 40_000
+        v = rng.normal(size=(lines, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        r = (np.arange(M // lines) / (M // lines) - 0.5)
+        x = np.ascontiguousarray((v[:, None, :] * r[None, :, None]).reshape(-1, 3))
+        x = np.clip(x, -0.5, np.nextafter(0.5, 0.0))
+        print(json.dumps(dict(config="cfg3 grid with a 3-D RADIAL trajectory (clustered at the centre): N=128^3 n=256^3 M=%d m=6 fp64" % M,
+                              **pair_times([128] * 3, [256] * 3, 6, x, steps=5, warmup=2))), flush=True)
     if "cfg5" in want:
         print(json.dumps(dict(config="cfg5: 2-D CGNR 20 iterations x %d coils, 512^2 spiral, reference solver.c on the engine"
                                      % args.coils, **cfg5(args.coils, args.cpu_coils))), flush=True)
