@@ -276,9 +276,8 @@ struct Shared {
 // that the conversions happen once per value here and not once per MMA warp: psi2 as the (hi, lo) tf32 pair of the
 // 3xTF32 split, every other operand as one float in the low word.
 __device__ __forceinline__ double pack_tf32_pair(double v) {
-  unsigned hi, lo;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"((float) v));
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"((float) (v - (double) __uint_as_float(hi))));
+  const unsigned hi = (__float_as_uint((float) v) + 0x1000u) & 0xffffe000u;   // see split_tf32
+  const unsigned lo = __float_as_uint((float) (v - (double) __uint_as_float(hi)));
   return __hiloint2double((int) lo, (int) hi);   // low word = hi part, high word = lo part
 }
 __device__ __forceinline__ double pack_f32(double v) { return __hiloint2double(0, __float_as_int((float) v)); }
@@ -346,7 +345,11 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
       const double y2 = y * y;
       double E[2], O[2];
       int off[2];
+#ifdef NFFTCU_DBG_DEG2
+      const int ptop = 1;   // timing experiment only: wrong window
+#else
       const int ptop = P.deg >> 1;
+#endif
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         const int l = 2 * qg + r;
@@ -716,14 +719,12 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
 // fp64, i.e. fp32 accuracy.  One m16n8k8 covers exactly a 2 x 2 block of the m8n8k4 tiles of the fp64 kernels
 // (two pencil groups, two k4 steps), so the register window, the producers (window values still evaluated in
 // double and rounded once), the operand ring and the batch table are shared with them.
-__device__ __forceinline__ unsigned f2tf32(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// hi = x rounded to TF32 (nearest, on the 13 dropped mantissa bits, as two integer instructions instead of the
+// multi-instruction cvt.rna.tf32 sequence); lo = x - hi is exact in fp32 and is handed to the tensor core as it is:
+// an fp32 bit pattern is a valid TF32 operand whose low 13 mantissa bits the tensor core does not read.
 __device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
-  hi = f2tf32(x);
-  lo = f2tf32(x - __uint_as_float(hi));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3,
                                          unsigned b0, unsigned b1) {
@@ -805,6 +806,14 @@ interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
     if (zlo != zwin) advance_to(zlo);
     mbar_wait(&S.full[st], (j / kStages) & 1);
     commit();
+    // the refill for the NEXT batch goes out before this batch's MMAs (it lands in pend, not in the window): a slide
+    // by 2 or 4 cells gives every lane at most one pair; larger slides are done behind the MMAs as before
+    if (j + 1 < nbat) {
+      const int dz = bt_zlo(e_next) - zwin;
+      if (dz == 2 || dz == 4) {
+        while (zwin < bt_zlo(e_next)) { load_pair(zwin + kF); zwin += 2; }
+      }
+    }
 
     unsigned bh[4], bl[4];   // psi2 at slot 4s+kq of node nr: (hi, lo) packed by the producer
 #pragma unroll
@@ -827,10 +836,12 @@ interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
       for (int kk = 0; kk < 2; kk++)
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
+#ifndef NFFTCU_DBG_1MMA
           mma_tf32(c[cc], Al[2 * h][cc][2 * kk], Al[2 * h + 1][cc][2 * kk], Al[2 * h][cc][2 * kk + 1], Al[2 * h + 1][cc][2 * kk + 1],
                    bh[2 * kk], bh[2 * kk + 1]);
           mma_tf32(c[cc], Ah[2 * h][cc][2 * kk], Ah[2 * h + 1][cc][2 * kk], Ah[2 * h][cc][2 * kk + 1], Ah[2 * h + 1][cc][2 * kk + 1],
                    bl[2 * kk], bl[2 * kk + 1]);
+#endif
           mma_tf32(c[cc], Ah[2 * h][cc][2 * kk], Ah[2 * h + 1][cc][2 * kk], Ah[2 * h][cc][2 * kk + 1], Ah[2 * h + 1][cc][2 * kk + 1],
                    bh[2 * kk], bh[2 * kk + 1]);
         }
@@ -868,6 +879,8 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
 #pragma unroll
       for (int nt = 0; nt < 2; nt++) C[h][cc][nt][0] = C[h][cc][nt][1] = C[h][cc][nt][2] = C[h][cc][nt][3] = 0.f;
 
+  // one 16-byte reduction per pair (atomicAdd(float4*)) measured slower than two 8-byte ones on B200 (BT 5.70 vs 5.43 ms)
+  const bool vec4 = false;
   // retire pair (zp, zp+1) of the window (zp even, unwrapped): n-tile (zp>>3)&1, lanes kq == (zp&7)>>1
   auto retire_pair = [&](int zp) {
     int zw = zp;
@@ -877,8 +890,13 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
       _Pragma("unroll") for (int g = 0; g < 8; g++) {                                                       \
         float2 *dst = G + rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw;                                       \
         const int o = 2 * (g & 1);                                                                          \
-        atomicAdd(dst, make_float2(C[g >> 1][0][NT][o], C[g >> 1][1][NT][o]));                              \
-        atomicAdd(dst + 1, make_float2(C[g >> 1][0][NT][o + 1], C[g >> 1][1][NT][o + 1]));                  \
+        if (vec4) {   /* both cells of the pair in one 16-byte reduction */                                 \
+          atomicAdd(reinterpret_cast<float4 *>(dst), make_float4(C[g >> 1][0][NT][o], C[g >> 1][1][NT][o],  \
+                                                                 C[g >> 1][0][NT][o + 1], C[g >> 1][1][NT][o + 1])); \
+        } else {                                                                                            \
+          atomicAdd(dst, make_float2(C[g >> 1][0][NT][o], C[g >> 1][1][NT][o]));                            \
+          atomicAdd(dst + 1, make_float2(C[g >> 1][0][NT][o + 1], C[g >> 1][1][NT][o + 1]));                \
+        }                                                                                                   \
         C[g >> 1][0][NT][o] = C[g >> 1][1][NT][o] = C[g >> 1][0][NT][o + 1] = C[g >> 1][1][NT][o + 1] = 0.f; \
       }
       if (((zp >> 3) & 1) == 0) { NFFTCU_RETIRE(0) } else { NFFTCU_RETIRE(1) }
