@@ -54,8 +54,8 @@ int bind_device(const nfftcu_ctx *c) {
 size_t cbytes(const nfftcu_ctx *c, long long count) { return 2 * real_size(c) * (size_t) count; }
 
 int ensure_staging(nfftcu_ctx *c) {
-  if (!c->fhat_dev && c->N_total > 0) NFFTCU_CUDA(cudaMalloc(&c->fhat_dev, cbytes(c, c->N_total)));
-  if (!c->f_dev && c->M > 0) NFFTCU_CUDA(cudaMalloc(&c->f_dev, cbytes(c, c->M)));
+  if (!c->fhat_dev && c->N_total > 0) NFFTCU_CUDA(pool_malloc(&c->fhat_dev, cbytes(c, c->N_total)));
+  if (!c->f_dev && c->M > 0) NFFTCU_CUDA(pool_malloc(&c->f_dev, cbytes(c, c->M)));
   return NFFTCU_OK;
 }
 
@@ -121,17 +121,20 @@ int nodes_ready(nfftcu_ctx *c) {
   c->ref_sorted = false;
   c->tile_ready = false;
   c->mma_ready = false;
+  c->tile2_ready = false;
   if (!c->direct_only) {
     // B / B^T kernel family: DMMA (mma3d.cu) > register pencils (pencil3d.cu) > generic warp-per-node
     const bool use_mma = mma3d_supported(c) && (c->opt_b_kernel == 0 || c->opt_b_kernel == 3);
     const bool use_tile = !use_mma && tile3d_supported(c) && c->opt_b_kernel != 1;
+    const bool use_tile2 = tile2d_supported(c) && c->opt_b_kernel != 1;   // d = 2: shared-memory tiles (tile2d.cu)
     // the reference-order sort is the index_x witness and the order the generic kernels walk
-    if (!(use_tile || use_mma) || (c->flags & (1u << 11))) {   // NFFT_SORT_NODES
+    if (!(use_tile || use_mma || use_tile2) || (c->flags & (1u << 11))) {   // NFFT_SORT_NODES
       NFFTCU_TRY(sort_nodes(c));
       c->ref_sorted = true;
     }
     if (use_mma) NFFTCU_TRY(mma3d_bin_nodes(c));
     else if (use_tile) NFFTCU_TRY(tile3d_bin_nodes(c));
+    else if (use_tile2) NFFTCU_TRY(tile2d_bin_nodes(c));
     else if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
   }
   c->have_nodes = true;
@@ -153,9 +156,9 @@ int stage_and_compare(nfftcu_ctx *c, const void *x, cudaMemcpyKind kind, bool *c
   const size_t bytes = real_size(c) * (size_t) c->M * c->d;
   *changed = true;
   if (bytes == 0) { *changed = !c->have_nodes; return NFFTCU_OK; }
-  if (!c->x_stage) NFFTCU_CUDA(cudaMalloc(&c->x_stage, bytes));
-  if (!c->x_dev) NFFTCU_CUDA(cudaMalloc(&c->x_dev, bytes));
-  if (!c->diff_flag) NFFTCU_CUDA(cudaMalloc((void **) &c->diff_flag, sizeof(int)));
+  if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, bytes));
+  if (!c->x_dev) NFFTCU_CUDA(pool_malloc(&c->x_dev, bytes));
+  if (!c->diff_flag) NFFTCU_CUDA(pool_malloc((void **) &c->diff_flag, sizeof(int)));
   NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x, bytes, kind, c->stream));
   if (c->have_nodes) {
     int h = 0;
@@ -263,7 +266,7 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
       c->c_host[t][(size_t) ks] = (double) (1.0L / bessel_i0_series(arg));
     }
     const size_t bytes = real_size(c) * (size_t) N[t];
-    NFFTCU_CUDA(cudaMalloc(&c->c_dev[t], bytes));
+    NFFTCU_CUDA(pool_malloc(&c->c_dev[t], bytes));
     if (precision == NFFTCU_DOUBLE) {
       NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], c->c_host[t].data(), bytes, cudaMemcpyHostToDevice));
     } else {
@@ -273,9 +276,9 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
     }
   }
   if (!c->direct_only) {
-    NFFTCU_CUDA(cudaMalloc(&c->grid, cbytes(c, c->n_total)));
+    NFFTCU_CUDA(pool_malloc(&c->grid, cbytes(c, c->n_total)));
     int r = fft_plan_axes(c);
-    if (r == NFFTCU_OK && tile3d_supported(c)) r = build_kb_poly(c);
+    if (r == NFFTCU_OK && (tile3d_supported(c) || tile2d_supported(c))) r = build_kb_poly(c);
     if (r != NFFTCU_OK) {
       nfftcu_destroy(c);
       return r;
@@ -291,18 +294,18 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
-    if (c->c_dev[t]) cudaFree(c->c_dev[t]);
+    if (c->c_dev[t]) pool_free(c->c_dev[t]);
   void *bufs[] = {c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
   for (int i = 0; i < 4; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; i++)
     if (c->evk[i]) cudaEventDestroy(c->evk[i]);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->ev_side) cudaEventDestroy(c->ev_side);
-  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->h_flag) pool_free_host(c->h_flag);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return NFFTCU_OK;
@@ -433,9 +436,9 @@ static int host_transform_refresh(nfftcu_ctx *c, const void *x_host, const void 
   }
   NFFTCU_TRY(ensure_staging(c));
   if (!c->side_stream) NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-  if (!c->h_flag) NFFTCU_CUDA(cudaMallocHost((void **) &c->h_flag, sizeof(int)));
-  if (!c->x_stage) NFFTCU_CUDA(cudaMalloc(&c->x_stage, xbytes));
-  if (!c->diff_flag) NFFTCU_CUDA(cudaMalloc((void **) &c->diff_flag, sizeof(int)));
+  if (!c->h_flag) NFFTCU_CUDA(pool_malloc_host((void **) &c->h_flag, sizeof(int)));
+  if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, xbytes));
+  if (!c->diff_flag) NFFTCU_CUDA(pool_malloc((void **) &c->diff_flag, sizeof(int)));
   const bool forward = which == 0;
   const size_t in_bytes = forward ? cbytes(c, c->N_total) : cbytes(c, c->M);
   const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
@@ -607,19 +610,19 @@ int64_t nfftcu_launch_count(nfftcu_ctx *c) { return c ? c->launches : 0; }
 
 int nfftcu_malloc_device(void **ptr, size_t bytes, int device) {
   NFFTCU_CUDA(cudaSetDevice(device));
-  NFFTCU_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+  NFFTCU_CUDA(pool_malloc(ptr, bytes ? bytes : 1));
   return NFFTCU_OK;
 }
 int nfftcu_free_device(void *ptr) {
-  if (ptr) NFFTCU_CUDA(cudaFree(ptr));
+  if (ptr) NFFTCU_CUDA(pool_free(ptr));
   return NFFTCU_OK;
 }
 int nfftcu_malloc_pinned(void **ptr, size_t bytes) {
-  NFFTCU_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+  NFFTCU_CUDA(pool_malloc_host(ptr, bytes ? bytes : 1));
   return NFFTCU_OK;
 }
 int nfftcu_free_pinned(void *ptr) {
-  if (ptr) NFFTCU_CUDA(cudaFreeHost(ptr));
+  if (ptr) NFFTCU_CUDA(pool_free_host(ptr));
   return NFFTCU_OK;
 }
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {

@@ -31,6 +31,14 @@ void set_error(const char *fmt, ...);
     if (r__ != NFFTCU_OK) return r__;                                                           \
   } while (0)
 
+// ---- cached allocations (mempool.cu): drop-in for cudaMalloc / cudaFree / cudaMallocHost / cudaFreeHost ----------
+cudaError_t pool_malloc_bytes(void **p, size_t bytes);
+cudaError_t pool_free(void *p);
+cudaError_t pool_malloc_host_bytes(void **p, size_t bytes);
+cudaError_t pool_free_host(void *p);
+template <typename T> inline cudaError_t pool_malloc(T **p, size_t bytes) { return pool_malloc_bytes((void **) p, bytes); }
+template <typename T> inline cudaError_t pool_malloc_host(T **p, size_t bytes) { return pool_malloc_host_bytes((void **) p, bytes); }
+
 // ---- scalar/complex type traits ----------------------------------------------------------------
 template <typename T> struct Cplx;
 template <> struct Cplx<double> { typedef double2 type; };
@@ -88,6 +96,7 @@ struct nfftcu_ctx_s {
   void *psi_table = nullptr;        // optional: M * d * (2m+2) reals in processing order
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;
+  bool tile2_ready = false;         // tile_* hold the tile order of the 2-D kernels (tile2d.cu)
   bool mma_ready = false;           // tile_* hold the (tile, u2) order of the DMMA kernels (mma3d.cu)
   void *mma_batches = nullptr;      // uint2 per batch: first node, zlo | nb << 24 | last << 28
   uint32_t *mma_batch_start = nullptr;   // units+1 offsets into mma_batches
@@ -153,6 +162,10 @@ bool tile3d_supported(const nfftcu_ctx *c);                         // tile3d.cu
 int tile3d_bin_nodes(nfftcu_ctx *c);                                // tile3d.cu
 int tile3d_interp(nfftcu_ctx *c, void *f_dev);                      // tile3d.cu
 int tile3d_spread(nfftcu_ctx *c, const void *f_dev);                // tile3d.cu
+bool tile2d_supported(const nfftcu_ctx *c);                         // tile2d.cu
+int tile2d_bin_nodes(nfftcu_ctx *c);                                // tile2d.cu
+int tile2d_interp(nfftcu_ctx *c, void *f_dev);                      // tile2d.cu
+int tile2d_spread(nfftcu_ctx *c, const void *f_dev);                // tile2d.cu
 bool mma3d_supported(const nfftcu_ctx *c);                          // mma3d.cu
 int mma3d_bin_nodes(nfftcu_ctx *c);                                 // mma3d.cu
 int mma3d_interp(nfftcu_ctx *c, void *f_dev);                       // mma3d.cu

@@ -581,7 +581,7 @@ int upload_twiddles(const nfftcu_ctx *c, long long count, long long num_stride, 
       ((float *) host.data())[2 * q + 1] = (float) ci;
     }
   }
-  NFFTCU_CUDA(cudaMalloc(out, host.size()));
+  NFFTCU_CUDA(pool_malloc(out, host.size()));
   NFFTCU_CUDA(cudaMemcpy(*out, host.data(), host.size(), cudaMemcpyHostToDevice));
   return NFFTCU_OK;
 }
@@ -777,7 +777,7 @@ int fft_plan_axes(nfftcu_ctx *c) {
     NFFTCU_TRY(upload_twiddles(c, (ax.len >> s) + 1, 1ll << s, ax.len, &ax.twA));
     NFFTCU_TRY(upload_twiddles(c, 1ll << s, 1, ax.len, &ax.twB));
     c->fft_no_prune = true;
-    if (!c->grid2) NFFTCU_CUDA(cudaMalloc(&c->grid2, 2 * real_size(c) * (size_t) c->n_total));
+    if (!c->grid2) NFFTCU_CUDA(pool_malloc(&c->grid2, 2 * real_size(c) * (size_t) c->n_total));
   }
   return NFFTCU_OK;
 }
@@ -787,11 +787,11 @@ void fft_free_axes(nfftcu_ctx *c) {
     FftAxis &ax = c->fft[t];
     void **ptrs[] = {&ax.whole.tw, &ax.sub1.tw, &ax.sub2.tw, &ax.twA, &ax.twB};
     for (void **p : ptrs) {
-      if (*p) cudaFree(*p);
+      if (*p) pool_free(*p);
       *p = nullptr;
     }
   }
-  if (c->grid2) cudaFree(c->grid2);
+  if (c->grid2) pool_free(c->grid2);
   c->grid2 = nullptr;
 }
 

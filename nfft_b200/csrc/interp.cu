@@ -155,6 +155,7 @@ int run_generic(nfftcu_ctx *c, void *f_dev) {
 int stage_B(nfftcu_ctx *c, void *f_dev) {
   if (c->M == 0) return NFFTCU_OK;
   if (c->mma_ready) return mma3d_interp(c, f_dev);
+  if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_interp(c, f_dev);
   if (c->tile_ready && c->opt_b_kernel != 1) return tile3d_interp(c, f_dev);
   if (!c->ref_sorted) {
     set_error("stage_B: generic kernel needs the reference node order (set NFFTCU_OPT_B_KERNEL before set_nodes)");
@@ -167,7 +168,7 @@ int build_psi_table(nfftcu_ctx *c) {
   if (c->M == 0) return NFFTCU_OK;
   const NodeGeom geo = make_node_geom(c);
   const size_t bytes = real_size(c) * (size_t) c->M * geo.d * geo.W;
-  if (!c->psi_table) NFFTCU_CUDA(cudaMalloc(&c->psi_table, bytes));
+  if (!c->psi_table) NFFTCU_CUDA(pool_malloc(&c->psi_table, bytes));
   const int threads = 256;
   long long blocks = ((long long) c->M * geo.d * geo.W + threads - 1) / threads;
   const long long cap = (long long) c->sm_count * 16;

@@ -15,6 +15,8 @@
 // plan keeps the closed form (kb_phi in common.cuh).
 #include "common.cuh"
 
+#include <mutex>
+
 #include <math.h>
 
 namespace nfftcu {
@@ -65,11 +67,50 @@ void cheb_fit_monomial(int p, long double m, long double b, int l, std::vector<l
 
 // Fills c->kbpoly (host, double) with layout coef[(t*(kKbPolyDeg+1) + k)*W + l], k = power of y, and
 // uploads it.  Returns NFFTCU_OK; c->kbpoly_deg stays -1 when no adequate polynomial was found.
+// The fit depends on (precision, m, b_t) only and costs ~20 ms of long-double arithmetic: plan-per-coil callers create
+// many identical plans, so the results are cached per process.
+struct FitKey {
+  int prec, d;
+  long long m;
+  double b[NFFTCU_MAX_D];
+  bool operator==(const FitKey &o) const {
+    if (prec != o.prec || d != o.d || m != o.m) return false;
+    for (int t = 0; t < d; t++) if (b[t] != o.b[t]) return false;
+    return true;
+  }
+};
+struct FitEntry { FitKey key; int fit; std::vector<double> coef; };
+static std::mutex g_fit_mutex;
+static std::vector<FitEntry> g_fit_cache;
+
+static int upload_poly(nfftcu_ctx *c) {
+  if (c->kbpoly_dev) pool_free(c->kbpoly_dev);
+  c->kbpoly_dev = nullptr;
+  NFFTCU_CUDA(pool_malloc(&c->kbpoly_dev, sizeof(double) * c->kbpoly_host.size()));
+  NFFTCU_CUDA(cudaMemcpy(c->kbpoly_dev, c->kbpoly_host.data(), sizeof(double) * c->kbpoly_host.size(),
+                         cudaMemcpyHostToDevice));
+  return NFFTCU_OK;
+}
+
 int build_kb_poly(nfftcu_ctx *c) {
   const int W = 2 * (int) c->m + 2;
   const long double m = (long double) c->m;
   c->kbpoly_deg = -1;
   c->kbpoly_fit = -1;
+  FitKey key;
+  key.prec = c->prec; key.d = c->d; key.m = c->m;
+  for (int t = 0; t < c->d; t++) key.b[t] = c->b[t];
+  {
+    std::lock_guard<std::mutex> lock(g_fit_mutex);
+    for (const FitEntry &e : g_fit_cache)
+      if (e.key == key) {
+        if (e.fit < 0) return NFFTCU_OK;
+        c->kbpoly_deg = kKbPolyDeg;
+        c->kbpoly_fit = e.fit;
+        c->kbpoly_host = e.coef;
+        return upload_poly(c);
+      }
+  }
   // The device keeps the coefficients of one tap in registers and runs a fixed-length Horner loop, so
   // the table is always stored with kKbPolyDeg+1 coefficients per tap (higher ones zero).
   // fp32 plans need the window to ~1e-9 of its peak only (their results carry 1e-7): about half the degree
@@ -101,13 +142,12 @@ int build_kb_poly(nfftcu_ctx *c) {
       break;
     }
   }
+  {
+    std::lock_guard<std::mutex> lock(g_fit_mutex);
+    if (g_fit_cache.size() < 64) g_fit_cache.push_back(FitEntry{key, c->kbpoly_fit, c->kbpoly_host});
+  }
   if (c->kbpoly_deg < 0) return NFFTCU_OK;
-  if (c->kbpoly_dev) cudaFree(c->kbpoly_dev);
-  c->kbpoly_dev = nullptr;
-  NFFTCU_CUDA(cudaMalloc(&c->kbpoly_dev, sizeof(double) * c->kbpoly_host.size()));
-  NFFTCU_CUDA(cudaMemcpy(c->kbpoly_dev, c->kbpoly_host.data(), sizeof(double) * c->kbpoly_host.size(),
-                         cudaMemcpyHostToDevice));
-  return NFFTCU_OK;
+  return upload_poly(c);
 }
 
 }  // namespace nfftcu

@@ -1092,14 +1092,14 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   const MmaParams P = make_params(c);
   const long long units = (long long) P.NT0 * P.NT1 * P.zseg;
   const long long nkeys = (long long) P.NT0 * P.NT1 * P.n2;
-  if (!c->tile_keys) NFFTCU_CUDA(cudaMalloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
-  if (!c->tile_perm) NFFTCU_CUDA(cudaMalloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
-  if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, real_size(c) * (size_t) M * 3));
-  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
+  if (!c->tile_keys) NFFTCU_CUDA(pool_malloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
+  if (!c->tile_perm) NFFTCU_CUDA(pool_malloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
+  if (!c->tile_x) NFFTCU_CUDA(pool_malloc(&c->tile_x, real_size(c) * (size_t) M * 3));
+  if (!c->f_tile) NFFTCU_CUDA(pool_malloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
   if (!c->bin_start || c->tile_nbins != units) {
-    if (c->bin_start) cudaFree(c->bin_start);
+    if (c->bin_start) pool_free(c->bin_start);
     c->bin_start = nullptr;
-    NFFTCU_CUDA(cudaMalloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    NFFTCU_CUDA(pool_malloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (units + 1)));
     c->tile_nbins = units;
   }
   const int kb = 256;
@@ -1119,12 +1119,12 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   c->launches++;
   // batch table: count per unit, scan, fill
   if (c->mma_units != units) {
-    if (c->mma_batch_start) cudaFree(c->mma_batch_start);
-    if (c->mma_counts) cudaFree(c->mma_counts);
-    if (c->mma_chunk_start) cudaFree(c->mma_chunk_start);
+    if (c->mma_batch_start) pool_free(c->mma_batch_start);
+    if (c->mma_counts) pool_free(c->mma_counts);
+    if (c->mma_chunk_start) pool_free(c->mma_chunk_start);
     c->mma_batch_start = c->mma_counts = c->mma_chunk_start = nullptr;
-    NFFTCU_CUDA(cudaMalloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
-    NFFTCU_CUDA(cudaMalloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
+    NFFTCU_CUDA(pool_malloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    NFFTCU_CUDA(pool_malloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
     c->mma_units = units;
   }
   const unsigned wgrid = (unsigned) ((units * 32 + kb - 1) / kb);
@@ -1135,15 +1135,15 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   NFFTCU_CUDA(cudaMemcpyAsync(&total, c->mma_batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
   if ((long long) total > c->mma_batch_cap) {
-    if (c->mma_batches) cudaFree(c->mma_batches);
+    if (c->mma_batches) pool_free(c->mma_batches);
     c->mma_batches = nullptr;
     c->mma_batch_cap = (long long) total + total / 8 + 1024;
-    NFFTCU_CUDA(cudaMalloc(&c->mma_batches, sizeof(uint2) * (size_t) c->mma_batch_cap));
+    NFFTCU_CUDA(pool_malloc(&c->mma_batches, sizeof(uint2) * (size_t) c->mma_batch_cap));
   }
   mma_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
                                                         c->mma_batch_start, (uint2 *) c->mma_batches, units, P);
   // chunks: count per unit (reusing the counts scratch), scan, fill
-  if (!c->mma_chunk_start) NFFTCU_CUDA(cudaMalloc((void **) &c->mma_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
+  if (!c->mma_chunk_start) NFFTCU_CUDA(pool_malloc((void **) &c->mma_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
   const unsigned ugrid = (unsigned) ((units + kb - 1) / kb);
   mma_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_counts, units);
   mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_chunk_start, units);
@@ -1151,10 +1151,10 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, c->mma_chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
   if ((long long) nchunks > c->mma_chunk_cap) {
-    if (c->mma_chunks) cudaFree(c->mma_chunks);
+    if (c->mma_chunks) pool_free(c->mma_chunks);
     c->mma_chunks = nullptr;
     c->mma_chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
-    NFFTCU_CUDA(cudaMalloc(&c->mma_chunks, sizeof(uint4) * (size_t) c->mma_chunk_cap));
+    NFFTCU_CUDA(pool_malloc(&c->mma_chunks, sizeof(uint4) * (size_t) c->mma_chunk_cap));
   }
   mma_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_chunk_start, (uint4 *) c->mma_chunks, units,
                                                     P.zseg);

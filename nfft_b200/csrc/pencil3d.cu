@@ -645,7 +645,7 @@ int prepare_records(nfftcu_ctx *c, const void *f_dev, const TileParams &P) {
   typedef typename Cplx<T>::type C;
   const size_t bytes = record_bytes<T, W>(c->M);
   if (!c->tile_psi) {
-    NFFTCU_CUDA(cudaMalloc(&c->tile_psi, bytes));
+    NFFTCU_CUDA(pool_malloc(&c->tile_psi, bytes));
     NFFTCU_CUDA(cudaMemsetAsync(c->tile_psi, 0, bytes, c->stream));
     c->tile_psi_valid = false;
   }
@@ -751,13 +751,13 @@ int tile3d_bin_nodes(nfftcu_ctx *c) {
   if (M == 0) return NFFTCU_OK;
   const TileParams P = make_params(c);
   const long long nbins = (long long) P.NT0 * P.NT1 * P.NS;
-  if (!c->tile_keys) NFFTCU_CUDA(cudaMalloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
-  if (!c->tile_perm) NFFTCU_CUDA(cudaMalloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
-  if (!c->tile_x) NFFTCU_CUDA(cudaMalloc(&c->tile_x, real_size(c) * (size_t) M * 3));
-  if (!c->f_tile) NFFTCU_CUDA(cudaMalloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
+  if (!c->tile_keys) NFFTCU_CUDA(pool_malloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
+  if (!c->tile_perm) NFFTCU_CUDA(pool_malloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
+  if (!c->tile_x) NFFTCU_CUDA(pool_malloc(&c->tile_x, real_size(c) * (size_t) M * 3));
+  if (!c->f_tile) NFFTCU_CUDA(pool_malloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
   if (!c->bin_start || c->tile_nbins != nbins) {
-    if (c->bin_start) cudaFree(c->bin_start);
-    NFFTCU_CUDA(cudaMalloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (nbins + 1)));
+    if (c->bin_start) pool_free(c->bin_start);
+    NFFTCU_CUDA(pool_malloc((void **) &c->bin_start, sizeof(uint32_t) * (size_t) (nbins + 1)));
     c->tile_nbins = nbins;
   }
   const int kb = 256;

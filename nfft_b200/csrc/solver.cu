@@ -306,7 +306,7 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
   auto fail = [&](int rc) { nfftcu_solver_destroy(s); return rc; };
 #define SOLVER_ALLOC(ptr, bytes)                                                                    \
   do {                                                                                              \
-    if (cudaMalloc(&(ptr), (bytes) ? (bytes) : 16) != cudaSuccess) {                                \
+    if (pool_malloc(&(ptr), (bytes) ? (bytes) : 16) != cudaSuccess) {                                \
       set_error("nfftcu_solver_create: cudaMalloc of %zu bytes failed", (size_t) (bytes));          \
       return fail(NFFTCU_ENOMEM);                                                                   \
     }                                                                                               \
@@ -324,7 +324,7 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
   SOLVER_ALLOC(s->partial, kMaxBlocks * sizeof(double));
 #undef SOLVER_ALLOC
   if (cudaMemset(s->sc, 0, 8 * sizeof(double)) != cudaSuccess ||
-      cudaMallocHost(&s->sc_host, 8 * sizeof(double)) != cudaSuccess ||
+      pool_malloc_host(&s->sc_host, 8 * sizeof(double)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_fhat, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_r, cudaEventDisableTiming) != cudaSuccess) {
@@ -342,12 +342,12 @@ int nfftcu_solver_destroy(nfftcu_solver *s) {
   if (s->ev_fhat) cudaEventDestroy(s->ev_fhat);
   if (s->ev_r) cudaEventDestroy(s->ev_r);
   if (s->vec[NFFTCU_SOLVER_Z_HAT_ITER] == s->vec[NFFTCU_SOLVER_P_HAT_ITER]) s->vec[NFFTCU_SOLVER_Z_HAT_ITER] = nullptr;
-  for (void *&p : s->vec) { if (p) cudaFree(p); p = nullptr; }
-  if (s->fhat_in) cudaFree(s->fhat_in);
-  if (s->f_in) cudaFree(s->f_in);
-  if (s->sc) cudaFree(s->sc);
-  if (s->partial) cudaFree(s->partial);
-  if (s->sc_host) cudaFreeHost(s->sc_host);
+  for (void *&p : s->vec) { if (p) pool_free(p); p = nullptr; }
+  if (s->fhat_in) pool_free(s->fhat_in);
+  if (s->f_in) pool_free(s->f_in);
+  if (s->sc) pool_free(s->sc);
+  if (s->partial) pool_free(s->partial);
+  if (s->sc_host) pool_free_host(s->sc_host);
   delete s;
   return NFFTCU_OK;
 }

@@ -177,10 +177,10 @@ int radix_sort_pairs(nfftcu_ctx *c, uint64_t *keys, uint32_t *vals, long long M,
   const size_t cbytes = sizeof(uint32_t) * 256 * (size_t) ntiles;
   const size_t need = kbytes + vpad + cbytes;
   if (c->sort_tmp_bytes < need) {
-    if (c->sort_tmp) cudaFree(c->sort_tmp);
+    if (c->sort_tmp) pool_free(c->sort_tmp);
     c->sort_tmp = nullptr;
     c->sort_tmp_bytes = 0;
-    NFFTCU_CUDA(cudaMalloc(&c->sort_tmp, need));
+    NFFTCU_CUDA(pool_malloc(&c->sort_tmp, need));
     c->sort_tmp_bytes = need;
   }
   uint64_t *kA = keys, *kB = (uint64_t *) c->sort_tmp;
@@ -227,9 +227,9 @@ int sort_nodes(nfftcu_ctx *c) {
   const long long M = c->M;
   if (M == 0) return NFFTCU_OK;
   const size_t kbytes = sizeof(uint64_t) * (size_t) M, vbytes = sizeof(uint32_t) * (size_t) M;
-  if (!c->keys_ref) NFFTCU_CUDA(cudaMalloc(&c->keys_ref, kbytes));
-  if (!c->perm) NFFTCU_CUDA(cudaMalloc((void **) &c->perm, vbytes));
-  if (!c->x_sorted) NFFTCU_CUDA(cudaMalloc(&c->x_sorted, real_size(c) * (size_t) M * c->d));
+  if (!c->keys_ref) NFFTCU_CUDA(pool_malloc(&c->keys_ref, kbytes));
+  if (!c->perm) NFFTCU_CUDA(pool_malloc((void **) &c->perm, vbytes));
+  if (!c->x_sorted) NFFTCU_CUDA(pool_malloc(&c->x_sorted, real_size(c) * (size_t) M * c->d));
   c->perm_ref = c->perm;
   KeyGeom g;
   g.d = c->d;

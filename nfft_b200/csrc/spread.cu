@@ -136,6 +136,7 @@ int stage_BT(nfftcu_ctx *c, const void *f_dev) {
   NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, 2 * real_size(c) * (size_t) c->n_total, c->stream));
   if (c->M == 0) return NFFTCU_OK;
   if (c->mma_ready) return mma3d_spread(c, f_dev);
+  if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_spread(c, f_dev);
   if (c->tile_ready && c->opt_b_kernel != 1) return tile3d_spread(c, f_dev);
   if (!c->ref_sorted) {
     set_error("stage_BT: generic kernel needs the reference node order (set NFFTCU_OPT_B_KERNEL before set_nodes)");

@@ -819,3 +819,43 @@ def test_fft_general_lengths_vs_oracle(N, n, m, M, precision):
         x, fh, f = x.astype(np.float64), fh.astype(np.complex128), f.astype(np.complex128)
     assert rel_l2(out_f, o.trafo(N, n, m, x, fh)) <= TOL[precision]
     assert rel_l2(out_fh, o.adjoint(N, n, m, x, f, True)) <= TOL[precision]
+
+
+# ---- (15) 2-D shared-memory tile kernels (tile2d.cu) against the generic kernels and the oracle ------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("N,n,m,M,mode", [
+    ([64, 64], [128, 128], 6, 20000, "uniform"),
+    ([32, 48], [64, 96], 6, 5000, "uniform"),
+    ([20, 30], [50, 72], 5, 3000, "uniform"),          # n not a multiple of the tile edge: partial tiles wrap
+    ([8, 8], [16, 16], 6, 500, "uniform"),             # footprint (45) larger than the grid: rows / columns alias
+    ([16, 10], [33, 21], 2, 700, "uniform"),           # odd n, small window
+    ([64, 64], [160, 144], 7, 4000, "uniform"),        # 2m+2 = 16 taps
+    ([128, 128], [256, 256], 6, 60000, "cluster"),     # thousands of nodes in one tile: many chunks per tile
+    ([128, 128], [256, 256], 4, 30000, "edges"),       # nodes on cell boundaries and at +-0.5
+])
+def test_tile2d_vs_generic_and_oracle(N, n, m, M, mode, precision):
+    rng = np.random.default_rng(91)
+    o = oracle(precision)
+    x = rng.random((M, 2)) - 0.5
+    if mode == "cluster":
+        x = 0.02 * rng.normal(size=(M, 2)) + 0.3
+        x = (x + 0.5) % 1.0 - 0.5
+    if mode == "edges":
+        x = np.round(x * 64) / 64
+        x[: M // 20] = -0.5
+    x = np.minimum(x, 0.5 - 2 ** -20).astype(o.real)
+    NN = int(np.prod(N))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    outs = []
+    for kernel in (0, 1):   # 0: tile2d, 1: generic warp-per-node
+        eng = cabi.Engine(N, n, m, M, precision=precision)
+        eng.set_option(cabi.OPT_B_KERNEL, kernel)
+        eng.set_nodes(x)
+        outs.append((eng.trafo(fh), eng.adjoint(f)))
+        eng.close()
+    tol = TOL[precision] if mode != "cluster" or precision == "double" else 1e-4   # fp32 sums of ~10^4 terms per cell
+    assert rel_l2(outs[0][0], o.trafo(N, n, m, x, fh)) <= TOL[precision]
+    assert rel_l2(outs[0][1], o.adjoint(N, n, m, x, f)) <= tol
+    assert rel_l2(outs[0][0], outs[1][0]) <= (1e-13 if precision == "double" else 1e-5)
+    assert rel_l2(outs[0][1], outs[1][1]) <= (1e-13 if precision == "double" else tol)

@@ -30,3 +30,20 @@ for rep in range(4):
     d = np.diff(t) * 1e3
     print("rep %d: init %.1f ms, nodes+precompute %.1f ms, first pair %.1f ms, 20 pairs %.1f ms (%.2f ms/pair), finalize %.1f ms"
           % (rep, d[0], d[1], d[2], d[3], d[3] / 20, d[4]), flush=True)
+
+# the device-resident solver on the same shape: per-call times of solver_init / before_loop / 20 steps / finalize
+import ctypes as C
+L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsolver_dev_b200.so"), mode=os.RTLD_LOCAL)
+fn = L.solver_driver_run
+fn.restype = C.c_int
+M, NN = 512 * 512, 512 * 512
+y = np.ascontiguousarray(rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5))
+w = np.ones(M); w_hat = np.ones(NN)
+f_hat = np.zeros(NN, dtype=np.complex128); dots = np.zeros(64)
+ia = lambda a: (C.c_int * len(a))(*a)
+p_ = lambda a: a.ctypes.data_as(C.c_void_p)
+for iters in (1, 1, 20, 20, 40):
+    t0 = time.perf_counter()
+    fn(C.c_int(2), ia([512, 512]), C.c_int(M), ia([1024, 1024]), C.c_int(6), C.c_uint(flags), C.c_uint((1 << 2) | (1 << 6)),
+       p_(x), p_(y), p_(w), p_(w_hat), C.c_int(iters), p_(f_hat), p_(dots), C.c_double(0.0), None)
+    print("device solver driver, %2d iterations: %.1f ms" % (iters, (time.perf_counter() - t0) * 1e3), flush=True)
