@@ -444,11 +444,13 @@ static int host_transform_refresh(nfftcu_ctx *c, const void *x_host, const void 
   const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
   void *in_dev = forward ? c->fhat_dev : c->f_dev;
   void *out_dev = forward ? c->f_dev : c->fhat_dev;
-  // the side stream must not start before earlier work on the plan's stream that may still read x_stage
+  // the side stream must not start before earlier work on the plan's stream that may still read x_stage, and not
+  // before the transform's own input is on the device: the node upload would share the host link with it and delay the
+  // first kernel; behind it, the node upload overlaps the kernels
   if (!c->ev_side) NFFTCU_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   NFFTCU_CUDA(cudaEventRecord(c->ev_side, c->stream));
   NFFTCU_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
-  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
   NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->side_stream));
   NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->side_stream));
   {
