@@ -224,33 +224,26 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// Both waits use the hardware-suspended form of try_wait (suspend-time hint): the warp is parked by the barrier unit and
+// wakes when the phase completes, instead of polling.  An SM sub-partition has ONE dispatch port and a DMMA holds it
+// for 16 cycles, so every polling instruction of a waiting warp is taken from the DMMA stream of its neighbours.
+#ifndef NFFTCU_MMA_SUSPEND_NS
+#define NFFTCU_MMA_SUSPEND_NS 0x989680
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity), "r"(NFFTCU_MMA_SUSPEND_NS) : "memory");
 }
 
-// producer-side wait: the producers run up to kStages batches ahead and mostly wait; back off between polls
-// so that the polling loop does not take issue slots from the MMA warps of the same scheduler
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, int parity) {
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    if (done) break;
-    __nanosleep(64);
-  }
-}
+// producer-side wait: the producers run up to kStages batches ahead and mostly wait
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, int parity) { mbar_wait(bar, parity); }
 
 // ---- shared memory ----------------------------------------------------------------------------------------
 // A ring of kStages operand blocks; producer warp w fills the stages of batches j = w (mod 4).
