@@ -9,6 +9,7 @@
  * the per-step mirrors are asynchronous copies.  There is no host iteration in this file: an mv plan that is not
  * an NFFT plan of this library is refused.
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,44 +32,57 @@ typedef nfft_b200_cdouble C;
 __attribute__((visibility("hidden"))) void Y(b200_nodes_for_transform)(Y(plan) *ths);
 
 /* solver_plan_complex has no spare member for the device object: keep a registry keyed by the plan address */
+/* (distinct solver plans may be driven from different host threads, like distinct nfft plans) */
 typedef struct reg_s { const void *key; nfftcu_solver *dev; struct reg_s *next; } reg_t;
 static reg_t *registry = NULL;
+static pthread_mutex_t registry_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static nfftcu_solver *reg_find(const void *key)
 {
   reg_t *r;
-  for (r = registry; r; r = r->next) if (r->key == key) return r->dev;
-  return NULL;
+  nfftcu_solver *dev = NULL;
+  pthread_mutex_lock(&registry_lock);
+  for (r = registry; r; r = r->next) if (r->key == key) { dev = r->dev; break; }
+  pthread_mutex_unlock(&registry_lock);
+  return dev;
 }
 
 static void reg_put(const void *key, nfftcu_solver *dev)
 {
   reg_t *r;
-  for (r = registry; r; r = r->next)
-    if (r->key == key)
-    {
-      if (r->dev) nfftcu_solver_destroy(r->dev);   /* plan re-initialised without finalize */
-      r->dev = dev;
-      return;
-    }
-  r = (reg_t*) malloc(sizeof(reg_t));
+  nfftcu_solver *stale = NULL;
+  pthread_mutex_lock(&registry_lock);
+  for (r = registry; r; r = r->next) if (r->key == key) break;
+  if (r)
+  {
+    stale = r->dev;   /* plan re-initialised without finalize */
+    r->dev = dev;
+  }
+  else
+  {
+    r = (reg_t*) malloc(sizeof(reg_t));
+    if (r) { r->key = key; r->dev = dev; r->next = registry; registry = r; }
+  }
+  pthread_mutex_unlock(&registry_lock);
   if (!r) Y(die)("solver_init: out of memory");
-  r->key = key; r->dev = dev; r->next = registry;
-  registry = r;
+  if (stale) nfftcu_solver_destroy(stale);
 }
 
 static nfftcu_solver *reg_take(const void *key)
 {
   reg_t **pp, *r;
+  nfftcu_solver *dev = NULL;
+  pthread_mutex_lock(&registry_lock);
   for (pp = &registry; (r = *pp) != NULL; pp = &r->next)
     if (r->key == key)
     {
-      nfftcu_solver *dev = r->dev;
+      dev = r->dev;
       *pp = r->next;
       free(r);
-      return dev;
+      break;
     }
-  return NULL;
+  pthread_mutex_unlock(&registry_lock);
+  return dev;
 }
 
 static void check_cu(int status)

@@ -11,9 +11,10 @@
 //     kbpoly.cu, or sinh / sqrt when no polynomial fit exists for this m), in double for both precisions,
 //   * interpolation: one half-warp per node, lane l owns column u1 + l, runs down the 2m+2 rows with one 16-byte
 //     shared load and two FMAs per tap, then a 16-lane shuffle reduction;
-//   * spreading: race-free without atomics inside the tile: half-warp h owns the footprint rows r = h (mod 16); a
-//     node's 2m+2 <= 16 consecutive rows meet every residue at most once, so per node every owner adds at most one
-//     row (lane l: column u1 + l) with a plain read-modify-write; all owners walk all nodes of the chunk.
+//   * spreading: race-free without atomics inside the tile: thread (h, l) of the 16 x 16 CTA owns the footprint cells
+//     with row = h, column = l (mod 16); a node's 2m+2 <= 16 consecutive rows / columns meet every residue at most
+//     once, so per node every thread adds at most one cell with a plain read-modify-write and no two threads share a
+//     cell; all threads walk all nodes of the chunk.
 // Both kernels are bound by shared-memory wavefronts (one 16-byte access per tap), not by HBM: the footprint is
 // read / flushed once per chunk.
 #include "common.cuh"
@@ -23,7 +24,8 @@ namespace nfftcu {
 namespace {
 
 constexpr int kT2 = 32;            // tile edge in cells
-constexpr int kChunkNodes = 128;   // nodes per CTA
+constexpr int kChunkNodes = 128;   // nodes per round: their window values sit in shared memory
+constexpr int kCtaNodes = 1024;    // nodes per CTA (8 rounds): one footprint load / flush per CTA
 constexpr int kThreads2 = 256;
 constexpr int kMaxW2 = 16;         // 2m+2 <= 16 (half-warp per node)
 
@@ -67,7 +69,7 @@ __global__ void tile2_bounds_kernel(const uint64_t *__restrict__ keys, uint32_t 
 __global__ void tile2_chunk_count_kernel(const uint32_t *__restrict__ tile_start, uint32_t *__restrict__ counts, long long tiles) {
   const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= tiles) return;
-  counts[t] = (tile_start[t + 1] - tile_start[t] + kChunkNodes - 1) / kChunkNodes;
+  counts[t] = (tile_start[t + 1] - tile_start[t] + kCtaNodes - 1) / kCtaNodes;
 }
 
 // exclusive scan, single CTA (tile counts are small: n_total / 1024 entries)
@@ -97,8 +99,8 @@ __global__ void tile2_chunk_fill_kernel(const uint32_t *__restrict__ tile_start,
   if (t >= tiles) return;
   const uint32_t k0 = tile_start[t], k1 = tile_start[t + 1];
   uint32_t c = chunk_start[t];
-  for (uint32_t k = k0; k < k1; k += kChunkNodes, c++)
-    chunks[c] = make_uint4((uint32_t) t, k, k + kChunkNodes < k1 ? k + kChunkNodes : k1, 0u);
+  for (uint32_t k = k0; k < k1; k += kCtaNodes, c++)
+    chunks[c] = make_uint4((uint32_t) t, k, k + kCtaNodes < k1 ? k + kCtaNodes : k1, 0u);
 }
 
 template <typename C2>
@@ -166,47 +168,50 @@ interp_tile2_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__r
   double *coef = reinterpret_cast<double *>(org + kChunkNodes);
   const uint4 ch = chunks[blockIdx.x];
   const int ta = (int) ch.x / P.NT1, tb = (int) ch.x - ta * P.NT1;
-  const int k0 = (int) ch.y, cnt = (int) (ch.z - ch.y);
+  const int kbeg = (int) ch.y, kend = (int) ch.z;
 
   for (int i = threadIdx.x; i < P.F * P.F; i += blockDim.x) {
     const int r = i / P.F, cc = i - r * P.F;
     const typename Cplx<TS>::type v = G[(size_t) wrap2(kT2 * ta + r, P.n0) * P.n1 + wrap2(kT2 * tb + cc, P.n1)];
     tile[r * P.pitch + cc] = make_double2((double) v.x, (double) v.y);
   }
-  chunk_windows<TS, false>(xt, nullptr, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
-  __syncthreads();
-
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
-  for (int j0 = 0; j0 < cnt; j0 += kThreads2 / 16) {   // warp-uniform trip count: the shuffles below need all 32 lanes
-    const int j = j0 + hw;
-    const bool live = j < cnt;
-    const NodeOrg o = org[live ? j : 0];
-    double ar = 0.0, ai = 0.0;
-    if (live && l < P.W) {
-      const double2 *col = tile + (size_t) o.r0 * P.pitch + o.c0 + l;
-      const double *p0 = psi0 + j * kMaxW2;
+  for (int k0 = kbeg; k0 < kend; k0 += kChunkNodes) {
+    const int cnt = min(kChunkNodes, kend - k0);
+    chunk_windows<TS, false>(xt, nullptr, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
+    __syncthreads();
+    for (int j0 = 0; j0 < cnt; j0 += kThreads2 / 16) {   // warp-uniform trip count: the shuffles below need all 32 lanes
+      const int j = j0 + hw;
+      const bool live = j < cnt;
+      const NodeOrg o = org[live ? j : 0];
+      double ar = 0.0, ai = 0.0;
+      if (live && l < P.W) {
+        const double2 *col = tile + (size_t) o.r0 * P.pitch + o.c0 + l;
+        const double *p0 = psi0 + j * kMaxW2;
 #pragma unroll 2
-      for (int l0 = 0; l0 < P.W; l0++) {
-        const double2 v = col[(size_t) l0 * P.pitch];
-        const double w = p0[l0];
-        ar = fma(w, v.x, ar);
-        ai = fma(w, v.y, ai);
+        for (int l0 = 0; l0 < P.W; l0++) {
+          const double2 v = col[(size_t) l0 * P.pitch];
+          const double w = p0[l0];
+          ar = fma(w, v.x, ar);
+          ai = fma(w, v.y, ai);
+        }
+        const double w1 = psi1[j * kMaxW2 + l];
+        ar *= w1;
+        ai *= w1;
       }
-      const double w1 = psi1[j * kMaxW2 + l];
-      ar *= w1;
-      ai *= w1;
-    }
 #pragma unroll
-    for (int s = 8; s > 0; s >>= 1) {
-      ar += __shfl_xor_sync(0xffffffffu, ar, s);
-      ai += __shfl_xor_sync(0xffffffffu, ai, s);
+      for (int s = 8; s > 0; s >>= 1) {
+        ar += __shfl_xor_sync(0xffffffffu, ar, s);
+        ai += __shfl_xor_sync(0xffffffffu, ai, s);
+      }
+      if (live && l == 0) {
+        typename Cplx<TS>::type out;
+        out.x = (TS) ar;
+        out.y = (TS) ai;
+        f[perm[k0 + j]] = out;
+      }
     }
-    if (live && l == 0) {
-      typename Cplx<TS>::type out;
-      out.x = (TS) ar;
-      out.y = (TS) ai;
-      f[perm[k0 + j]] = out;
-    }
+    __syncthreads();   // the next round overwrites the window values
   }
 }
 
@@ -226,30 +231,35 @@ spread_tile2_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restric
   double *coef = reinterpret_cast<double *>(org + kChunkNodes);
   const uint4 ch = chunks[blockIdx.x];
   const int ta = (int) ch.x / P.NT1, tb = (int) ch.x - ta * P.NT1;
-  const int k0 = (int) ch.y, cnt = (int) (ch.z - ch.y);
+  const int kbeg = (int) ch.y, kend = (int) ch.z;
 
   for (int i = threadIdx.x; i < P.F * P.pitch; i += blockDim.x) tile[i] = make_double2(0.0, 0.0);
-  chunk_windows<TS, true>(xt, ft, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
-  __syncthreads();
-
-  // half-warp h owns the footprint rows r = h (mod 16)
+  // thread (h, l) owns the footprint cells with row = h and column = l (mod 16): a node's <= 16 consecutive rows and
+  // columns meet every residue at most once, so per node a thread updates at most one cell, no two threads ever touch
+  // the same cell, and a thread's own read-modify-writes are ordered by the hardware -- no atomics, no barriers
+  // inside the node loop.
   const int h = threadIdx.x >> 4, l = threadIdx.x & 15;
   const double2 *pf = reinterpret_cast<const double2 *>(psi1);
-  for (int j = 0; j < cnt; j++) {
-    const NodeOrg o = org[j];
-    const int l0 = (h - o.r0) & 15;   // the one row of this node with r0 + l0 = h (mod 16)
-    if (l0 < P.W && l < P.W) {
-      double2 *cell = tile + (size_t) (o.r0 + l0) * P.pitch + o.c0 + l;
-      const double w = psi0[j * kMaxW2 + l0];
-      const double2 a = pf[j * kMaxW2 + l];
-      double2 v = *cell;
-      v.x = fma(w, a.x, v.x);
-      v.y = fma(w, a.y, v.y);
-      *cell = v;
+  for (int k0 = kbeg; k0 < kend; k0 += kChunkNodes) {
+    const int cnt = min(kChunkNodes, kend - k0);
+    chunk_windows<TS, true>(xt, ft, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; j++) {
+      const NodeOrg o = org[j];
+      const int l0 = (h - o.r0) & 15, l1 = (l - o.c0) & 15;
+      if (l0 < P.W && l1 < P.W) {
+        double2 *cell = tile + (size_t) (o.r0 + l0) * P.pitch + o.c0 + l1;
+        const double w = psi0[j * kMaxW2 + l0];
+        const double2 a = pf[j * kMaxW2 + l1];
+        double2 v = *cell;
+        v.x = fma(w, a.x, v.x);
+        v.y = fma(w, a.y, v.y);
+        *cell = v;
+      }
     }
-    __syncwarp();   // the next node's lanes may touch the cells this node's lanes wrote
+    __syncthreads();   // the next round overwrites the window values; the flush reads the tile
   }
-  __syncthreads();
 
   TS *Gs = reinterpret_cast<TS *>(G);
   for (int i = threadIdx.x; i < P.F * P.F; i += blockDim.x) {
