@@ -52,6 +52,7 @@ typedef struct nfftcu_ctx_s nfftcu_ctx;
 #define NFFTCU_OPT_B_FLUSH 5       /* DMMA spreading: 0 auto | 1 RED.ADD from registers | 2 staged TMA bulk reductions */
 #define NFFTCU_OPT_FFT_PRUNE 6     /* 1 (default): band-pruned FFT passes and D without zero padding inside trafo/adjoint | 0: full passes */
 #define NFFTCU_OPT_FFT_KERNEL 7    /* 0 auto (register-resident Stockham for 2^k lengths 64..2048) | 1 shared-memory Stockham only */
+#define NFFTCU_OPT_WINDOW_IMAGES 8 /* 3-D tensor kernels: per-batch window images built with the node set and fed by TMA: 0 auto (when they fit) | 1 off | 2 on */
 #define NFFTCU_OPT_NODE_ORDER 4    /* 0 auto | 1 reference row-major key | 2 tile-binned */
 
 const char *nfftcu_last_error(void);

@@ -295,7 +295,7 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) pool_free(c->c_dev[t]);
-  void *bufs[] = {c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
+  void *bufs[] = {c->mma_images, c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)
     if (p) pool_free(p);
@@ -565,6 +565,7 @@ int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
     case NFFTCU_OPT_B_FLUSH: c->opt_b_flush = (int) value; break;
     case NFFTCU_OPT_FFT_PRUNE: c->opt_fft_prune = (int) value; break;
     case NFFTCU_OPT_FFT_KERNEL: c->opt_fft_kernel = (int) value; break;
+    case NFFTCU_OPT_WINDOW_IMAGES: c->opt_window_images = (int) value; break;
     default:
       set_error("nfftcu_set_option: unknown option %d", option);
       return NFFTCU_EINVAL;

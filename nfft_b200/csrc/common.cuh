@@ -105,6 +105,10 @@ struct nfftcu_ctx_s {
   uint32_t *mma_chunk_start = nullptr;   // units+1 offsets into mma_chunks
   void *mma_chunks = nullptr;       // uint4 per CTA: tile, first batch, end batch (runs of <= 384 batches of one unit)
   long long mma_nchunks = 0, mma_chunk_cap = 0;
+  void *mma_images = nullptr;       // placed operand blocks (psi0, psi1, psi2: 3 KB) of every batch, built per node set when they fit
+  size_t mma_images_bytes = 0;
+  bool mma_images_ready = false;
+  int opt_window_images = 0;        // 0 auto | 1 off | 2 on regardless of the memory budget
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

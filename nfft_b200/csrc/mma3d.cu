@@ -59,6 +59,8 @@ struct MmaParams {
   int T;            // tile edge: 17 - W
   int NT0, NT1;
   int zseg;         // work units per tile along z
+  const double *img;   // window images (kImgDoubles per batch) or null
+  long long M;
   int m;
   int deg;          // Horner length (fitted polynomial degree)
 };
@@ -275,28 +277,73 @@ __device__ __forceinline__ double pack_tf32_pair(double v) {
 }
 __device__ __forceinline__ double pack_f32(double v) { return __hiloint2double(0, __float_as_int((float) v)); }
 
-template <typename TS, int W, bool SPREAD, bool TF32 = false>
+constexpr int kImgDoubles = 3 * kF * kNB;   // one batch image: psi0, psi1, psi2 placed = 3072 bytes
+
+// interpolation: the batch in stage st has been released by all MMA warps -- add up the 128 per-lane partial sums
+template <typename TS, int W, bool SPREAD>
+__device__ __forceinline__ void finalize_batch(Shared<W, SPREAD> &S, int st, const uint32_t *__restrict__ perm,
+                                               TS *__restrict__ f, int lane) {
+  if (!SPREAD) {
+    // output o = 2*node + comp lives at [w][nr][node >> 1][2*(node & 1) + comp] = 16 consecutive doubles per
+    // (w, nr); lanes o and o+16 each sum 16 of the 32 partials
+    const uint2 mt = S.meta[st];
+    const double *rp = &S.red[st][0][0][0][0] + (lane & 15) + (lane >> 4) * 16 * 16;
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) { v0 += rp[q * 16]; v1 += rp[(q + 1) * 16]; }
+    v0 += v1;
+    v0 += __shfl_xor_sync(kFull, v0, 16);
+    if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = (TS) v0;
+    __syncwarp();
+  }
+}
+
+// Feeder warp pw (0..3) of a CTA that runs on precomputed window images: per batch one elected lane hands the
+// 3072-byte image to the TMA unit, which lands it in the ring stage and completes the stage's full barrier.
+template <typename TS, int W, bool SPREAD>
+__device__ __forceinline__ void feeder_loop(Shared<W, SPREAD> &S, const double *__restrict__ img,
+                                            const uint32_t *__restrict__ perm, TS *__restrict__ f,
+                                            const uint2 *__restrict__ table, int nbat, int pw, int lane) {
+  for (int j = pw; j < nbat; j += 4) {
+    const int st = j % kStages;
+    if (j >= kStages) {
+      mbar_wait(&S.empty[st], ((j / kStages) - 1) & 1);
+      finalize_batch<TS, W, SPREAD>(S, st, perm, f, lane);
+    }
+    if (lane == 0) {
+      S.meta[st] = table[j];
+      // the MMA warps' (generic proxy) reads of the stage are ordered before this point by the empty barrier; order
+      // them before the async-proxy write as well
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&S.full[st])),
+                   "r"((unsigned) (kImgDoubles * sizeof(double))) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_addr(&S.ops[st][0][0][0])), "l"(img + (size_t) j * kImgDoubles),
+                     "r"((unsigned) (kImgDoubles * sizeof(double))), "r"(smem_addr(&S.full[st])) : "memory");
+    }
+    __syncwarp();
+  }
+  if (!SPREAD) {
+    for (int jj = pw; jj < nbat; jj += 4) {
+      if (jj + kStages < nbat) continue;
+      const int st = jj % kStages;
+      mbar_wait(&S.empty[st], (jj / kStages) & 1);
+      finalize_batch<TS, W, SPREAD>(S, st, perm, f, lane);
+    }
+  }
+}
+
+// IMAGE = true: plan-time build of the window images -- the same evaluation and placement, written to img[j] in
+// global memory instead of the ring (no barriers, no finalisation; always the SPREAD = false operand set)
+template <typename TS, int W, bool SPREAD, bool TF32 = false, bool IMAGE = false>
 __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__restrict__ xt,
                                               const typename Cplx<TS>::type *__restrict__ ft,
                                               const uint32_t *__restrict__ perm,
                                               TS *__restrict__ f, const uint2 *__restrict__ table,
-                                              int nbat, int a, int bt, const MmaParams &P, int pw, int lane) {
+                                              int nbat, int a, int bt, const MmaParams &P, int pw, int lane,
+                                              double *__restrict__ img = nullptr) {
   const int i = lane & 7, qg = lane >> 3;
-  auto finalize = [&](int st) {   // interpolation: the batch in stage st has been released by all MMA warps
-    if (!SPREAD) {
-      // output o = 2*node + comp lives at [w][nr][node >> 1][2*(node & 1) + comp] = 16 consecutive doubles per
-      // (w, nr); lanes o and o+16 each sum 16 of the 32 partials
-      const uint2 mt = S.meta[st];
-      const double *rp = &S.red[st][0][0][0][0] + (lane & 15) + (lane >> 4) * 16 * 16;
-      double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 16; q += 2) { v0 += rp[q * 16]; v1 += rp[(q + 1) * 16]; }
-      v0 += v1;
-      v0 += __shfl_xor_sync(kFull, v0, 16);
-      if (lane < 2 * kNB && (lane >> 1) < bt_nb(mt)) f[2 * (size_t) perm[mt.x + (lane >> 1)] + (lane & 1)] = (TS) v0;
-      __syncwarp();
-    }
-  };
+  auto finalize = [&](int st) { finalize_batch<TS, W, SPREAD>(S, st, perm, f, lane); };
   // the prefetched values stay in the storage type until they are used: a conversion right behind the load would
   // make the warp wait for the load at once
   auto load_nodes = [&](uint2 mt, TS &xv, TS &fv) {
@@ -315,10 +362,11 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
     uint2 mt_next2 = make_uint2(0, 0);
     if (j + 4 < nbat) load_nodes(mt_next, xv_next, fv_next);
     if (j + 8 < nbat) mt_next2 = table[j + 8];
-    if (j >= kStages) {
+    if (!IMAGE && j >= kStages) {
       mbar_wait_sleep(&S.empty[st], ((j / kStages) - 1) & 1);
       finalize(st);
     }
+    double *const ops = IMAGE ? img + (size_t) j * kImgDoubles : &S.ops[st][0][0][0];   // [v][slot][node]
     const int nb = bt_nb(mt);
     const bool live = i < nb;
     double fr = 0.0, fi = 0.0;
@@ -371,26 +419,28 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
         const double yo = y * O[r];
         const double va = (tap && live) ? E[r] + yo : 0.0, vb = (tap && live) ? E[r] - yo : 0.0;
         if (SPREAD && t == 1) {
-          S.ops[st][1][sa][i] = TF32 ? pack_f32(va * fr) : va * fr;
-          S.ops[st][1][sb][i] = TF32 ? pack_f32(vb * fr) : vb * fr;
-          S.ops[st][SPREAD ? 3 : 0][sa][i] = TF32 ? pack_f32(va * fi) : va * fi;
-          S.ops[st][SPREAD ? 3 : 0][sb][i] = TF32 ? pack_f32(vb * fi) : vb * fi;
+          ops[(1 * kF + sa) * kNB + i] = TF32 ? pack_f32(va * fr) : va * fr;
+          ops[(1 * kF + sb) * kNB + i] = TF32 ? pack_f32(vb * fr) : vb * fr;
+          ops[(3 * kF + sa) * kNB + i] = TF32 ? pack_f32(va * fi) : va * fi;
+          ops[(3 * kF + sb) * kNB + i] = TF32 ? pack_f32(vb * fi) : vb * fi;
         } else if (TF32) {
-          S.ops[st][t][sa][i] = t == 2 ? pack_tf32_pair(va) : pack_f32(va);
-          S.ops[st][t][sb][i] = t == 2 ? pack_tf32_pair(vb) : pack_f32(vb);
+          ops[(t * kF + sa) * kNB + i] = t == 2 ? pack_tf32_pair(va) : pack_f32(va);
+          ops[(t * kF + sb) * kNB + i] = t == 2 ? pack_tf32_pair(vb) : pack_f32(vb);
         } else {
-          S.ops[st][t][sa][i] = va;
-          S.ops[st][t][sb][i] = vb;
+          ops[(t * kF + sa) * kNB + i] = va;
+          ops[(t * kF + sb) * kNB + i] = vb;
         }
       }
     }
-    if (lane == 0) S.meta[st] = mt;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&S.full[st]);
+    if (!IMAGE) {
+      if (lane == 0) S.meta[st] = mt;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.full[st]);
+    }
     mt = mt_next; mt_next = mt_next2;
     xv = xv_next; fv = fv_next;
   }
-  if (!SPREAD) {
+  if (!SPREAD && !IMAGE) {
     for (int jj = pw; jj < nbat; jj += 4) {
       if (jj + kStages < nbat) continue;   // finished in the loop, when the stage was refilled
       const int st = jj % kStages;
@@ -428,7 +478,8 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
   __syncthreads();                                                                                    \
   if (tid >= 128) {                                                                                   \
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));                             \
-    producer_loop<TS, W, SPREADV, TF32V>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31); \
+    if (IMG) feeder_loop<TS, W, SPREADV>(S, P.img + (size_t) b0 * kImgDoubles, perm, f, table, nbat, (tid >> 5) - 4, tid & 31); \
+    else producer_loop<TS, W, SPREADV, TF32V>(S, xt, ft, perm, f, table, nbat, a, bt, P, (tid >> 5) - 4, tid & 31); \
     return;                                                                                           \
   }                                                                                                   \
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMmaRegs));                                \
@@ -437,7 +488,7 @@ __device__ __forceinline__ void producer_loop(Shared<W, SPREAD> &S, const TS *__
   const unsigned *const rowoff_s = S.rowoff + 4 * warp * kF + nr;   /* group g: [(g >> 1) * kF + 8 * (g & 1)] */
 
 // ---- interpolation ------------------------------------------------------------------------------------
-template <typename TS, int W>
+template <typename TS, int W, bool IMG>
 __global__ void __launch_bounds__(256, 2)
 interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                   const uint32_t *__restrict__ perm, TS *__restrict__ f,
@@ -541,7 +592,7 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
 // FLUSH = 1: staged per warp in shared memory as 128-byte runs and reduced into the grid by the TMA unit
 constexpr int kStgRow = 9;   // staging row pitch in 16-byte cells: 8 cells + 1 pad (bank-conflict-free, 16-byte aligned)
 
-template <typename TS, int W, int FLUSH>
+template <typename TS, int W, int FLUSH, bool IMG>
 __global__ void __launch_bounds__(256, 2)
 spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                   const typename Cplx<TS>::type *__restrict__ ft,
@@ -648,6 +699,16 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
+    double fr[2] = {0.0, 0.0}, fi[2] = {0.0, 0.0};   // IMG: samples of nodes kq and 4 + kq (the image holds psi1, not psi1 f)
+    if (IMG) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+        if (4 * ks + kq < bt_nb(e_next)) {
+          const typename Cplx<TS>::type v = ft[(size_t) e_next.x + 4 * ks + kq];
+          fr[ks] = (double) v.x;
+          fi[ks] = (double) v.y;
+        }
+    }
     if (j + 1 < nbat) e_next = table[j + 1];
     // ---- slide the window to zlo: the cells below it are final
     if (zwin < 0) zwin = zlo;
@@ -668,8 +729,14 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        p1r[hh][ks] = S.ops[st][1][8 * hh + nr][4 * ks + kq];
-        p1i[hh][ks] = S.ops[st][3][8 * hh + nr][4 * ks + kq];
+        if (IMG) {
+          const double q1 = S.ops[st][1][8 * hh + nr][4 * ks + kq];
+          p1r[hh][ks] = q1 * fr[ks];
+          p1i[hh][ks] = q1 * fi[ks];
+        } else {
+          p1r[hh][ks] = S.ops[st][1][8 * hh + nr][4 * ks + kq];
+          p1i[hh][ks] = S.ops[st][3][8 * hh + nr][4 * ks + kq];
+        }
       }
     double p0[4][2];
 #pragma unroll
@@ -726,7 +793,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int W>
+template <int W, bool IMG>
 __global__ void __launch_bounds__(256, 2)
 interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
                    const uint32_t *__restrict__ perm, float *__restrict__ f,
@@ -854,7 +921,7 @@ interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
   }
 }
 
-template <int W>
+template <int W, bool IMG>
 __global__ void __launch_bounds__(256, 2)
 spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const float2 *__restrict__ ft,
                    const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
@@ -902,6 +969,16 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
+    float fr[2] = {0.f, 0.f}, fi[2] = {0.f, 0.f};   // IMG: samples of nodes kq and 4 + kq
+    if (IMG) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+        if (4 * ks + kq < bt_nb(e_next)) {
+          const float2 v = ft[(size_t) e_next.x + 4 * ks + kq];
+          fr[ks] = v.x;
+          fi[ks] = v.y;
+        }
+    }
     if (j + 1 < nbat) e_next = table[j + 1];
     if (zwin < 0) zwin = zlo;
     if (zlo != zwin) {
@@ -924,8 +1001,14 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        p1r[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][1][8 * hh + nr][4 * ks + kq])->x);
-        p1i[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][3][8 * hh + nr][4 * ks + kq])->x);
+        const float q1 = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][1][8 * hh + nr][4 * ks + kq])->x);
+        if (IMG) {
+          p1r[hh][ks] = q1 * fr[ks];
+          p1i[hh][ks] = q1 * fi[ks];
+        } else {
+          p1r[hh][ks] = q1;
+          p1i[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][3][8 * hh + nr][4 * ks + kq])->x);
+        }
       }
     float p0[4][2];
 #pragma unroll
@@ -957,6 +1040,36 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
   for (int zp = zwin; zp < zwin + kF; zp += 2) retire_pair(zp);
 }
 
+// ---- window images (plan time) ----------------------------------------------------------------------------------
+// The window values of a node set do not change between transforms, and evaluating them in the kernels costs the
+// producer warps ~11 000 cycles per batch on an FP64 pipe that the DMMA stream keeps busy (measured with clock64()
+// probes: the MMA warps wait for operands 8 % of the time and the producers never idle).  When memory allows, the
+// placed operand block of every batch -- psi0, psi1, psi2 as the ring stage holds them, 3 KB -- is therefore written
+// once per node set (the reference's precompute_psi, nfft.c:5819-5844, stores psi per node for the same reason) and
+// the kernels' producer warps become feeders: one TMA bulk copy per batch.  For spreading the image holds psi1 and
+// the MMA warps multiply by the samples.  4.1 GB at cfg3; plans whose images would not fit keep the evaluating producers.
+template <typename TS, int W, bool TF32>
+__global__ void __launch_bounds__(128)
+mma_images_kernel(const TS *__restrict__ xt, const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
+                  const double *__restrict__ poly, double *__restrict__ img, MmaParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Shared<W, false> &S = *reinterpret_cast<Shared<W, false> *>(smem_raw);
+  const int tid = threadIdx.x;
+  const uint4 chunk = chunks[blockIdx.x];
+  const uint32_t b0 = chunk.y;
+  const int nbat = (int) (chunk.z - b0);
+  if (nbat == 0) return;
+  const int tile = (int) chunk.x;
+  const int a = tile / P.NT1, bt = tile - a * P.NT1;
+  for (int i = tid; i < 3 * W * kCoefK; i += 128) {
+    const int t = i / (W * kCoefK), l = (i / kCoefK) % W, k = i % kCoefK;
+    S.coef[i] = k <= kKbPolyDeg ? poly[(t * (kKbPolyDeg + 1) + k) * W + l] : 0.0;
+  }
+  __syncthreads();
+  producer_loop<TS, W, false, TF32, true>(S, xt, nullptr, nullptr, nullptr, table + b0, nbat, a, bt, P, tid >> 5, tid & 31,
+                                          img + (size_t) b0 * kImgDoubles);
+}
+
 MmaParams make_params(const nfftcu_ctx *c) {
   MmaParams P;
   P.n0 = (int) c->n[0];
@@ -973,6 +1086,8 @@ MmaParams make_params(const nfftcu_ctx *c) {
   if (zseg < 1) zseg = 1;
   P.zseg = (int) zseg;
   P.deg = c->kbpoly_fit;
+  P.img = c->mma_images_ready ? (const double *) c->mma_images : nullptr;
+  P.M = c->M;
   return P;
 }
 
@@ -983,8 +1098,8 @@ size_t spread_smem() {
   return b;
 }
 
-template <typename TS, int W>
-int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
+template <typename TS, int W, bool IMG>
+int launch_img(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
   typedef typename Cplx<TS>::type C2;
   const unsigned grid = (unsigned) c->mma_nchunks;
   if (grid == 0) return NFFTCU_OK;
@@ -995,9 +1110,9 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   if (sizeof(TS) == 4 && c->opt_b_kernel != 3) {   // fp32 plans: TF32 tensor path (NFFTCU_OPT_B_KERNEL = 3 forces DMMA)
     if (!spread) {
       const size_t smem = sizeof(Shared<W, false>);
-      NFFTCU_CUDA(cudaFuncSetAttribute(interp_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      NFFTCU_CUDA(cudaFuncSetAttribute(interp_tf32_kernel<W, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
-      interp_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((const float2 *) c->grid, (const float *) c->tile_x, c->tile_perm,
+      interp_tf32_kernel<W, IMG><<<grid, 256, smem, c->stream>>>((const float2 *) c->grid, (const float *) c->tile_x, c->tile_perm,
                                                             (float *) f_out, chunks, table, poly, P);
       if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
       c->launches++;
@@ -1006,9 +1121,9 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
       mma_gather_f_kernel<float2><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
           (const float2 *) f_in, c->tile_perm, (float2 *) c->f_tile, c->M);
       const size_t smem = sizeof(Shared<W, true>);
-      NFFTCU_CUDA(cudaFuncSetAttribute(spread_tf32_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_tf32_kernel<W, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
-      spread_tf32_kernel<W><<<grid, 256, smem, c->stream>>>((float2 *) c->grid, (const float *) c->tile_x,
+      spread_tf32_kernel<W, IMG><<<grid, 256, smem, c->stream>>>((float2 *) c->grid, (const float *) c->tile_x,
                                                             (const float2 *) c->f_tile, chunks, table, poly, P);
       if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
       c->launches += 2;
@@ -1018,9 +1133,9 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   }
   if (!spread) {
     const size_t smem = sizeof(Shared<W, false>);
-    NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<TS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    NFFTCU_CUDA(cudaFuncSetAttribute(interp_mma_kernel<TS, W, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
-    interp_mma_kernel<TS, W><<<grid, 256, smem, c->stream>>>((const C2 *) c->grid, xt, c->tile_perm, (TS *) f_out,
+    interp_mma_kernel<TS, W, IMG><<<grid, 256, smem, c->stream>>>((const C2 *) c->grid, xt, c->tile_perm, (TS *) f_out,
                                                              chunks, table, poly, P);
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches++;
@@ -1028,17 +1143,17 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
     const int kb = 256;
     mma_gather_f_kernel<C2><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>(
         (const C2 *) f_in, c->tile_perm, (C2 *) c->f_tile, c->M);
-    const bool bulk = sizeof(TS) == 8 && (P.n2 % 8 == 0) && c->opt_b_flush == 2;
+    const bool bulk = !IMG && sizeof(TS) == 8 && (P.n2 % 8 == 0) && c->opt_b_flush == 2;
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     if (bulk) {
       const size_t smem = spread_smem<W, 1>();
-      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<double, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<double, W, 1><<<grid, 256, smem, c->stream>>>(
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<double, W, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<double, W, 1, false><<<grid, 256, smem, c->stream>>>(
           (double2 *) c->grid, (const double *) c->tile_x, (const double2 *) c->f_tile, chunks, table, poly, P);
     } else {
       const size_t smem = spread_smem<W, 0>();
-      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<TS, W, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      spread_mma_kernel<TS, W, 0><<<grid, 256, smem, c->stream>>>((C2 *) c->grid, xt, (const C2 *) c->f_tile,
+      NFFTCU_CUDA(cudaFuncSetAttribute(spread_mma_kernel<TS, W, 0, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      spread_mma_kernel<TS, W, 0, IMG><<<grid, 256, smem, c->stream>>>((C2 *) c->grid, xt, (const C2 *) c->f_tile,
                                                                   chunks, table, poly, P);
     }
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
@@ -1046,6 +1161,48 @@ int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaP
   }
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
+}
+
+template <typename TS, int W>
+int launch(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread, const MmaParams &P) {
+  return P.img ? launch_img<TS, W, true>(c, f_in, f_out, spread, P) : launch_img<TS, W, false>(c, f_in, f_out, spread, P);
+}
+
+// plan time: window images for the current node set (see mma_images_kernel), when they fit
+template <typename TS, int W>
+int build_images_w(nfftcu_ctx *c, const MmaParams &P, long long nbatches) {
+  const size_t smem = sizeof(Shared<W, false>);
+  const unsigned grid = (unsigned) c->mma_nchunks;
+  double *img = (double *) c->mma_images;
+  const bool tf32 = sizeof(TS) == 4 && c->opt_b_kernel != 3;
+  (void) nbatches;
+  if (tf32) {
+    NFFTCU_CUDA(cudaFuncSetAttribute(mma_images_kernel<TS, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mma_images_kernel<TS, W, true><<<grid, 128, smem, c->stream>>>((const TS *) c->tile_x, (const uint4 *) c->mma_chunks,
+                                                                  (const uint2 *) c->mma_batches,
+                                                                  (const double *) c->kbpoly_dev, img, P);
+  } else {
+    NFFTCU_CUDA(cudaFuncSetAttribute(mma_images_kernel<TS, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mma_images_kernel<TS, W, false><<<grid, 128, smem, c->stream>>>((const TS *) c->tile_x, (const uint4 *) c->mma_chunks,
+                                                                   (const uint2 *) c->mma_batches,
+                                                                   (const double *) c->kbpoly_dev, img, P);
+  }
+  c->launches++;
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+template <typename TS>
+int build_images(nfftcu_ctx *c, const MmaParams &P, long long nbatches) {
+  switch (2 * (int) c->m + 2) {
+    case 6: return build_images_w<TS, 6>(c, P, nbatches);
+    case 8: return build_images_w<TS, 8>(c, P, nbatches);
+    case 10: return build_images_w<TS, 10>(c, P, nbatches);
+    case 12: return build_images_w<TS, 12>(c, P, nbatches);
+    case 14: return build_images_w<TS, 14>(c, P, nbatches);
+    default: break;
+  }
+  return NFFTCU_EINVAL;
 }
 
 template <typename TS>
@@ -1154,6 +1311,30 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   c->mma_nchunks = nchunks;
   c->launches += 6;
   NFFTCU_CUDA(cudaGetLastError());
+  // window images: on when they fit (NFFTCU_OPT_WINDOW_IMAGES: 0 auto | 1 off | 2 on regardless of the budget)
+  c->mma_images_ready = false;
+  if (c->opt_window_images != 1 && total > 0) {
+    const size_t need = sizeof(double) * kImgDoubles * (size_t) total;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const bool have = c->mma_images && c->mma_images_bytes >= need;
+    const bool fits = have || c->opt_window_images == 2 || (need <= free_b / 2 && need <= ((size_t) 48 << 30));
+    if (fits) {
+      if (!have) {
+        if (c->mma_images) pool_free(c->mma_images);
+        c->mma_images = nullptr;
+        c->mma_images_bytes = 0;
+        if (pool_malloc(&c->mma_images, need + need / 16) == cudaSuccess) c->mma_images_bytes = need + need / 16;
+        else cudaGetLastError();   // no room after all: keep the evaluating producers
+      }
+      if (c->mma_images) {
+        MmaParams Pi = P;
+        Pi.img = nullptr;
+        NFFTCU_TRY(c->prec == NFFTCU_DOUBLE ? build_images<double>(c, Pi, total) : build_images<float>(c, Pi, total));
+        c->mma_images_ready = true;
+      }
+    }
+  }
   c->mma_ready = true;
   return NFFTCU_OK;
 }

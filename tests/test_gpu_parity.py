@@ -524,6 +524,33 @@ def test_tile3d_clustered_nodes_are_cut_into_chunks(precision):
         assert rel_l2(got_fh, want) <= 2 * rel_l2(o.adjoint(N, n, m, x, f), want) + 1e-5   # no worse than the fp32 reference
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("N,n,m,M", [([16, 16, 16], [32, 32, 32], 6, 20000), ([20, 18, 21], [40, 36, 42], 4, 5000),
+                                     ([12, 12, 12], [24, 24, 24], 2, 3000)])
+def test_tile3d_window_images_vs_evaluating_producers(N, n, m, M, precision):
+    """3-D tensor kernels fed by plan-time window images (TMA bulk copy per batch, NFFTCU_OPT_WINDOW_IMAGES auto)
+    against the same kernels with evaluating producer warps (option 1), and both against the oracle."""
+    rng = np.random.default_rng(35)
+    o = oracle(precision)
+    x = (rng.random((M, 3)) - 0.5).astype(o.real)
+    NN = int(np.prod(N))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(o.cplx)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(o.cplx)
+    outs = []
+    for images in (0, 1, 2):
+        eng = cabi.Engine(N, n, m, M, precision=precision)
+        eng.set_option(cabi.OPT_WINDOW_IMAGES, images)
+        eng.set_nodes(x)
+        outs.append((eng.trafo(fh), eng.adjoint(f)))
+        eng.close()
+    assert rel_l2(outs[0][0], o.trafo(N, n, m, x, fh)) <= TOL[precision]
+    assert rel_l2(outs[0][1], o.adjoint(N, n, m, x, f)) <= TOL[precision]
+    tight = 1e-14 if precision == "double" else 2e-6
+    for k in (1, 2):
+        assert rel_l2(outs[k][0], outs[0][0]) <= tight
+        assert rel_l2(outs[k][1], outs[0][1]) <= tight
+
+
 def test_tile3d_z_segments_small_grid_many_nodes():
     """few tiles -> the sweep is split into z segments; every segment flushes / preloads its window."""
     rng = np.random.default_rng(32)
