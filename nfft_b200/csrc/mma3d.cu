@@ -48,6 +48,11 @@
 
 namespace nfftcu {
 
+#ifdef NFFTCU_DBG_CLOCKS
+// timing probes (debug builds only, tools/dbg_clocks.py): clock64() section totals of MMA warp 0 of every CTA
+__device__ unsigned long long g_dbg[16];
+#endif
+
 namespace {
 
 constexpr int kNB = 8;        // nodes per batch
@@ -541,13 +546,21 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
     }
   };
 
+#ifdef NFFTCU_DBG_CLOCKS
+  long long tw = 0, tm = 0, tr = 0, tt = 0, t_all = clock64();
+#define DBG_T(var) const long long var = clock64()
+#else
+#define DBG_T(var)
+#endif
   uint2 e_next = table[0];
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
     if (j + 1 < nbat) e_next = table[j + 1];   // lands during this batch: the next window base
     if (zlo != zwin) advance_to(zlo);
+    DBG_T(c0);
     mbar_wait(&S.full[st], (j / kStages) & 1);
+    DBG_T(c1);
 
     // ---- T = G * psi2, weighted row sums
     double bf[4];
@@ -578,13 +591,25 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
     }
     // the window registers are free again: slide the window to the next batch now, so that the refill
     // loads fly while this batch is being reduced
+    DBG_T(c2);
     if (j + 1 < nbat && bt_zlo(e_next) != zwin) advance_to(bt_zlo(e_next));
+    DBG_T(c3);
     // per-lane partial sums go to the ring; the producer warp that refills the stage adds them up
     *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][0]) = make_double2(accr0, acci0);
     *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][2]) = make_double2(accr1, acci1);
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.empty[st]);
+#ifdef NFFTCU_DBG_CLOCKS
+    { const long long c4 = clock64(); tw += c1 - c0; tm += c2 - c1; tr += c3 - c2; tt += c4 - c3; }
+#endif
   }
+#ifdef NFFTCU_DBG_CLOCKS
+  if (warp == 0 && lane == 0) {
+    atomicAdd(&g_dbg[0], (unsigned long long) tw); atomicAdd(&g_dbg[1], (unsigned long long) tm);
+    atomicAdd(&g_dbg[2], (unsigned long long) tr); atomicAdd(&g_dbg[3], (unsigned long long) tt);
+    atomicAdd(&g_dbg[4], (unsigned long long) (clock64() - t_all)); atomicAdd(&g_dbg[5], (unsigned long long) nbat);
+  }
+#endif
 }
 
 // ---- spreading ------------------------------------------------------------------------------------------
@@ -1338,6 +1363,16 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   c->mma_ready = true;
   return NFFTCU_OK;
 }
+
+#ifdef NFFTCU_DBG_CLOCKS
+extern "C" int nfftcu_debug_clocks(unsigned long long *out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_dbg, z, sizeof(z));
+  return 0;
+}
+#endif
 
 int mma3d_interp(nfftcu_ctx *c, void *f_dev) {
   return c->prec == NFFTCU_DOUBLE ? dispatch<double>(c, nullptr, f_dev, false) : dispatch<float>(c, nullptr, f_dev, false);

@@ -25,6 +25,4 @@ for rep in range(3):
     nb = max(v[5], 1)
     print("rep %d: batches %d | per batch (MMA warp 0): wait-full %.0f, mma+weights %.0f, refill issue %.0f, tail %.0f, loop total %.0f clks"
           % (rep, v[5], v[0] / nb, v[1] / nb, v[2] / nb, v[3] / nb, v[4] / nb))
-    pb = max(v[10], 1)
-    print("       producer warp 0: batches %d, per own batch: wait-empty %.0f, iteration total %.0f clks" % (v[10], v[8] / pb, v[9] / pb))
 eng.close()
