@@ -369,7 +369,9 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": a_dom,
                     "launch_ms": t_dom, "peak_source": pk_src,
                     "note": "FP64 tensor cores (DMMA m8n8k4): useful flops only, zero padding of the 16^3 window "
-                            "(67 % lane efficiency) not counted",
+                            "(67 % lane efficiency) not counted; traffic includes the plan-time window images "
+                            "(3 KB per 8-node batch, 4.06 GB, a PRE_PSI-style table the TMA unit streams once per launch) "
+                            "on top of ~1.3 GB for grid + nodes",
                     "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak,
                             "peak_source": peak_src}}
         elif tf32:
