@@ -108,6 +108,7 @@ struct nfftcu_ctx_s {
   void *mma_images = nullptr;       // placed operand blocks (psi0, psi1, psi2: 3 KB) of every batch, built per node set when they fit
   size_t mma_images_bytes = 0;
   bool mma_images_ready = false;
+  bool mma_images_tf32 = false;     // images hold packed fp32 / TF32 pairs (fp32 plans on the TF32 kernels)
   int opt_window_images = 0;        // 0 auto | 1 off | 2 on regardless of the memory budget
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted

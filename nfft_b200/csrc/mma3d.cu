@@ -1111,7 +1111,9 @@ MmaParams make_params(const nfftcu_ctx *c) {
   if (zseg < 1) zseg = 1;
   P.zseg = (int) zseg;
   P.deg = c->kbpoly_fit;
-  P.img = c->mma_images_ready ? (const double *) c->mma_images : nullptr;
+  // the images hold fp64 values or packed fp32 / TF32 pairs, fixed when they were built: use them only for that kernel family
+  const bool want_tf32 = c->prec == NFFTCU_FLOAT && c->opt_b_kernel != 3;
+  P.img = (c->mma_images_ready && c->mma_images_tf32 == want_tf32) ? (const double *) c->mma_images : nullptr;
   P.M = c->M;
   return P;
 }
@@ -1356,6 +1358,7 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
         MmaParams Pi = P;
         Pi.img = nullptr;
         NFFTCU_TRY(c->prec == NFFTCU_DOUBLE ? build_images<double>(c, Pi, total) : build_images<float>(c, Pi, total));
+        c->mma_images_tf32 = c->prec == NFFTCU_FLOAT && c->opt_b_kernel != 3;
         c->mma_images_ready = true;
       }
     }
