@@ -749,20 +749,23 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
     for (int nt = 0; nt < 2; nt++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) bf[nt][ks] = S.ops[st][2][8 * nt + nr][4 * ks + kq];
-    double p1r[2][2], p1i[2][2];   // [half][k-step]
+    double p1r[2][2], p1i[2][2];   // [half][k-step]: psi1 f.re, psi1 f.im (IMG: psi1 in p1r, the samples go into psi2 instead)
 #pragma unroll
     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        if (IMG) {
-          const double q1 = S.ops[st][1][8 * hh + nr][4 * ks + kq];
-          p1r[hh][ks] = q1 * fr[ks];
-          p1i[hh][ks] = q1 * fi[ks];
-        } else {
-          p1r[hh][ks] = S.ops[st][1][8 * hh + nr][4 * ks + kq];
-          p1i[hh][ks] = S.ops[st][3][8 * hh + nr][4 * ks + kq];
-        }
+        p1r[hh][ks] = S.ops[st][1][8 * hh + nr][4 * ks + kq];
+        p1i[hh][ks] = IMG ? 0.0 : S.ops[st][3][8 * hh + nr][4 * ks + kq];
       }
+    // IMG: the sample of node k multiplies the B operand psi2[k][z] (8 products per lane) instead of the A operand
+    // psi0 psi1 [row][k] (32 per lane): G += (psi0 psi1) * (psi2 f.re), (psi0 psi1) * (psi2 f.im)
+    double bfi[2][2];
+    if (IMG) {
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) { bfi[nt][ks] = bf[nt][ks] * fi[ks]; bf[nt][ks] *= fr[ks]; }
+    }
     double p0[4][2];
 #pragma unroll
     for (int h = 0; h < 4; h++) { p0[h][0] = S.ops[st][0][4 * warp + h][kq]; p0[h][1] = S.ops[st][0][4 * warp + h][4 + kq]; }
@@ -773,17 +776,17 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
 #pragma unroll
       for (int hh = 0; hh < 2; hh++) {
         const int g = 2 * h + hh;
-        const double ar0 = p0[h][0] * p1r[hh][0], ai0 = p0[h][0] * p1i[hh][0];
-        const double ar1 = p0[h][1] * p1r[hh][1], ai1 = p0[h][1] * p1i[hh][1];
+        const double ar0 = p0[h][0] * p1r[hh][0], ar1 = p0[h][1] * p1r[hh][1];
+        const double ai0 = IMG ? ar0 : p0[h][0] * p1i[hh][0], ai1 = IMG ? ar1 : p0[h][1] * p1i[hh][1];
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           dmma(C[g][0][nt][0], C[g][0][nt][1], ar0, bf[nt][0]);
-          dmma(C[g][1][nt][0], C[g][1][nt][1], ai0, bf[nt][0]);
+          dmma(C[g][1][nt][0], C[g][1][nt][1], ai0, IMG ? bfi[nt][0] : bf[nt][0]);
         }
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
           dmma(C[g][0][nt][0], C[g][0][nt][1], ar1, bf[nt][1]);
-          dmma(C[g][1][nt][0], C[g][1][nt][1], ai1, bf[nt][1]);
+          dmma(C[g][1][nt][0], C[g][1][nt][1], ai1, IMG ? bfi[nt][1] : bf[nt][1]);
         }
       }
     }
