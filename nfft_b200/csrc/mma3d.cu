@@ -1024,20 +1024,27 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
         bh[nt][ks] = v.x;
         bl[nt][ks] = v.y;
       }
-    float p1r[2][2], p1i[2][2];    // [half][k half]
+    float p1r[2][2], p1i[2][2];    // [half][k half]: psi1 f.re, psi1 f.im (IMG: psi1 in p1r, the samples go into psi2 instead)
 #pragma unroll
     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        const float q1 = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][1][8 * hh + nr][4 * ks + kq])->x);
-        if (IMG) {
-          p1r[hh][ks] = q1 * fr[ks];
-          p1i[hh][ks] = q1 * fi[ks];
-        } else {
-          p1r[hh][ks] = q1;
-          p1i[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][3][8 * hh + nr][4 * ks + kq])->x);
-        }
+        p1r[hh][ks] = __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][1][8 * hh + nr][4 * ks + kq])->x);
+        p1i[hh][ks] = IMG ? 0.f : __uint_as_float(reinterpret_cast<const uint2 *>(&S.ops[st][3][8 * hh + nr][4 * ks + kq])->x);
       }
+    // IMG: the sample of node k multiplies the B operand psi2[k][z] (8 products and splits per lane) instead of the
+    // A operand psi0 psi1 [row][k] (32 per lane); the A fragments are then shared by the re and im accumulators
+    unsigned bih[2][2], bil[2][2];
+    if (IMG) {
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          const float v2 = __uint_as_float(bh[nt][ks]) + __uint_as_float(bl[nt][ks]);
+          split_tf32(v2 * fi[ks], bih[nt][ks], bil[nt][ks]);
+          split_tf32(v2 * fr[ks], bh[nt][ks], bl[nt][ks]);
+        }
+    }
     float p0[4][2];
 #pragma unroll
     for (int h = 0; h < 4; h++) {
@@ -1048,19 +1055,36 @@ spread_tf32_kernel(float2 *__restrict__ G, const float *__restrict__ xt, const f
     if (lane == 0) mbar_arrive(&S.empty[st]);   // operands are in registers: the stage can be refilled
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-#pragma unroll
-      for (int cc = 0; cc < 2; cc++) {
+      if (IMG) {
         // A fragment: a0 (group 2h, node kq), a1 (group 2h+1, node kq), a2 (group 2h, node 4+kq), a3 (group 2h+1, node 4+kq)
         unsigned ah[4], al[4];
-        split_tf32(p0[h][0] * (cc ? p1i[0][0] : p1r[0][0]), ah[0], al[0]);
-        split_tf32(p0[h][0] * (cc ? p1i[1][0] : p1r[1][0]), ah[1], al[1]);
-        split_tf32(p0[h][1] * (cc ? p1i[0][1] : p1r[0][1]), ah[2], al[2]);
-        split_tf32(p0[h][1] * (cc ? p1i[1][1] : p1r[1][1]), ah[3], al[3]);
+        split_tf32(p0[h][0] * p1r[0][0], ah[0], al[0]);
+        split_tf32(p0[h][0] * p1r[1][0], ah[1], al[1]);
+        split_tf32(p0[h][1] * p1r[0][1], ah[2], al[2]);
+        split_tf32(p0[h][1] * p1r[1][1], ah[3], al[3]);
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-          mma_tf32(C[h][cc][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
-          mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
-          mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+          mma_tf32(C[h][0][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+          mma_tf32(C[h][1][nt], al[0], al[1], al[2], al[3], bih[nt][0], bih[nt][1]);
+          mma_tf32(C[h][0][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+          mma_tf32(C[h][1][nt], ah[0], ah[1], ah[2], ah[3], bil[nt][0], bil[nt][1]);
+          mma_tf32(C[h][0][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+          mma_tf32(C[h][1][nt], ah[0], ah[1], ah[2], ah[3], bih[nt][0], bih[nt][1]);
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          unsigned ah[4], al[4];
+          split_tf32(p0[h][0] * (cc ? p1i[0][0] : p1r[0][0]), ah[0], al[0]);
+          split_tf32(p0[h][0] * (cc ? p1i[1][0] : p1r[1][0]), ah[1], al[1]);
+          split_tf32(p0[h][1] * (cc ? p1i[0][1] : p1r[0][1]), ah[2], al[2]);
+          split_tf32(p0[h][1] * (cc ? p1i[1][1] : p1r[1][1]), ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {
+            mma_tf32(C[h][cc][nt], al[0], al[1], al[2], al[3], bh[nt][0], bh[nt][1]);
+            mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bl[nt][0], bl[nt][1]);
+            mma_tf32(C[h][cc][nt], ah[0], ah[1], ah[2], ah[3], bh[nt][0], bh[nt][1]);
+          }
         }
       }
     }
