@@ -502,38 +502,49 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
   const typename Cplx<TS>::type *const ft = nullptr;
   NFFTCU_MMA_PROLOGUE(false, false)
 
-  double A[8][2][4];   // [group][re/im][slot]: grid value of pencil (group, nr) at the cell of slot 4*s+kq
-  int zwin = -1000;    // window base (even); the window holds cells [zwin, zwin+16), cell z in slot z mod 16
+  // Contraction order: the pencils first, V[z, node] = sum_p G[p, z] w[p, node] with the row weights
+  // w = psi0[l0] psi1[l1] as the B operand (16 products per lane and batch), then f_node = sum_z psi2[z, node] V[z, node]
+  // in 8 FMAs per lane.  (The other order -- z first, then 32 weighted row sums per lane -- costs three times the
+  // non-tensor FP64 instructions, and those are what the FP64 pipe has no room for.)  The warp owns the 64 pencils
+  // p = 0..63 of its four footprint rows, l0 = 4 warp + (p >> 4), l1 = p & 15.  DMMA m8n8k4: rows = 8 window cells,
+  // k = 4 pencils, columns = 8 nodes; k-step s covers pencils 4s .. 4s+3.
+  // A[s][mt][re/im]: grid value of pencil 4s+kq at the window cell in slot 8*mt+nr (cell z sits in slot z mod 16)
+  double A[16][2][2];
+  int zwin = -1000;    // window base (even); the window holds cells [zwin, zwin+16)
+  const unsigned *const poff = S.rowoff + 4 * warp * kF + kq;   // pencil 4s+kq of this warp: poff[4 * s]
 
   auto fill_all = [&](int zlo) {
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
-      int z = zlo + ((4 * s + kq - zlo) & 15);
+    for (int mt = 0; mt < 2; mt++) {
+      int z = zlo + ((8 * mt + nr - zlo) & 15);
       if (z >= n2) z -= n2;
 #pragma unroll
-      for (int g = 0; g < 8; g++) {
-        const typename Cplx<TS>::type v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];
-        A[g][0][s] = (double) v.x;
-        A[g][1][s] = (double) v.y;
+      for (int s = 0; s < 16; s++) {
+        const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+        A[s][mt][0] = (double) v.x;
+        A[s][mt][1] = (double) v.y;
       }
     }
   };
-  // pair (zp, zp+1), zp even: cell zp+(kq&1) belongs to the lanes with (kq>>1) == (zp>>1)&1, slot (zp>>2)&3
+  // pair (zp, zp+1), zp even: cell zp + (nr & 1) belongs to the lanes with (nr >> 1) == (zp & 7) >> 1, m-tile (zp >> 3) & 1
   auto load_pair = [&](int zp) {
-    if ((kq >> 1) == ((zp >> 1) & 1)) {
-      int z = zp + (kq & 1);
+    if ((nr >> 1) == ((zp & 7) >> 1)) {
+      int z = zp + (nr & 1);
       if (z >= n2) z -= n2;
-      switch ((zp >> 2) & 3) {
-#define NFFTCU_LOADPAIR(SL)                                                                     \
-        case SL:                                                                                \
-          _Pragma("unroll") for (int g = 0; g < 8; g++) {                                       \
-            const typename Cplx<TS>::type v = G[rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + z];     \
-            A[g][0][SL] = (double) v.x;                                                         \
-            A[g][1][SL] = (double) v.y;                                                         \
-          }                                                                                     \
-          break;
-        NFFTCU_LOADPAIR(0) NFFTCU_LOADPAIR(1) NFFTCU_LOADPAIR(2) NFFTCU_LOADPAIR(3)
-#undef NFFTCU_LOADPAIR
+      if (((zp >> 3) & 1) == 0) {
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+          const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+          A[s][0][0] = (double) v.x;
+          A[s][0][1] = (double) v.y;
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+          const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+          A[s][1][0] = (double) v.x;
+          A[s][1][1] = (double) v.y;
+        }
       }
     }
   };
@@ -562,39 +573,39 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
     mbar_wait(&S.full[st], (j / kStages) & 1);
     DBG_T(c1);
 
-    // ---- T = G * psi2, weighted row sums
-    double bf[4];
+    // ---- row weights of node nr: w[s] = psi0[l0 = 4 warp + (s >> 2)] psi1[l1 = 4 (s & 3) + kq]
+    double q0[4], q1[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) bf[s] = S.ops[st][2][4 * s + kq][nr];
-    const double2 p1a = *reinterpret_cast<const double2 *>(&S.ops[st][1][nr][2 * kq]);
-    const double2 p1b = *reinterpret_cast<const double2 *>(&S.ops[st][1][8 + nr][2 * kq]);
-    double accr0 = 0.0, accr1 = 0.0, acci0 = 0.0, acci1 = 0.0;
-#pragma unroll
-    for (int h = 0; h < 4; h++) {   // footprint row l0 = 4*warp + h: groups 2h (l1 < 8) and 2h+1
-      double c[2][2][2];
-#pragma unroll
-      for (int gg = 0; gg < 2; gg++)
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) c[gg][cc][0] = c[gg][cc][1] = 0.0;
-#pragma unroll
-      for (int s = 0; s < 4; s++)
-#pragma unroll
-        for (int gg = 0; gg < 2; gg++)
-#pragma unroll
-          for (int cc = 0; cc < 2; cc++) dmma(c[gg][cc][0], c[gg][cc][1], A[2 * h + gg][cc][s], bf[s]);
-      const double2 p0 = *reinterpret_cast<const double2 *>(&S.ops[st][0][4 * warp + h][2 * kq]);
-      const double wa0 = p0.x * p1a.x, wa1 = p0.y * p1a.y, wb0 = p0.x * p1b.x, wb1 = p0.y * p1b.y;
-      accr0 = fma(wa0, c[0][0][0], accr0); accr1 = fma(wa1, c[0][0][1], accr1);
-      acci0 = fma(wa0, c[0][1][0], acci0); acci1 = fma(wa1, c[0][1][1], acci1);
-      accr0 = fma(wb0, c[1][0][0], accr0); accr1 = fma(wb1, c[1][0][1], accr1);
-      acci0 = fma(wb0, c[1][1][0], acci0); acci1 = fma(wb1, c[1][1][1], acci1);
+    for (int i = 0; i < 4; i++) {
+      q0[i] = S.ops[st][0][4 * warp + i][nr];
+      q1[i] = S.ops[st][1][4 * i + kq][nr];
     }
+    const double2 p2a = *reinterpret_cast<const double2 *>(&S.ops[st][2][nr][2 * kq]);       // psi2, slot nr, nodes 2kq, 2kq+1
+    const double2 p2b = *reinterpret_cast<const double2 *>(&S.ops[st][2][8 + nr][2 * kq]);   // slot 8 + nr
+    double c[2][2][2];   // [m-tile][re/im][col]: V[slot 8 mt + nr][node 2 kq + col]
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) c[mt][cc][0] = c[mt][cc][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const double w = q0[s >> 2] * q1[s & 3];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) dmma(c[mt][cc][0], c[mt][cc][1], A[s][mt][cc], w);
+    }
+    double accr0 = p2a.x * c[0][0][0], accr1 = p2a.y * c[0][0][1];
+    double acci0 = p2a.x * c[0][1][0], acci1 = p2a.y * c[0][1][1];
+    accr0 = fma(p2b.x, c[1][0][0], accr0); accr1 = fma(p2b.y, c[1][0][1], accr1);
+    acci0 = fma(p2b.x, c[1][1][0], acci0); acci1 = fma(p2b.y, c[1][1][1], acci1);
+    DBG_T(c2);
     // the window registers are free again: slide the window to the next batch now, so that the refill
     // loads fly while this batch is being reduced
-    DBG_T(c2);
     if (j + 1 < nbat && bt_zlo(e_next) != zwin) advance_to(bt_zlo(e_next));
     DBG_T(c3);
-    // per-lane partial sums go to the ring; the producer warp that refills the stage adds them up
+    // per-lane partial sums (over the lane's window cell pair and the warp's pencils) go to the ring; the producer /
+    // feeder warp that refills the stage adds them up
     *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][0]) = make_double2(accr0, acci0);
     *reinterpret_cast<double2 *>(&S.red[st][warp][nr][kq][2]) = make_double2(accr1, acci1);
     __syncwarp();
