@@ -511,7 +511,9 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
   // A[s][mt][re/im]: grid value of pencil 4s+kq at the window cell in slot 8*mt+nr (cell z sits in slot z mod 16)
   double A[16][2][2];
   int zwin = -1000;    // window base (even); the window holds cells [zwin, zwin+16)
-  const unsigned *const poff = S.rowoff + 4 * warp * kF + kq;   // pencil 4s+kq of this warp: poff[4 * s]
+  unsigned poff[16];   // grid offsets of the lane's pencils 4s+kq, kept in registers for the whole sweep
+#pragma unroll
+  for (int s = 0; s < 16; s++) poff[s] = S.rowoff[4 * warp * kF + 4 * s + kq];
 
   auto fill_all = [&](int zlo) {
 #pragma unroll
@@ -520,7 +522,7 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
       if (z >= n2) z -= n2;
 #pragma unroll
       for (int s = 0; s < 16; s++) {
-        const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+        const typename Cplx<TS>::type v = G[poff[s] + z];
         A[s][mt][0] = (double) v.x;
         A[s][mt][1] = (double) v.y;
       }
@@ -534,14 +536,14 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
       if (((zp >> 3) & 1) == 0) {
 #pragma unroll
         for (int s = 0; s < 16; s++) {
-          const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+          const typename Cplx<TS>::type v = G[poff[s] + z];
           A[s][0][0] = (double) v.x;
           A[s][0][1] = (double) v.y;
         }
       } else {
 #pragma unroll
         for (int s = 0; s < 16; s++) {
-          const typename Cplx<TS>::type v = G[poff[4 * s] + z];
+          const typename Cplx<TS>::type v = G[poff[s] + z];
           A[s][1][0] = (double) v.x;
           A[s][1][1] = (double) v.y;
         }
