@@ -696,6 +696,9 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
     sblk = -1;
     snext = 0;
   };
+  unsigned goff[8];   // grid offsets of the lane's pencils (group g, nr), kept in registers for the whole sweep
+#pragma unroll
+  for (int g = 0; g < 8; g++) goff[g] = rowoff_s[(g >> 1) * kF + 8 * (g & 1)];
   // retire pair (zp, zp+1) of the window (zp even, unwrapped): n-tile (zp>>3)&1, lanes kq == (zp&7)>>1
   auto retire_pair = [&](int zp) {
     int zw = zp;
@@ -717,7 +720,7 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         if (FLUSH == 0) {
-          TS *dst = Gd + 2 * ((size_t) rowoff_s[(g >> 1) * kF + 8 * (g & 1)] + zw);
+          TS *dst = Gd + 2 * ((size_t) goff[g] + zw);
           if (nt == 0) {
             red_add(dst, C[g][0][0][0]); red_add(dst + 1, C[g][1][0][0]);
             red_add(dst + 2, C[g][0][0][1]); red_add(dst + 3, C[g][1][0][1]);
