@@ -249,6 +249,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
       "}\n" ::"r"(smem_addr(bar)), "r"(parity), "r"(NFFTCU_MMA_SUSPEND_NS) : "memory");
 }
 
+// non-blocking phase test: issued early, its latency overlaps the code up to the point where the result is needed
+__device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, int parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return done;
+}
+
 // producer-side wait: the producers run up to kStages batches ahead and mostly wait
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, int parity) { mbar_wait(bar, parity); }
 
@@ -569,10 +581,11 @@ interp_mma_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__res
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
+    const uint32_t ready = mbar_test(&S.full[st], (j / kStages) & 1);   // normally complete: the feeders run stages ahead
     if (j + 1 < nbat) e_next = table[j + 1];   // lands during this batch: the next window base
     if (zlo != zwin) advance_to(zlo);
     DBG_T(c0);
-    mbar_wait(&S.full[st], (j / kStages) & 1);
+    if (!ready) mbar_wait(&S.full[st], (j / kStages) & 1);
     DBG_T(c1);
 
     // ---- row weights of node nr: w[s] = psi0[l0 = 4 warp + (s >> 2)] psi1[l1 = 4 (s & 3) + kq]
@@ -740,6 +753,7 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
+    const uint32_t ready = mbar_test(&S.full[st], (j / kStages) & 1);   // result needed behind the window slide
     double fr[2] = {0.0, 0.0}, fi[2] = {0.0, 0.0};   // IMG: samples of nodes kq and 4 + kq (the image holds psi1, not psi1 f)
     if (IMG) {
 #pragma unroll
@@ -759,7 +773,7 @@ spread_mma_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict_
       zwin = zlo;
     }
     // ---- G += (psi0 psi1 f) * psi2
-    mbar_wait(&S.full[st], (j / kStages) & 1);
+    if (!ready) mbar_wait(&S.full[st], (j / kStages) & 1);
     double bf[2][2];   // [n-tile][k-step]
 #pragma unroll
     for (int nt = 0; nt < 2; nt++)
