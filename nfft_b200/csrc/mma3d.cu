@@ -920,9 +920,10 @@ interp_tf32_kernel(const float2 *__restrict__ G, const float *__restrict__ xt,
   for (int j = 0; j < nbat; j++) {
     const int st = j % kStages;
     const int zlo = bt_zlo(e_next);
+    const uint32_t ready = mbar_test(&S.full[st], (j / kStages) & 1);   // result needed behind the window slide
     if (j + 1 < nbat) e_next = table[j + 1];
     if (zlo != zwin) advance_to(zlo);
-    mbar_wait(&S.full[st], (j / kStages) & 1);
+    if (!ready) mbar_wait(&S.full[st], (j / kStages) & 1);
     commit();
     // the refill for the NEXT batch goes out before this batch's MMAs (it lands in pend, not in the window): a slide
     // by 2 or 4 cells gives every lane at most one pair; larger slides are done behind the MMAs as before
