@@ -1,5 +1,6 @@
-// mma3d.cu -- 3-D interpolation (B) and spreading (B^T) in fp64 with the window contraction along z
-// issued as FP64 tensor-core instructions (DMMA, mma.sync.m8n8k4.f64): the fast path for d = 3, m <= 6.
+// mma3d.cu -- 3-D interpolation (B) and spreading (B^T) with the window contraction issued as tensor-core
+// instructions: FP64 DMMA (mma.sync.m8n8k4.f64) for fp64 plans, 3xTF32 mma.sync.m16n8k8 for fp32 plans; the fast
+// path for d = 3, m <= 6.
 //
 // Reference being replaced: nfft_trafo_3d_B / nfft_trafo_3d_compute (kernel/nfft/nfft.c:4687-4914,
 // 4020-4265) and nfft_adjoint_3d_B with its atomic / blockwise compute variants (5126-5384,
@@ -19,31 +20,39 @@
 //   in z), 8 at a time, and a batch only takes nodes with u2 in [zlo, zlo+2], zlo even, so that all its
 //   taps fall in the WINDOW z in [zlo, zlo+16).
 //
-//   interpolation   T[row, node] = sum_z G[row, z] * psi2[z, node]     rows = 256 pencils x (re, im)
-//                   f_node       = sum_row psi0[row, node] psi1[row, node] T[row, node]
-//   spreading       G[row, z]   += sum_node (psi0 psi1 f)[row, node] * psi2[node, z]
+//   interpolation   V[z, node]  = sum_p G[p, z] * (psi0 psi1)[p, node]      p = 256 pencils, re / im separately
+//                   f_node      = sum_z psi2[z, node] V[z, node]
+//   spreading       G[p, z]    += sum_node (psi0 psi1)[p, node] * (psi2 f)[node, z]
 //
-// A CTA of 4 warps owns a tile; warp w owns footprint rows l0 = 4w..4w+3, all 16 l1, i.e. 8 groups of
-// 8 pencils x (re, im) = 16 m-tiles.  The window lives in REGISTERS for the whole sweep of the tile along z:
-// as A fragments for interpolation (64 doubles per lane, refilled two cells at a time from L2, one
-// pair prefetched a batch ahead), as C accumulators for spreading (64 doubles per lane, retired two
-// cells at a time).  Window slots are circular (cell z lives in slot z mod 16), so sliding the window
-// moves no registers.  Per batch a warp issues 64 DMMAs (16 m-tiles x 4 k-steps, resp. 16 m-tiles x 2
-// n-tiles x 2 k-steps) = 16384 FMAs for 8 nodes: lane efficiency (14/16)^3 = 67 % of the useful 5488 per node.
+// (The non-tensor FP64 work of the MMA warps is what the in-order warps have no room for, so both kernels keep it
+// minimal: interpolation contracts the pencils first, with the row weights psi0 psi1 as the B operand -- 16
+// products per lane and batch -- and applies psi2 in 8 FMAs, instead of contracting z first and forming 32
+// weighted row sums per lane; spreading multiplies the samples into the B operand psi2 -- 8 products per lane --
+// instead of the A operand psi0 psi1, whose fragments are then shared by the re / im accumulators.)
+//
+// A CTA of 4 MMA warps owns a tile; warp w owns footprint rows l0 = 4w..4w+3, all 16 l1 = 64 pencils.  The window
+// lives in REGISTERS for the whole sweep of the tile along z: as A fragments for interpolation (64 doubles per lane,
+// refilled two cells at a time from L2 behind the batch's DMMAs), as C accumulators for spreading (64 doubles per
+// lane, retired two cells at a time with RED.ADD).  Window slots are circular (cell z lives in slot z mod 16), so
+// sliding the window moves no registers.  Per batch a warp issues 64 DMMAs = 16384 FMAs for 8 nodes: lane
+// efficiency (14/16)^3 = 67 % of the useful 5488 per node.
 //
 // Batches are formed once per node set (plan time, like the reference's precompute_psi): a table of
-// (first node, count, window base) per batch and the batch range of every work unit.
+// (first node, count, window base) per batch, the batch range of every work unit, and the chunk list (runs of at
+// most 384 batches of one unit: a CTA's load is bounded for clustered node sets).
 //
-// Warp specialisation.  A CTA has two warpgroups.  The PRODUCER warps evaluate the window from the node
-// coordinates (24 bytes per node instead of a 416-byte record): the piecewise polynomials of kbpoly.cu,
-// one Horner chain per (dimension, slot, node) entry -- a warp owns every 4th batch and runs its 12
-// chains per lane interleaved -- written zero-padded and already placed (offset in the footprint,
-// circular slot in z) into a ring of shared operand blocks.  The MMA warps only wait on the ring's
-// mbarriers; setmaxnreg moves the registers the producers do not need to them (200 / 56).
+// Warp specialisation.  A CTA has two warpgroups; setmaxnreg moves registers from the second to the MMA warps
+// (200 / 56).  The second group delivers, per batch, the placed operand block psi0 / psi1 / psi2 -- zero-padded,
+// offset in the footprint, circular slot in z -- into a ring of shared-memory stages guarded by full / empty
+// mbarriers, and for interpolation adds up the partial sums the MMA warps release:
+//   * FEEDER mode (default, when the images fit): the blocks were written once per node set by mma_images_kernel
+//     (3 KB per batch) and one elected lane per batch issues a TMA bulk copy that completes the stage's full barrier;
+//   * PRODUCER mode: the warps evaluate the window from the node coordinates -- the piecewise polynomials of
+//     kbpoly.cu, a warp owns every 4th batch and runs its 12 Horner chains per lane interleaved.
 //
-// Spreading retires cells through shared memory: a warp stages the retired pairs of ITS rows as
-// 128-byte runs (8 cells) and hands complete runs to the TMA unit as bulk reductions
-// (cp.reduce.async.bulk .add.f64), so that L2 sees line-sized reductions instead of scattered RED.64.
+// fp32 plans run the same structure on the TF32 tensor path (mma.sync.m16n8k8, 3xTF32 split; *_tf32_kernel below).
+// Spreading has an optional flush through shared memory and TMA bulk reductions (cp.reduce.async.bulk .add.f64,
+// FLUSH = 1, NFFTCU_OPT_B_FLUSH = 2); plain RED.ADD from the accumulator registers measured faster and is the default.
 #include "common.cuh"
 
 namespace nfftcu {
