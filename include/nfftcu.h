@@ -42,6 +42,8 @@ extern "C" {
 #define NFFTCU_ESTATE (-5)   /* call order violated (e.g. transform before set_nodes) */
 
 #define NFFTCU_MAX_D 8
+#define NFFTCU_MAX_PEERS 8            /* GPUs of one NVSwitch domain that can share an adjoint reduction */
+#define NFFTCU_PEER_HANDLE_BYTES 192  /* opaque per-rank blob of nfftcu_peer_export (three CUDA IPC handles) */
 
 typedef struct nfftcu_ctx_s nfftcu_ctx;
 
@@ -98,10 +100,12 @@ int nfftcu_get_index_x(nfftcu_ctx *ctx, int64_t *index_x_host);
 int nfftcu_trafo(nfftcu_ctx *ctx, const void *f_hat_host, void *f_host);
 int nfftcu_adjoint(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);
 /* The same with an unannounced node refresh, for plans without a psi flag, where the reference re-reads
- * x on every call (nfft.c:4889, 5351): x_host is uploaded and compared with the resident nodes on a side
- * stream while the transform already runs with the resident nodes; only when they differ are the nodes
- * re-sorted and the transform repeated.  *changed (may be NULL) reports whether that happened, i.e.
- * whether index_x has to be fetched again. */
+ * x on every call (nfft.c:4889, 5351): the transform starts at once with the resident nodes while host threads
+ * compute a 64-bit fingerprint of x_host; only when it differs from the fingerprint of the array the resident
+ * nodes were uploaded from are the nodes uploaded, re-sorted and the transform repeated (no PCIe traffic for
+ * unchanged nodes).  NFFT_B200_EXACT_NODE_CHECK=1, or resident nodes that came from nfftcu_set_nodes_dev, select the
+ * exact variant: x_host is uploaded on a side stream and compared word for word on the device.  *changed (may be
+ * NULL) reports whether the nodes were replaced, i.e. whether index_x has to be fetched again. */
 int nfftcu_trafo_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_hat_host, void *f_host, int *changed);
 int nfftcu_adjoint_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_host, void *f_hat_host, int *changed);
 /* nfft_trafo_direct / nfft_adjoint_direct (nfft.c:145-297): exact NDFT */
@@ -129,7 +133,7 @@ void *nfftcu_grid_ptr(nfftcu_ctx *ctx);           /* device pointer, n_total com
 
 /* ---- plumbing ----------------------------------------------------------------------------- */
 int nfftcu_set_option(nfftcu_ctx *ctx, int option, int64_t value);
-int nfftcu_set_stream(nfftcu_ctx *ctx, void *cuda_stream);   /* cudaStream_t; NULL = own stream */
+int nfftcu_set_stream(nfftcu_ctx *ctx, void *cuda_stream);   /* cudaStream_t; NULL = own (non-blocking) stream; the legacy default stream is cudaStreamLegacy = (void*) 1 */
 void *nfftcu_get_stream(nfftcu_ctx *ctx);
 int nfftcu_sync(nfftcu_ctx *ctx);
 /* milliseconds of the last transform's D, F, B(^T) stages -> plan member MEASURE_TIME_t
@@ -141,13 +145,72 @@ int nfftcu_b_kernel_time(nfftcu_ctx *ctx, float *ms);
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 int64_t nfftcu_launch_count(nfftcu_ctx *ctx);
 
+/* Roofline denominators measured on `device` right now (peaks.cu): FP64 tensor-core rate (mma.sync m8n8k4 f64, the
+ * pipe the fp64 B / B^T kernels are bound by), legacy mma.sync m16n8k8 TF32 rate (fp32 plans), and a 1 GiB device copy
+ * (read + write bytes).  Any pointer may be NULL.  bench.py calls this in-process and records the values it used. */
+int nfftcu_measure_peaks(int device, double *fp64_tensor_tflops, double *tf32_mma_sync_tflops, double *copy_gbs);
+
 /* device / pinned memory for C callers that do not link the CUDA runtime themselves */
 int nfftcu_malloc_device(void **ptr, size_t bytes, int device);
 int nfftcu_free_device(void *ptr);
 int nfftcu_malloc_pinned(void **ptr, size_t bytes);
 int nfftcu_free_pinned(void *ptr);
+/* backing store of nfft_malloc / nfft_free (kernel/util/malloc.c): buffers of NFFT_B200_PINNED_MALLOC_MIN bytes
+ * (default 256 KiB; 0 = never) or more are page-locked and portable across devices, smaller ones (and every request
+ * when no CUDA device exists) come from the C heap; nfftcu_host_free accepts both kinds.  Returns NULL when out of memory. */
+void *nfftcu_host_alloc(size_t bytes);
+void nfftcu_host_free(void *ptr);
+/* device and page-locked buffers freed by finalized plans are cached per process (mempool.cu, NFFT_B200_POOL_MB);
+ * this returns the cache to the driver, for processes that share the GPU with other CUDA users */
+void nfftcu_pool_trim(void);
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int nfftcu_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+
+/* ---- multi-GPU, node-sharded (north_star configs[3]) ------------------------------------------------
+ * The reference is a single-node CPU code; these entry points are what a multi-GPU build of nfft_trafo /
+ * nfft_adjoint sits on.  Nodes are sorted once by the reference key (nfft.c:75-109) and cut into equal-count
+ * slabs of the sorted order, one per GPU, so that every GPU works on a compact slab of the grid.
+ *
+ * (1) nfftcu_get_sorted_slab: positions [begin, end) of the reference-sorted node list of a plan -- the nodes
+ *     (x_out_dev, (end-begin)*d reals) and their original indices (perm_out_dev) -- copied into device buffers of the
+ *     plan's device.  A process-per-GPU driver calls it on a plan holding the whole node set to obtain its slab.
+ * (2) fused D^T + cross-GPU reduction over NVLink peer memory (peer.cu): nfftcu_peer_export writes an opaque blob of
+ *     NFFTCU_PEER_HANDLE_BYTES describing this rank's grid / exchange buffer / flags; the caller gathers the blobs of
+ *     all ranks (rank order) and passes them to nfftcu_peer_attach.  nfftcu_adjoint_dev_peer then computes
+ *     f_hat = sum_r D^T F^H B_r^T f_r with the sum taken INSIDE the D^T kernel through peer loads; every rank
+ *     receives the complete f_hat.  All ranks must call it the same number of times (device-side flag barriers).
+ * (3) nfftcu_group_*: ONE process driving several GPUs behind the host-pointer interface of nfft_trafo /
+ *     nfft_adjoint (what libnfft3_b200.so uses when NFFT_B200_DEVICES lists more than one device): x is sorted on the
+ *     first device and distributed as slabs; trafo replicates f_hat, runs D+F redundantly and B per slab; adjoint
+ *     runs B^T+F per slab and the fused D^T+reduce, every device delivering its slice of f_hat.  The permutation
+ *     between caller order and slab order of f is an all-to-all over peer memory, so that every device moves only
+ *     M/P samples over its own host link. */
+int nfftcu_get_sorted_slab(nfftcu_ctx *ctx, int64_t begin, int64_t end, void *x_out_dev, uint32_t *perm_out_dev);
+int nfftcu_peer_export(nfftcu_ctx *ctx, void *handles);
+int nfftcu_peer_attach(nfftcu_ctx *ctx, int rank, int world, const void *all_handles);
+int nfftcu_peer_detach(nfftcu_ctx *ctx);
+int nfftcu_adjoint_dev_peer(nfftcu_ctx *ctx, const void *f_dev, void *f_hat_dev);
+int nfftcu_peer_reduce_only(nfftcu_ctx *ctx, void *f_hat_dev);   /* the fused D^T + reduce alone (profiling) */
+int nfftcu_peer_error(nfftcu_ctx *ctx);   /* 1: a flag barrier timed out waiting for a peer, results are invalid */
+
+typedef struct nfftcu_group_s nfftcu_group;
+int nfftcu_group_create(nfftcu_group **out, int precision, int d, const int64_t *N, const int64_t *n, int64_t m,
+                        int64_t M, unsigned flags, const int *devices, int ndevices);
+int nfftcu_group_destroy(nfftcu_group *g);
+int nfftcu_group_set_nodes(nfftcu_group *g, const void *x_host);          /* returns after the slabs are resident */
+int64_t nfftcu_group_nodes_version(nfftcu_group *g);
+int nfftcu_group_get_index_x(nfftcu_group *g, int64_t *index_x_host);    /* the reference's index_x, 2*M entries */
+int nfftcu_group_trafo(nfftcu_group *g, const void *f_hat_host, void *f_host);
+int nfftcu_group_adjoint(nfftcu_group *g, const void *f_host, void *f_hat_host);
+/* the same with the unannounced node refresh of nfftcu_trafo_refresh (fingerprint of x_host) */
+int nfftcu_group_trafo_refresh(nfftcu_group *g, const void *x_host, const void *f_hat_host, void *f_host, int *changed);
+int nfftcu_group_adjoint_refresh(nfftcu_group *g, const void *x_host, const void *f_host, void *f_hat_host, int *changed);
+int nfftcu_group_direct(nfftcu_group *g, int adjoint, const void *in_host, void *out_host);   /* exact NDFT, device 0 */
+int nfftcu_group_size(nfftcu_group *g);
+nfftcu_ctx *nfftcu_group_ctx(nfftcu_group *g, int rank);                 /* the per-device plan (options, timing) */
+/* milliseconds of the last group transform: [0] host->device copies, [1] device compute incl. the peer exchange,
+ * [2] device->host copies (wall clock of the slowest device each) */
+int nfftcu_group_times(nfftcu_group *g, float ms[3]);
 
 /* ---- device-resident inverse-NFFT iterations --------------------------------------------------------------
  * Replaces the host loops of kernel/solver/solver.c (solver_before_loop_complex 81-125, solver_loop_one_step_complex

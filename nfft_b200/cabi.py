@@ -16,6 +16,7 @@ _LIB = None
 _LIBPATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnfftcu.so")
 
 DOUBLE, FLOAT = 0, 1
+PEER_HANDLE_BYTES = 192
 OPT_TIMING, OPT_PSI_TABLE, OPT_B_KERNEL, OPT_NODE_ORDER, OPT_B_FLUSH, OPT_FFT_PRUNE, OPT_FFT_KERNEL, OPT_WINDOW_IMAGES = 1, 2, 3, 4, 5, 6, 7, 8
 
 # every symbol include/nfftcu.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -31,6 +32,13 @@ SYMBOLS = (
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
     "nfftcu_solver_create", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
     "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
+    "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim",
+    "nfftcu_get_sorted_slab", "nfftcu_peer_export", "nfftcu_peer_attach", "nfftcu_peer_detach",
+    "nfftcu_adjoint_dev_peer", "nfftcu_peer_error", "nfftcu_peer_reduce_only",
+    "nfftcu_group_create", "nfftcu_group_destroy", "nfftcu_group_set_nodes", "nfftcu_group_nodes_version",
+    "nfftcu_group_get_index_x", "nfftcu_group_trafo", "nfftcu_group_adjoint", "nfftcu_group_trafo_refresh",
+    "nfftcu_group_adjoint_refresh", "nfftcu_group_direct", "nfftcu_group_size", "nfftcu_group_ctx",
+    "nfftcu_group_times",
 )
 
 
@@ -79,6 +87,35 @@ def lib() -> C.CDLL:
         L.nfftcu_free_pinned.argtypes = [vp]
         L.nfftcu_memcpy_h2d.argtypes = [vp, vp, C.c_size_t]
         L.nfftcu_memcpy_d2h.argtypes = [vp, vp, C.c_size_t]
+        L.nfftcu_measure_peaks.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.nfftcu_host_alloc.argtypes = [C.c_size_t]
+        L.nfftcu_host_alloc.restype = vp
+        L.nfftcu_host_free.argtypes = [vp]
+        L.nfftcu_host_free.restype = None
+        L.nfftcu_pool_trim.restype = None
+        L.nfftcu_get_sorted_slab.argtypes = [vp, i64, i64, vp, vp]
+        L.nfftcu_peer_export.argtypes = [vp, vp]
+        L.nfftcu_peer_attach.argtypes = [vp, ci, ci, vp]
+        L.nfftcu_peer_detach.argtypes = [vp]
+        L.nfftcu_adjoint_dev_peer.argtypes = [vp, vp, vp]
+        L.nfftcu_peer_error.argtypes = [vp]
+        L.nfftcu_peer_reduce_only.argtypes = [vp, vp]
+        L.nfftcu_group_create.argtypes = [C.POINTER(vp), ci, ci, C.POINTER(i64), C.POINTER(i64), i64, i64, C.c_uint,
+                                          C.POINTER(ci), ci]
+        L.nfftcu_group_destroy.argtypes = [vp]
+        L.nfftcu_group_set_nodes.argtypes = [vp, vp]
+        L.nfftcu_group_nodes_version.argtypes = [vp]
+        L.nfftcu_group_nodes_version.restype = i64
+        L.nfftcu_group_get_index_x.argtypes = [vp, vp]
+        for name in ("nfftcu_group_trafo", "nfftcu_group_adjoint"):
+            getattr(L, name).argtypes = [vp, vp, vp]
+        for name in ("nfftcu_group_trafo_refresh", "nfftcu_group_adjoint_refresh"):
+            getattr(L, name).argtypes = [vp, vp, vp, vp, C.POINTER(ci)]
+        L.nfftcu_group_direct.argtypes = [vp, ci, vp, vp]
+        L.nfftcu_group_size.argtypes = [vp]
+        L.nfftcu_group_ctx.argtypes = [vp, ci]
+        L.nfftcu_group_ctx.restype = vp
+        L.nfftcu_group_times.argtypes = [vp, C.POINTER(C.c_float)]
         _LIB = L
     return _LIB
 
@@ -97,6 +134,13 @@ def _ptr(a) -> C.c_void_p:
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(int(a))
+
+
+def measure_peaks(device: int = 0):
+    """(fp64 tensor TFLOP/s, mma.sync TF32 TFLOP/s, device copy GB/s) measured now on `device` (peaks.cu)."""
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _ck(lib().nfftcu_measure_peaks(device, C.byref(a), C.byref(b), C.byref(c)))
+    return float(a.value), float(b.value), float(c.value)
 
 
 class Engine:
@@ -134,7 +178,13 @@ class Engine:
         _ck(self.L.nfftcu_set_option(self.ctx, opt, value))
 
     def set_stream(self, cuda_stream: int):
-        _ck(self.L.nfftcu_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+        """Run on the given cudaStream_t.  torch reports its default stream as handle 0, which in the C ABI means
+        "own stream"; the legacy default stream is therefore passed as cudaStreamLegacy (0x1).  ``None`` restores
+        the engine's own (non-blocking) stream."""
+        if cuda_stream is None:
+            _ck(self.L.nfftcu_set_stream(self.ctx, C.c_void_p(0)))
+        else:
+            _ck(self.L.nfftcu_set_stream(self.ctx, C.c_void_p(int(cuda_stream) or 1)))
 
     def sync(self):
         _ck(self.L.nfftcu_sync(self.ctx))
@@ -192,6 +242,30 @@ class Engine:
     def trafo_dev(self, f_hat_dev, f_dev): _ck(self.L.nfftcu_trafo_dev(self.ctx, _ptr(f_hat_dev), _ptr(f_dev)))
     def adjoint_dev(self, f_dev, f_hat_dev): _ck(self.L.nfftcu_adjoint_dev(self.ctx, _ptr(f_dev), _ptr(f_hat_dev)))
 
+    # ---- multi-GPU building blocks (include/nfftcu.h "multi-GPU, node-sharded") ----
+    def sorted_slab(self, begin: int, end: int, x_out_dev, perm_out_dev):
+        """reference-sorted nodes [begin, end) and their original indices -> device buffers (async on the stream)"""
+        _ck(self.L.nfftcu_get_sorted_slab(self.ctx, int(begin), int(end), _ptr(x_out_dev), _ptr(perm_out_dev)))
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _ck(self.L.nfftcu_peer_export(self.ctx, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, all_handles: bytes):
+        assert len(all_handles) == world * PEER_HANDLE_BYTES
+        _ck(self.L.nfftcu_peer_attach(self.ctx, rank, world, C.c_char_p(all_handles)))
+
+    def adjoint_dev_peer(self, f_dev, f_hat_dev):
+        """adjoint with the cross-GPU reduction fused into D^T over peer memory (peer.cu); all ranks call it"""
+        _ck(self.L.nfftcu_adjoint_dev_peer(self.ctx, _ptr(f_dev), _ptr(f_hat_dev)))
+
+    def peer_reduce_only(self, f_hat_dev):
+        _ck(self.L.nfftcu_peer_reduce_only(self.ctx, _ptr(f_hat_dev)))
+
+    def peer_error(self) -> int:
+        return int(self.L.nfftcu_peer_error(self.ctx))
+
     # ---- single stages ----
     def stage_D(self, f_hat_dev): _ck(self.L.nfftcu_stage_D(self.ctx, _ptr(f_hat_dev)))
     def stage_F(self, sign: int): _ck(self.L.nfftcu_stage_F(self.ctx, sign))
@@ -213,6 +287,74 @@ class Engine:
         assert g.size == self.n_total
         self.sync()
         _ck(self.L.nfftcu_memcpy_h2d(C.c_void_p(self.grid_ptr()), _ptr(g), g.nbytes))
+
+
+class Group:
+    """ONE process driving several GPUs (``nfftcu_group_*``): node-sharded trafo / adjoint on HOST arrays."""
+
+    def __init__(self, N: Sequence[int], n: Sequence[int], m: int, M: int, devices: Sequence[int], *,
+                 precision: str = "double", flags: int = 0):
+        self.L = lib()
+        self.precision = precision
+        self.real = np.float64 if precision == "double" else np.float32
+        self.cplx = np.complex128 if precision == "double" else np.complex64
+        self.d, self.M, self.N_total = len(N), int(M), int(np.prod(N))
+        self.g = C.c_void_p(0)
+        Na = (C.c_int64 * self.d)(*[int(v) for v in N])
+        na = (C.c_int64 * self.d)(*[int(v) for v in n])
+        dv = (C.c_int * len(devices))(*[int(v) for v in devices])
+        _ck(self.L.nfftcu_group_create(C.byref(self.g), DOUBLE if precision == "double" else FLOAT, self.d, Na, na,
+                                       int(m), self.M, flags, dv, len(devices)))
+
+    def close(self):
+        if self.g:
+            _ck(self.L.nfftcu_group_destroy(self.g))
+            self.g = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_nodes(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=self.real)
+        assert x.size == self.M * self.d
+        _ck(self.L.nfftcu_group_set_nodes(self.g, _ptr(x)))
+
+    def index_x(self) -> np.ndarray:
+        out = np.empty((max(self.M, 1), 2), dtype=np.int64)
+        _ck(self.L.nfftcu_group_get_index_x(self.g, _ptr(out)))
+        return out[: self.M]
+
+    def trafo(self, f_hat, out=None):
+        f_hat = np.ascontiguousarray(f_hat, dtype=self.cplx)
+        out = np.empty(max(self.M, 1), dtype=self.cplx) if out is None else out
+        _ck(self.L.nfftcu_group_trafo(self.g, _ptr(f_hat), _ptr(out)))
+        return out[: self.M]
+
+    def adjoint(self, f, out=None):
+        f = np.ascontiguousarray(f, dtype=self.cplx)
+        out = np.empty(self.N_total, dtype=self.cplx) if out is None else out
+        _ck(self.L.nfftcu_group_adjoint(self.g, _ptr(f), _ptr(out)))
+        return out
+
+    def times(self):
+        ms = (C.c_float * 3)()
+        _ck(self.L.nfftcu_group_times(self.g, ms))
+        return [float(v) for v in ms]
+
+
+def host_alloc(nbytes: int) -> int:
+    """page-locked host memory from the library's nfft_malloc backing store (address)"""
+    p = lib().nfftcu_host_alloc(nbytes)
+    if not p:
+        raise MemoryError(nbytes)
+    return int(p)
+
+
+def host_free(addr: int):
+    lib().nfftcu_host_free(C.c_void_p(addr))
 
 
 class DeviceBuffer:

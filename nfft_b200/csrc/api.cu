@@ -9,7 +9,10 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <thread>
 
 namespace nfftcu {
 
@@ -36,6 +39,77 @@ long double bessel_i0_series(long double x) {
     if (term < sum * 0x1p-70L) break;
   }
   return sum;
+}
+
+// ---- 64-bit fingerprint of a host array (node change detection without moving the nodes) ----------------------
+// Plans without a node-bound psi flag get no notice when the caller rewrites x; the reference simply re-reads x on
+// every transform (nfft.c:4889, 5351).  Re-uploading x to compare it on the device costs 24 B/node of PCIe and host
+// memory traffic per transform; instead the host array is hashed by a few host threads WHILE the device already runs
+// the transform with the resident nodes, and only a mismatch triggers upload + re-sort + a repeated transform.
+// Chunks of 1 MiB are hashed independently (four multiply-rotate lanes over 8-byte words, xxhash-style constants)
+// and combined in order, so the result does not depend on the thread count.
+inline uint64_t rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+inline uint64_t mix64(uint64_t h) {
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+  return h;
+}
+uint64_t hash_chunk(const unsigned char *p, size_t bytes, uint64_t seed) {
+  const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL;
+  uint64_t a0 = seed + P1, a1 = seed ^ P2, a2 = seed * P1 + 1, a3 = seed - P2;
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    a0 = rotl64(a0 + w[0] * P2, 31) * P1;
+    a1 = rotl64(a1 + w[1] * P2, 31) * P1;
+    a2 = rotl64(a2 + w[2] * P2, 31) * P1;
+    a3 = rotl64(a3 + w[3] * P2, 31) * P1;
+  }
+  uint64_t tail = 0;
+  for (int sh = 0; i < bytes; i++, sh += 8) {
+    if (sh == 64) { a0 = rotl64(a0 + tail * P2, 31) * P1; tail = 0; sh = 0; }
+    tail |= (uint64_t) p[i] << sh;
+  }
+  a1 = rotl64(a1 + tail * P2, 31) * P1;
+  return mix64(rotl64(a0, 1) + rotl64(a1, 7) + rotl64(a2, 12) + rotl64(a3, 18) + (uint64_t) bytes);
+}
+}  // namespace
+uint64_t fingerprint(const void *data, size_t bytes) {
+  const size_t kChunk = (size_t) 1 << 20;
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  const unsigned char *p = (const unsigned char *) data;
+  if (nchunks <= 4) {
+    uint64_t h = 0x1234567ULL;
+    for (size_t k = 0; k < nchunks; k++)
+      h = mix64(h ^ hash_chunk(p + k * kChunk, k + 1 < nchunks ? kChunk : bytes - k * kChunk, k));
+    return h ^ bytes;
+  }
+  static const unsigned max_threads = [] {
+    const char *e = getenv("NFFT_B200_HASH_THREADS");
+    unsigned t = e ? (unsigned) atoi(e) : std::thread::hardware_concurrency();
+    if (const char *o = getenv("OMP_NUM_THREADS")) { const unsigned ot = (unsigned) atoi(o); if (!e && ot > 0 && ot < t) t = ot; }
+    return t < 1 ? 1u : (t > 32 ? 32u : t);
+  }();
+  unsigned nt = max_threads;
+  if (nt > nchunks / 2) nt = (unsigned) (nchunks / 2);
+  if (nt < 1) nt = 1;
+  std::vector<uint64_t> part(nchunks);
+  auto work = [&](unsigned tid) {
+    for (size_t k = tid; k < nchunks; k += nt)
+      part[k] = hash_chunk(p + k * kChunk, k + 1 < nchunks ? kChunk : bytes - k * kChunk, k);
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &t : th) t.join();
+  uint64_t h = 0x1234567ULL;
+  for (size_t k = 0; k < nchunks; k++) h = mix64(h ^ part[k]);
+  return h ^ bytes;
+}
+namespace {
+bool exact_node_check() {
+  static const bool v = [] { const char *e = getenv("NFFT_B200_EXACT_NODE_CHECK"); return e && atoi(e) != 0; }();
+  return v;
 }
 
 int check_ctx(const nfftcu_ctx *c) {
@@ -117,11 +191,20 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
   return NFFTCU_OK;
 }
 
+}  // namespace
 int nodes_ready(nfftcu_ctx *c) {
+  if (c->nodes_only) {   // sorter of a multi-GPU group: the reference order is all that is needed
+    NFFTCU_TRY(sort_nodes(c));
+    c->ref_sorted = true;
+    c->have_nodes = true;
+    c->nodes_version++;
+    return NFFTCU_OK;
+  }
   c->ref_sorted = false;
   c->tile_ready = false;
   c->mma_ready = false;
   c->tile2_ready = false;
+  c->psi_table_valid = false;   // the generic kernels use the table only when it was rebuilt for these nodes
   if (!c->direct_only) {
     // B / B^T kernel family: DMMA (mma3d.cu) > register pencils (pencil3d.cu) > generic warp-per-node
     const bool use_mma = mma3d_supported(c) && (c->opt_b_kernel == 0 || c->opt_b_kernel == 3);
@@ -142,6 +225,7 @@ int nodes_ready(nfftcu_ctx *c) {
   return NFFTCU_OK;
 }
 
+namespace {
 __global__ void differs_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                                long long words, int *flag) {
   const long long stride = (long long) gridDim.x * blockDim.x;
@@ -152,14 +236,16 @@ __global__ void differs_kernel(const uint32_t *__restrict__ a, const uint32_t *_
 }
 
 // upload x into the staging buffer; returns changed=false when it equals the resident nodes
-int stage_and_compare(nfftcu_ctx *c, const void *x, cudaMemcpyKind kind, bool *changed) {
+int stage_and_compare(nfftcu_ctx *c, const void *x, cudaMemcpyKind kind, bool *changed, uint64_t *fp_out) {
   const size_t bytes = real_size(c) * (size_t) c->M * c->d;
   *changed = true;
+  if (fp_out && bytes == 0) *fp_out = fingerprint(x, 0);
   if (bytes == 0) { *changed = !c->have_nodes; return NFFTCU_OK; }
   if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, bytes));
   if (!c->x_dev) NFFTCU_CUDA(pool_malloc(&c->x_dev, bytes));
   if (!c->diff_flag) NFFTCU_CUDA(pool_malloc((void **) &c->diff_flag, sizeof(int)));
   NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x, bytes, kind, c->stream));
+  if (fp_out) *fp_out = fingerprint(x, bytes);   // host threads, while the copy is in flight
   if (c->have_nodes) {
     int h = 0;
     NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->stream));
@@ -198,6 +284,13 @@ int nfftcu_device_count(void) {
 
 int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n,
                   int64_t m, int64_t M, unsigned flags, int device) {
+  return create_ctx(out, precision, d, N, n, m, M, flags, device, false);
+}
+
+}  // extern "C"
+
+int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n,
+                       int64_t m, int64_t M, unsigned flags, int device, bool nodes_only) {
   if (!out || !N || !n || d < 1 || d > NFFTCU_MAX_D || m < 0 || M < 0 ||
       (precision != NFFTCU_DOUBLE && precision != NFFTCU_FLOAT)) {
     set_error("nfftcu_create: invalid argument (d=%d, m=%lld, M=%lld, precision=%d)", d,
@@ -216,18 +309,20 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
   }
   NFFTCU_CUDA(cudaSetDevice(device));
   nfftcu_ctx *c = new nfftcu_ctx_s();
+  // every failure below releases what the context already holds (nfftcu_destroy copes with a half-built context)
+  const int status = [&]() -> int {
   c->prec = precision;
   c->d = d;
   c->device = device;
   c->m = m;
   c->M = M;
   c->flags = flags;
+  c->nodes_only = nodes_only;
   c->N_total = 1;
   c->n_total = 1;
   for (int t = 0; t < d; t++) {
     if (N[t] < 1 || n[t] < 1) {
       set_error("nfftcu_create: N[%d]=%lld, n[%d]=%lld", t, (long long) N[t], t, (long long) n[t]);
-      delete c;
       return NFFTCU_EINVAL;
     }
     c->N[t] = N[t];
@@ -275,23 +370,30 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
       NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], tmp.data(), bytes, cudaMemcpyHostToDevice));
     }
   }
-  if (!c->direct_only) {
+  if (!c->direct_only && !nodes_only) {
     NFFTCU_CUDA(pool_malloc(&c->grid, cbytes(c, c->n_total)));
-    int r = fft_plan_axes(c);
-    if (r == NFFTCU_OK && (tile3d_supported(c) || tile2d_supported(c))) r = build_kb_poly(c);
-    if (r != NFFTCU_OK) {
-      nfftcu_destroy(c);
-      return r;
-    }
+    NFFTCU_TRY(fft_plan_axes(c));
+    if (tile3d_supported(c) || tile2d_supported(c)) NFFTCU_TRY(build_kb_poly(c));
+  }
+  return NFFTCU_OK;
+  }();
+  if (status != NFFTCU_OK) {
+    const std::string msg = g_err;   // nfftcu_destroy must not clobber the reason
+    nfftcu_destroy(c);
+    set_error("%s", msg.c_str());
+    return status;
   }
   *out = c;
   return NFFTCU_OK;
 }
 
+extern "C" {
+
 int nfftcu_destroy(nfftcu_ctx *c) {
   if (!c) return NFFTCU_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  peer_detach(c);
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) pool_free(c->c_dev[t]);
@@ -345,8 +447,26 @@ int nfftcu_set_nodes(nfftcu_ctx *c, const void *x_host) {
     set_error("nfftcu_set_nodes: x is NULL");
     return NFFTCU_EINVAL;
   }
+  const size_t xbytes = real_size(c) * (size_t) c->M * c->d;
+  uint64_t fp = 0;
+  bool have_fp = false;
+  if (c->have_nodes && c->x_fp_valid && !exact_node_check()) {
+    fp = fingerprint(x_host, xbytes);
+    have_fp = true;
+    if (fp == c->x_fp) return NFFTCU_OK;   // same nodes as the resident ones: nothing to upload, nothing to sort
+  }
   bool changed = true;
-  NFFTCU_TRY(stage_and_compare(c, x_host, cudaMemcpyHostToDevice, &changed));
+  if (have_fp) {   // known to differ: upload straight into the resident buffer's partner and swap
+    if (xbytes) {
+      if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, xbytes));
+      NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->stream));
+      void *t = c->x_dev; c->x_dev = c->x_stage; c->x_stage = t;
+    }
+  } else {
+    NFFTCU_TRY(stage_and_compare(c, x_host, cudaMemcpyHostToDevice, &changed, &fp));
+  }
+  c->x_fp = fp;
+  c->x_fp_valid = true;
   if (changed) NFFTCU_TRY(nodes_ready(c));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
   return NFFTCU_OK;
@@ -356,7 +476,8 @@ int nfftcu_set_nodes_dev(nfftcu_ctx *c, const void *x_dev) {
   NFFTCU_TRY(check_ctx(c));
   NFFTCU_TRY(bind_device(c));
   bool changed = true;
-  NFFTCU_TRY(stage_and_compare(c, x_dev, cudaMemcpyDeviceToDevice, &changed));
+  NFFTCU_TRY(stage_and_compare(c, x_dev, cudaMemcpyDefault, &changed, nullptr));   // x_dev may live on a peer device
+  c->x_fp_valid = false;   // no host array to fingerprint: transforms with a node refresh compare on the device
   if (changed) NFFTCU_TRY(nodes_ready(c));
   return NFFTCU_OK;
 }
@@ -388,6 +509,32 @@ int nfftcu_get_index_x(nfftcu_ctx *c, int64_t *index_x_host) {
   return NFFTCU_OK;
 }
 
+int nfftcu_get_sorted_slab(nfftcu_ctx *c, int64_t begin, int64_t end, void *x_out_dev, uint32_t *perm_out_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  if (begin < 0 || end < begin || end > c->M) {
+    set_error("nfftcu_get_sorted_slab: range [%lld, %lld) outside [0, %lld)", (long long) begin, (long long) end, (long long) c->M);
+    return NFFTCU_EINVAL;
+  }
+  if (c->direct_only && !c->nodes_only) {
+    set_error("nfftcu_get_sorted_slab: plan has no sorted nodes (direct-only plan)");
+    return NFFTCU_ESTATE;
+  }
+  if (!c->ref_sorted) {
+    NFFTCU_TRY(sort_nodes(c));
+    c->ref_sorted = true;
+  }
+  const size_t rs = real_size(c) * (size_t) c->d;
+  if (x_out_dev && end > begin)
+    NFFTCU_CUDA(cudaMemcpyAsync(x_out_dev, (const char *) c->x_sorted + rs * (size_t) begin, rs * (size_t) (end - begin),
+                                cudaMemcpyDeviceToDevice, c->stream));
+  if (perm_out_dev && end > begin)
+    NFFTCU_CUDA(cudaMemcpyAsync(perm_out_dev, c->perm_ref + begin, sizeof(uint32_t) * (size_t) (end - begin),
+                                cudaMemcpyDeviceToDevice, c->stream));
+  return NFFTCU_OK;
+}
+
 static int host_transform(nfftcu_ctx *c, const void *in_host, void *out_host, int which) {
   // which: 0 trafo, 1 adjoint, 2 trafo_direct, 3 adjoint_direct
   NFFTCU_TRY(check_ctx(c));
@@ -413,11 +560,13 @@ static int host_transform(nfftcu_ctx *c, const void *in_host, void *out_host, in
   return NFFTCU_OK;
 }
 
-// Transform with an unannounced node refresh (plans without a psi flag: the reference re-reads x on
-// every call, nfft.c:4889, 5351).  The upload of x and its comparison with the resident nodes run on a
-// side stream WHILE the transform runs with the resident nodes; only if the comparison reports a change
-// are the nodes re-sorted and the transform repeated.  Unchanged nodes -- every call of a solver loop --
-// cost no serial PCIe time.
+// Transform with an unannounced node refresh (plans without a psi flag: the reference re-reads x on every call,
+// nfft.c:4889, 5351).  The transform is launched at once with the resident nodes; meanwhile host threads fingerprint
+// the caller's x (no PCIe traffic, no device work).  Only if the fingerprint differs from that of the array the
+// resident nodes came from are the nodes uploaded and re-sorted and the transform repeated.  Unchanged nodes -- every
+// call of a solver loop -- cost nothing on the device or the host link.  Resident nodes without a host fingerprint
+// (set through nfftcu_set_nodes_dev) or NFFT_B200_EXACT_NODE_CHECK=1 use the exact variant instead: x is uploaded on a
+// side stream and compared word for word on the device while the transform runs.
 static int host_transform_refresh(nfftcu_ctx *c, const void *x_host, const void *in_host, void *out_host,
                                   int which, int *changed_out) {
   NFFTCU_TRY(check_ctx(c));
@@ -435,38 +584,53 @@ static int host_transform_refresh(nfftcu_ctx *c, const void *x_host, const void 
     return NFFTCU_EINVAL;
   }
   NFFTCU_TRY(ensure_staging(c));
-  if (!c->side_stream) NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-  if (!c->h_flag) NFFTCU_CUDA(pool_malloc_host((void **) &c->h_flag, sizeof(int)));
-  if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, xbytes));
-  if (!c->diff_flag) NFFTCU_CUDA(pool_malloc((void **) &c->diff_flag, sizeof(int)));
   const bool forward = which == 0;
   const size_t in_bytes = forward ? cbytes(c, c->N_total) : cbytes(c, c->M);
   const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
   void *in_dev = forward ? c->fhat_dev : c->f_dev;
   void *out_dev = forward ? c->f_dev : c->fhat_dev;
-  // the side stream must not start before earlier work on the plan's stream that may still read x_stage, and not
-  // before the transform's own input is on the device: the node upload would share the host link with it and delay the
-  // first kernel; behind it, the node upload overlaps the kernels
-  if (!c->ev_side) NFFTCU_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  const bool by_fingerprint = c->x_fp_valid && !exact_node_check();
   if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
-  NFFTCU_CUDA(cudaEventRecord(c->ev_side, c->stream));
-  NFFTCU_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
-  NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->side_stream));
-  NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->side_stream));
-  {
+  if (!by_fingerprint) {
+    if (!c->side_stream) NFFTCU_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    if (!c->h_flag) NFFTCU_CUDA(pool_malloc_host((void **) &c->h_flag, sizeof(int)));
+    if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, xbytes));
+    if (!c->diff_flag) NFFTCU_CUDA(pool_malloc((void **) &c->diff_flag, sizeof(int)));
+    // the side stream must not start before earlier work on the plan's stream that may still read x_stage, and not
+    // before the transform's own input is on the device: the node upload would share the host link with it
+    if (!c->ev_side) NFFTCU_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    NFFTCU_CUDA(cudaEventRecord(c->ev_side, c->stream));
+    NFFTCU_CUDA(cudaStreamWaitEvent(c->side_stream, c->ev_side, 0));
+    NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->side_stream));
+    NFFTCU_CUDA(cudaMemsetAsync(c->diff_flag, 0, sizeof(int), c->side_stream));
     const long long words = (long long) (xbytes / 4);
     long long blocks = (words + 255) / 256;
     if (blocks > (long long) c->sm_count * 16) blocks = (long long) c->sm_count * 16;
     differs_kernel<<<(unsigned) blocks, 256, 0, c->side_stream>>>((const uint32_t *) c->x_stage,
                                                                 (const uint32_t *) c->x_dev, words, c->diff_flag);
     c->launches++;
+    NFFTCU_CUDA(cudaMemcpyAsync(c->h_flag, c->diff_flag, sizeof(int), cudaMemcpyDeviceToHost, c->side_stream));
   }
-  NFFTCU_CUDA(cudaMemcpyAsync(c->h_flag, c->diff_flag, sizeof(int), cudaMemcpyDeviceToHost, c->side_stream));
   int r = forward ? trafo_dev_impl(c, in_dev, out_dev) : adjoint_dev_impl(c, in_dev, out_dev);
   if (r != NFFTCU_OK) return r;
-  NFFTCU_CUDA(cudaStreamSynchronize(c->side_stream));
-  if (*c->h_flag) {   // the nodes did change: adopt them and redo the transform (its input is still on the device)
+  bool changed;
+  uint64_t fp = 0;
+  if (by_fingerprint) {
+    fp = fingerprint(x_host, xbytes);   // host threads; the device is busy with the transform meanwhile
+    changed = fp != c->x_fp;
+  } else {
+    NFFTCU_CUDA(cudaStreamSynchronize(c->side_stream));
+    changed = *c->h_flag != 0;
+  }
+  if (changed) {   // the nodes did change: adopt them and redo the transform (its input is still on the device)
     NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+    if (by_fingerprint) {
+      if (!c->x_stage) NFFTCU_CUDA(pool_malloc(&c->x_stage, xbytes));
+      NFFTCU_CUDA(cudaMemcpyAsync(c->x_stage, x_host, xbytes, cudaMemcpyHostToDevice, c->stream));
+      c->x_fp = fp;
+    } else {
+      c->x_fp_valid = false;
+    }
     void *t = c->x_dev; c->x_dev = c->x_stage; c->x_stage = t;
     NFFTCU_TRY(nodes_ready(c));
     if (changed_out) *changed_out = 1;
@@ -628,6 +792,31 @@ int nfftcu_free_pinned(void *ptr) {
   if (ptr) NFFTCU_CUDA(pool_free_host(ptr));
   return NFFTCU_OK;
 }
+// nfft_malloc / nfft_free backing store (nfft3_host.c): large host buffers of the plan API (MALLOC_X / MALLOC_F_HAT /
+// MALLOC_F, index_x, and whatever callers allocate through nfft_malloc, e.g. kernel/mri/mri.c:94-96) are page-locked
+// so that the host-pointer transforms copy at the full link rate; small ones and the no-device case use the C heap.
+void *nfftcu_host_alloc(size_t bytes) {
+  static const size_t threshold = [] {
+    const char *e = getenv("NFFT_B200_PINNED_MALLOC_MIN");   // bytes; 0 disables page-locking
+    return e ? (size_t) atoll(e) : ((size_t) 1 << 18);
+  }();
+  void *p = nullptr;
+  if (bytes == 0) bytes = 1;
+  if (threshold > 0 && bytes >= threshold && nfftcu_device_count() > 0) {
+    if (pool_malloc_host(&p, bytes) == cudaSuccess && p) return p;
+    cudaGetLastError();
+    p = nullptr;
+  }
+  if (posix_memalign(&p, 64, bytes) != 0) return nullptr;
+  return p;
+}
+void nfftcu_host_free(void *p) {
+  if (!p) return;
+  if (pool_owns_host(p)) pool_free_host(p);
+  else free(p);
+}
+void nfftcu_pool_trim(void) { pool_trim(); }
+
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
   NFFTCU_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
   return NFFTCU_OK;

@@ -36,6 +36,8 @@ cudaError_t pool_malloc_bytes(void **p, size_t bytes);
 cudaError_t pool_free(void *p);
 cudaError_t pool_malloc_host_bytes(void **p, size_t bytes);
 cudaError_t pool_free_host(void *p);
+bool pool_owns_host(void *p);   // p is a live page-locked buffer handed out by pool_malloc_host
+void pool_trim();               // give all cached (free) device and page-locked buffers back to the driver
 template <typename T> inline cudaError_t pool_malloc(T **p, size_t bytes) { return pool_malloc_bytes((void **) p, bytes); }
 template <typename T> inline cudaError_t pool_malloc_host(T **p, size_t bytes) { return pool_malloc_host_bytes((void **) p, bytes); }
 
@@ -67,6 +69,8 @@ struct FftAxis {
 
 }  // namespace nfftcu
 
+namespace nfftcu { struct PeerState; }
+
 struct nfftcu_ctx_s {
   int prec = NFFTCU_DOUBLE;
   int d = 0;
@@ -94,6 +98,9 @@ struct nfftcu_ctx_s {
   void *keys_ref = nullptr;         // sorted reference keys (uint64), for index_x
   uint32_t *perm_ref = nullptr;     // reference permutation (== perm when node order is the reference key)
   void *psi_table = nullptr;        // optional: M * d * (2m+2) reals in processing order
+  bool psi_table_valid = false;     // table was built for the current nodes (nodes_ready clears it)
+  uint64_t x_fp = 0;                // fingerprint of the HOST array the resident nodes were uploaded from
+  bool x_fp_valid = false;
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;
   bool tile2_ready = false;         // tile_* hold the tile order of the 2-D kernels (tile2d.cu)
@@ -126,6 +133,9 @@ struct nfftcu_ctx_s {
   void *kbpoly_dev = nullptr;
   void *sort_tmp = nullptr;         // scratch kept between set_nodes calls
   size_t sort_tmp_bytes = 0;
+
+  nfftcu::PeerState *peer = nullptr;   // fused D^T + cross-GPU reduce (peer.cu)
+  bool nodes_only = false;             // sorter of a multi-GPU group: no grid, no FFT plan, never transforms
 
   // staging buffers for the host-pointer API
   void *fhat_dev = nullptr;
@@ -185,6 +195,14 @@ int stage_BT(nfftcu_ctx *c, const void *f_dev);                     // spread.cu
 int build_psi_table(nfftcu_ctx *c);                                 // interp.cu
 int ndft_trafo(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev);  // ndft.cu
 int ndft_adjoint(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev);// ndft.cu
+void peer_detach(nfftcu_ctx *c);                                    // peer.cu
+int peer_attach_local(nfftcu_ctx **ctxs, int world, bool all_outputs);   // peer.cu
+int peer_reduce_DT(nfftcu_ctx *c, void *f_hat_dev);                 // peer.cu
+void *peer_slice_ptr(nfftcu_ctx *c, long long *k_begin, long long *k_end);   // peer.cu
+int create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n, int64_t m, int64_t M,
+               unsigned flags, int device, bool nodes_only);        // api.cu
+int nodes_ready(nfftcu_ctx *c);                                     // api.cu
+uint64_t fingerprint(const void *data, size_t bytes);               // api.cu
 
 // ---- Kaiser-Bessel window, evaluated in double for both precisions ----------------------------
 // phi(t) with t = n*(x - l/n) the distance in grid units, s = m^2 - t^2:

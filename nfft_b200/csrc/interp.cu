@@ -138,7 +138,7 @@ int run_generic(nfftcu_ctx *c, void *f_dev) {
   const dim3 grid((unsigned) blocks), block(kWarpsPerBlock * 32);
   const C *g = (const C *) c->grid;
   const T *xs = (const T *) c->x_sorted;
-  const T *tab = (const T *) c->psi_table;
+  const T *tab = (c->opt_psi_table && c->psi_table_valid) ? (const T *) c->psi_table : nullptr;
   switch (c->d) {
     case 1: interp_generic_kernel<T, 1><<<grid, block, smem, c->stream>>>(g, xs, c->perm, (C *) f_dev, c->M, geo, tab); break;
     case 2: interp_generic_kernel<T, 2><<<grid, block, smem, c->stream>>>(g, xs, c->perm, (C *) f_dev, c->M, geo, tab); break;
@@ -181,6 +181,7 @@ int build_psi_table(nfftcu_ctx *c) {
         (const float *) c->x_sorted, (float *) c->psi_table, c->M, geo);
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
+  c->psi_table_valid = true;
   return NFFTCU_OK;
 }
 

@@ -5,7 +5,8 @@
 // cudaMallocHost / cudaFree(Host) dominate such a life cycle (tens of calls at 0.1 - 3 ms each).  Freed buffers are
 // therefore kept in exact-size free lists (per device for device memory) up to a byte cap and handed out again.
 // pool_free synchronises the device before a buffer becomes reusable, which is the guarantee cudaFree gives
-// implicitly.  Env NFFT_B200_POOL_MB sets the cap per kind (default 4096, 0 disables the caches).
+// implicitly.  Env NFFT_B200_POOL_MB sets the cap per kind (default 4096, 0 disables the caches); nfftcu_pool_trim()
+// returns everything cached to the driver (for processes that share the GPU with other CUDA users).
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -56,11 +57,12 @@ cudaError_t pool_get(Pool &P, bool host, void **out, size_t bytes) {
     P.free_list.erase(it);
     P.cached -= bytes;
   } else {
-    cudaError_t e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+    // page-locked memory is portable: every device of a sharded plan copies from / to it
+    cudaError_t e = host ? cudaHostAlloc(out, bytes, cudaHostAllocPortable) : cudaMalloc(out, bytes);
     if (e != cudaSuccess) {   // make room and retry once
       cudaGetLastError();
       flush(P, host);
-      e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+      e = host ? cudaHostAlloc(out, bytes, cudaHostAllocPortable) : cudaMalloc(out, bytes);
       if (e != cudaSuccess) return e;
     }
   }
@@ -83,7 +85,13 @@ cudaError_t pool_put(Pool &P, bool host, void *p) {
     return host ? cudaFreeHost(p) : cudaFree(p);
   }
   lock.unlock();
-  cudaError_t e = cudaDeviceSynchronize();   // what cudaFree guarantees: nothing in flight still uses the buffer
+  // what cudaFree guarantees: nothing in flight still uses the buffer -- on the device that OWNS it, which in a
+  // multi-GPU process need not be the current one
+  int prev = -1;
+  if (!host && cudaGetDevice(&prev) == cudaSuccess && prev != key.first) cudaSetDevice(key.first);
+  else prev = -1;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (prev >= 0) cudaSetDevice(prev);
   if (e != cudaSuccess) return e;
   lock.lock();
   P.free_list.insert({key, p});
@@ -97,5 +105,13 @@ cudaError_t pool_malloc_bytes(void **p, size_t bytes) { return pool_get(g_dev, f
 cudaError_t pool_free(void *p) { return pool_put(g_dev, false, p); }
 cudaError_t pool_malloc_host_bytes(void **p, size_t bytes) { return pool_get(g_host, true, p, bytes); }
 cudaError_t pool_free_host(void *p) { return pool_put(g_host, true, p); }
+bool pool_owns_host(void *p) {
+  std::lock_guard<std::mutex> lock(g_host.mu);
+  return g_host.live.count(p) != 0;
+}
+void pool_trim() {
+  { std::lock_guard<std::mutex> lock(g_dev.mu); flush(g_dev, false); }
+  { std::lock_guard<std::mutex> lock(g_host.mu); flush(g_host, true); }
+}
 
 }  // namespace nfftcu

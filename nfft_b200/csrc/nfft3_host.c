@@ -62,8 +62,10 @@ void *X(malloc)(size_t n)
 {
   void *p = NULL;
   if (X(malloc_hook)) return X(malloc_hook)(n);
-  if (n == 0) n = 1;
-  if (posix_memalign(&p, 64, n) != 0 || !p) X(die)("nfft_malloc: out of memory");
+  /* large buffers are page-locked (nfftcu_host_alloc) so that nfft_trafo / nfft_adjoint on MALLOC_X / MALLOC_F_HAT /
+   * MALLOC_F members -- and on anything else callers take from nfft_malloc -- copy at the full host-link rate */
+  p = nfftcu_host_alloc(n);
+  if (!p) X(die)("nfft_malloc: out of memory");
   return p;
 }
 
@@ -71,7 +73,7 @@ void X(free)(void *p)
 {
   if (!p) return;
   if (X(free_hook)) { X(free_hook)(p); return; }
-  free(p);
+  nfftcu_host_free(p);
 }
 
 /* ---- small util entry points the initialisers need (kernel/util/int.c, window.c) -------------- */
@@ -89,6 +91,9 @@ const char *X(get_window_name)(void) { return "kaiserbessel"; }
 
 /* ---- plan <-> context ------------------------------------------------------------------------ */
 static nfftcu_ctx *ctx_of(const X(plan) *ths) { return (nfftcu_ctx*) ths->my_fftw_plan1; }
+/* multi-device plans (NFFT_B200_DEVICES=0,1,...): the group sits in the second FFTW-plan slot, ctx_of() is then the
+ * plan of the group's first device (same geometry: window parameters, c_phi_inv, stage times) */
+static nfftcu_group *group_of(const X(plan) *ths) { return (nfftcu_group*) ths->my_fftw_plan2; }
 
 static void check_cu(int status)
 {
@@ -105,23 +110,28 @@ static void refresh_index_x(X(plan) *ths)
   if ((ths->flags & NFFT_SORT_NODES) && ths->index_x && ths->M_total > 0)
   {
     int64_t *dst = (int64_t*) ths->index_x;   /* NFFT_INT is 64-bit on LP64 */
-    int r = nfftcu_get_index_x(ctx_of(ths), dst);
+    int r = group_of(ths) ? nfftcu_group_get_index_x(group_of(ths), dst) : nfftcu_get_index_x(ctx_of(ths), dst);
     if (r != NFFTCU_OK && r != NFFTCU_ESTATE) check_cu(r);
   }
 }
 
+static int64_t nodes_version(const X(plan) *ths)
+{
+  return group_of(ths) ? nfftcu_group_nodes_version(group_of(ths)) : nfftcu_nodes_version(ctx_of(ths));
+}
+
 static void upload_nodes(X(plan) *ths)
 {
-  nfftcu_ctx *ctx = ctx_of(ths);
-  const int64_t before = nfftcu_nodes_version(ctx);
+  const int64_t before = nodes_version(ths);
   if (ths->M_total > 0 && !ths->x) X(die)("Member x not initialized.");
-  check_cu(nfftcu_set_nodes(ctx, ths->x));
-  if (nfftcu_nodes_version(ctx) != before) refresh_index_x(ths);
+  if (group_of(ths)) check_cu(nfftcu_group_set_nodes(group_of(ths), ths->x));
+  else check_cu(nfftcu_set_nodes(ctx_of(ths), ths->x));
+  if (nodes_version(ths) != before) refresh_index_x(ths);
 }
 
 static void nodes_for_transform(X(plan) *ths)
 {
-  if (!(ths->flags & NODE_BOUND_FLAGS) || nfftcu_nodes_version(ctx_of(ths)) == 0)
+  if (!(ths->flags & NODE_BOUND_FLAGS) || nodes_version(ths) == 0)
     upload_nodes(ths);
 }
 
@@ -147,10 +157,12 @@ static void store_times(X(plan) *ths)
 static void init_help(X(plan) *ths)
 {
   nfftcu_ctx *ctx = NULL;
+  nfftcu_group *grp = NULL;
   int64_t N64[NFFTCU_MAX_D], n64[NFFTCU_MAX_D];
   INT t;
-  int device = 0;
+  int device = 0, ndev = 0, devs[NFFTCU_MAX_PEERS], grid_plan = 1;
   const char *dev_env = getenv("NFFT_B200_DEVICE");
+  const char *devs_env = getenv("NFFT_B200_DEVICES");   /* "0,1,2,3": node-sharded over these GPUs (nfftcu_group_*) */
 
   if (ths->d < 1 || ths->d > NFFTCU_MAX_D) X(die)("nfft_init: rank d out of range [1,8]");
   if (ths->flags & NFFT_OMP_BLOCKWISE_ADJOINT) ths->flags |= NFFT_SORT_NODES;   /* nfft.c:5955 */
@@ -165,10 +177,34 @@ static void init_help(X(plan) *ths)
     n64[t] = ths->n[t];
   }
   if (dev_env) device = atoi(dev_env);
-  check_cu(nfftcu_create(&ctx, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total,
-      ths->flags, device));
+  for (t = 0; t < ths->d; t++)
+    if (ths->N[t] <= ths->m || ths->n[t] <= 2 * ths->m + 2) grid_plan = 0;   /* NDFT fallback plans stay on one device */
+  if (devs_env && grid_plan && ths->M_total >= 1024)
+  {
+    const char *s = devs_env;
+    while (*s && ndev < NFFTCU_MAX_PEERS)
+    {
+      char *end = NULL;
+      const long v = strtol(s, &end, 10);
+      if (end == s) break;
+      devs[ndev++] = (int) v;
+      s = (*end == ',') ? end + 1 : end;
+    }
+  }
+  if (ndev >= 2)
+  {
+    /* plans the group cannot take (an FFT axis long enough to be split) fall back to the first listed device */
+    if (nfftcu_group_create(&grp, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total, ths->flags, devs, ndev)
+        == NFFTCU_OK)
+      ctx = nfftcu_group_ctx(grp, 0);
+    else
+      device = devs[0];
+  }
+  if (!grp)
+    check_cu(nfftcu_create(&ctx, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total,
+        ths->flags, device));
   ths->my_fftw_plan1 = ctx;
-  ths->my_fftw_plan2 = NULL;
+  ths->my_fftw_plan2 = grp;
 
   ths->sigma = (R*) X(malloc)((size_t) ths->d * sizeof(R));
   ths->b = (R*) X(malloc)((size_t) ths->d * sizeof(R));
@@ -198,9 +234,16 @@ static void init_help(X(plan) *ths)
     ths->K = (INT) ((1U << m2K_[j]) * (unsigned) (ths->m + 2));
   }
   /* a per-node window table on the device stands in for psi of PRE_PSI / PRE_FULL_PSI */
-  if (ths->flags & (PRE_PSI | PRE_FULL_PSI))
-    check_cu(nfftcu_set_option(ctx, NFFTCU_OPT_PSI_TABLE, 1));
-  check_cu(nfftcu_set_option(ctx, NFFTCU_OPT_TIMING, getenv("NFFT_B200_MEASURE_TIME") ? 1 : 0));
+  {
+    int r, nctx = grp ? nfftcu_group_size(grp) : 1;
+    for (r = 0; r < nctx; r++)
+    {
+      nfftcu_ctx *cr = grp ? nfftcu_group_ctx(grp, r) : ctx;
+      if (ths->flags & (PRE_PSI | PRE_FULL_PSI))
+        check_cu(nfftcu_set_option(cr, NFFTCU_OPT_PSI_TABLE, 1));
+      check_cu(nfftcu_set_option(cr, NFFTCU_OPT_TIMING, getenv("NFFT_B200_MEASURE_TIME") ? 1 : 0));
+    }
+  }
 
   ths->psi = NULL;
   ths->psi_index_g = NULL;
@@ -317,13 +360,15 @@ void X(trafo)(X(plan) *ths)
     /* no psi flag: x may have changed without notice; refresh it overlapped with the transform */
     int changed = 0;
     if (ths->M_total > 0 && !ths->x) X(die)("Member x not initialized.");
-    check_cu(nfftcu_trafo_refresh(ctx_of(ths), ths->x, ths->f_hat, ths->f, &changed));
+    if (group_of(ths)) check_cu(nfftcu_group_trafo_refresh(group_of(ths), ths->x, ths->f_hat, ths->f, &changed));
+    else check_cu(nfftcu_trafo_refresh(ctx_of(ths), ths->x, ths->f_hat, ths->f, &changed));
     if (changed) refresh_index_x(ths);
   }
   else
   {
     nodes_for_transform(ths);
-    check_cu(nfftcu_trafo(ctx_of(ths), ths->f_hat, ths->f));
+    if (group_of(ths)) check_cu(nfftcu_group_trafo(group_of(ths), ths->f_hat, ths->f));
+    else check_cu(nfftcu_trafo(ctx_of(ths), ths->f_hat, ths->f));
   }
   store_times(ths);
 }
@@ -335,13 +380,15 @@ void X(adjoint)(X(plan) *ths)
   {
     int changed = 0;
     if (ths->M_total > 0 && !ths->x) X(die)("Member x not initialized.");
-    check_cu(nfftcu_adjoint_refresh(ctx_of(ths), ths->x, ths->f, ths->f_hat, &changed));
+    if (group_of(ths)) check_cu(nfftcu_group_adjoint_refresh(group_of(ths), ths->x, ths->f, ths->f_hat, &changed));
+    else check_cu(nfftcu_adjoint_refresh(ctx_of(ths), ths->x, ths->f, ths->f_hat, &changed));
     if (changed) refresh_index_x(ths);
   }
   else
   {
     nodes_for_transform(ths);
-    check_cu(nfftcu_adjoint(ctx_of(ths), ths->f, ths->f_hat));
+    if (group_of(ths)) check_cu(nfftcu_group_adjoint(group_of(ths), ths->f, ths->f_hat));
+    else check_cu(nfftcu_adjoint(ctx_of(ths), ths->f, ths->f_hat));
   }
   store_times(ths);
 }
@@ -358,14 +405,16 @@ void X(trafo_direct)(const X(plan) *ths)
 {
   if (!ths->f_hat || !ths->f) X(die)("nfft_trafo_direct: f_hat or f is NULL");
   upload_nodes((X(plan)*) ths);
-  check_cu(nfftcu_trafo_direct(ctx_of(ths), ths->f_hat, ths->f));
+  if (group_of(ths)) check_cu(nfftcu_group_direct(group_of(ths), 0, ths->f_hat, ths->f));
+  else check_cu(nfftcu_trafo_direct(ctx_of(ths), ths->f_hat, ths->f));
 }
 
 void X(adjoint_direct)(const X(plan) *ths)
 {
   if (!ths->f_hat || !ths->f) X(die)("nfft_adjoint_direct: f_hat or f is NULL");
   upload_nodes((X(plan)*) ths);
-  check_cu(nfftcu_adjoint_direct(ctx_of(ths), ths->f, ths->f_hat));
+  if (group_of(ths)) check_cu(nfftcu_group_direct(group_of(ths), 1, ths->f, ths->f_hat));
+  else check_cu(nfftcu_adjoint_direct(ctx_of(ths), ths->f, ths->f_hat));
 }
 
 /* ---- nfft_check, nfft.c:6169-6207 (same messages) ----------------------------------------------- */
@@ -393,8 +442,10 @@ void X(finalize)(X(plan) *ths)
 {
   INT t;
   if (ths->flags & NFFT_SORT_NODES) X(free)(ths->index_x);
-  check_cu(nfftcu_destroy(ctx_of(ths)));
+  if (group_of(ths)) check_cu(nfftcu_group_destroy(group_of(ths)));
+  else check_cu(nfftcu_destroy(ctx_of(ths)));
   ths->my_fftw_plan1 = NULL;
+  ths->my_fftw_plan2 = NULL;
   if (ths->flags & PRE_PHI_HUT)
   {
     for (t = 0; t < ths->d; t++) X(free)(ths->c_phi_inv[t]);

@@ -20,6 +20,7 @@
 
 struct nfftcu_solver_s {
   nfftcu_ctx *plan = nullptr;
+  int device = 0;                // cached: nfftcu_solver_destroy works after the plan is gone
   unsigned flags = 0;
   void *vec[8] = {nullptr};      // device vectors, index NFFTCU_SOLVER_*; Z may alias P
   void *fhat_in = nullptr;       // N_total complex: argument of the transform
@@ -302,6 +303,7 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
   NFFTCU_CUDA(cudaSetDevice(plan->device));
   nfftcu_solver_s *s = new nfftcu_solver_s();
   s->plan = plan;
+  s->device = plan->device;   // destroy must not touch the plan: nfft_finalize before solver_finalize is legal (solver.c:373-389)
   s->flags = flags;
   auto fail = [&](int rc) { nfftcu_solver_destroy(s); return rc; };
 #define SOLVER_ALLOC(ptr, bytes)                                                                    \
@@ -337,7 +339,7 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
 
 int nfftcu_solver_destroy(nfftcu_solver *s) {
   if (!s) return NFFTCU_OK;
-  cudaSetDevice(s->plan->device);
+  cudaSetDevice(s->device);
   if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
   if (s->ev_fhat) cudaEventDestroy(s->ev_fhat);
   if (s->ev_r) cudaEventDestroy(s->ev_r);

@@ -134,6 +134,9 @@ void X(init_advanced_complex)(X(plan_complex) *ths, Y(mv_plan_complex) *mv, unsi
   ths->mv = mv;
   ths->flags = flags;
   p = nfft_plan_of(ths);
+  if (p->my_fftw_plan2)
+    Y(die)("solver (B200): the device-resident solver drives single-device plans; unset NFFT_B200_DEVICES for the "
+           "plans a solver iterates on (coils are distributed plan-per-GPU, not node-sharded)");
   M = (size_t) mv->M_total;
   N = (size_t) mv->N_total;
   check_cu(nfftcu_solver_create(&dev, (nfftcu_ctx*) p->my_fftw_plan1, flags));

@@ -117,7 +117,7 @@ int run_generic(nfftcu_ctx *c, const void *f_dev) {
   const dim3 grid((unsigned) blocks), block(kWarpsPerBlock * 32);
   C *g = (C *) c->grid;
   const T *xs = (const T *) c->x_sorted;
-  const T *tab = (const T *) c->psi_table;
+  const T *tab = (c->opt_psi_table && c->psi_table_valid) ? (const T *) c->psi_table : nullptr;
   const C *f = (const C *) f_dev;
   switch (c->d) {
     case 1: spread_generic_kernel<T, 1><<<grid, block, smem, c->stream>>>(g, xs, c->perm, f, c->M, geo, tab); break;

@@ -1,0 +1,107 @@
+"""Full-size GPU parity (run with -m gpu on the B200 box): the BASELINE configs at the sizes bench.py times,
+through the reference-facing plan API of libnfft3_b200.so, against the REFERENCE's own nfft_trafo /
+nfft_adjoint (oracle/_ref = unmodified kernel/nfft/nfft.c compiled by oracle/refbuild) on the same inputs.
+
+Error measure: ||a - ref||_2 / ||ref||_2 (nfft_error_l_2_complex, kernel/util/error.c:163-166), the measure the
+reference's own tests use (tests/nfft.c:739-781).  Bars: fp64 <= 1e-12, fp32 <= 1e-5, index_x bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import rel_l2
+from nfft_b200 import plan_abi as abi
+from nfft_b200.plan import Plan
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not common.have_ref(), reason="oracle/_ref not present")]
+
+TOL = {"double": 1e-12, "float": 1e-5}
+# the reference's best CPU flags for a sorted 3-D plan; no PRE_PSI: psi on the fly
+FLAGS3 = (abi.PRE_PHI_HUT | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+          | abi.NFFT_SORT_NODES | abi.NFFT_OMP_BLOCKWISE_ADJOINT)
+
+
+def _inputs(N, M, precision, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    real = np.float64 if precision == "double" else np.float32
+    d, NN = len(N), int(np.prod(N))
+    x = (rng.random((M, d)) - 0.5).astype(real)
+    if precision == "float":
+        x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
+    fh = rng.random((NN, 2)).astype(real)
+    f = rng.random((M, 2)).astype(real)
+    return x, fh, f
+
+
+def _run(api_kw, N, n, m, M, flags, x, fh, f):
+    p = Plan.init_guru(len(N), N, M, n, m, flags, **api_kw)
+    p.x[:] = x
+    if p.flags & abi.PRE_ONE_PSI:
+        p.precompute_one_psi()
+    p.f_hat.view(p.api.real)[:] = fh.ravel()
+    p.trafo()
+    out_f = p.f.copy()
+    p.f.view(p.api.real)[:] = f.ravel()
+    p.adjoint()
+    out_fh = p.f_hat.copy()
+    idx = p.index_x.copy() if (p.flags & abi.NFFT_SORT_NODES) else None
+    p.finalize()
+    return out_f, out_fh, idx
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_cfg3_full_size_vs_reference(precision):
+    """BASELINE configs[2] at full size: 3-D N=128^3, n=256^3, M=10^7 uniform nodes, m=6, fp64 and nfftf_ fp32:
+    nfft_trafo, nfft_adjoint and the whole index_x (keys and permutation) against the reference run on the
+    same inputs."""
+    N, n, m, M = [128] * 3, [256] * 3, 6, 10_000_000
+    x, fh, f = _inputs(N, M, precision, 20260103)
+    ref_f, ref_fh, ref_idx = _run(dict(api=common.ref_api(precision)), N, n, m, M, FLAGS3, x, fh, f)
+    out_f, out_fh, idx = _run(dict(precision=precision), N, n, m, M, FLAGS3, x, fh, f)
+    e_t, e_a = rel_l2(out_f, ref_f), rel_l2(out_fh, ref_fh)
+    print(f"cfg3 {precision} M=1e7: trafo rel-l2 {e_t:.3e}, adjoint rel-l2 {e_a:.3e}")
+    assert e_t <= TOL[precision]
+    assert e_a <= TOL[precision]
+    assert np.array_equal(idx, ref_idx)
+
+
+@pytest.mark.skipif(os.environ.get("NFFT_B200_SKIP_CFG4_FULL") == "1", reason="disabled by env")
+def test_cfg4_full_size_vs_reference():
+    """BASELINE configs[3] at full size on one GPU: 3-D N=256^3, n=512^3, M=10^8 nodes, fp64 (the multi-GPU
+    runs shard exactly this node set): trafo, adjoint and index_x against the reference."""
+    N, n, m, M = [256] * 3, [512] * 3, 6, 100_000_000
+    x, fh, f = _inputs(N, M, "double", 20260104)
+    ref_f, ref_fh, ref_idx = _run(dict(api=common.ref_api("double")), N, n, m, M, FLAGS3, x, fh, f)
+    out_f, out_fh, idx = _run(dict(precision="double"), N, n, m, M, FLAGS3, x, fh, f)
+    e_t, e_a = rel_l2(out_f, ref_f), rel_l2(out_fh, ref_fh)
+    print(f"cfg4 double M=1e8: trafo rel-l2 {e_t:.3e}, adjoint rel-l2 {e_a:.3e}")
+    assert e_t <= 1e-12
+    assert e_a <= 1e-12
+    assert np.array_equal(idx, ref_idx)
+
+
+def _mri_spiral(M, N):
+    """applications/mri/mri2d/construct_knots_spiral.m:20-33 (arms = 1)."""
+    i = np.arange(M, dtype=np.float64)
+    t = np.sqrt(i / M)
+    w = N / 64.0 * 50.0
+    x = np.stack([0.5 * t * np.cos(2 * np.pi * w * t), 0.5 * t * np.sin(2 * np.pi * w * t)], axis=1)
+    return np.clip(x, -0.5, np.nextafter(0.5, 0.0))
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_cfg2_full_size_vs_reference(precision):
+    """BASELINE configs[1] at full size: 2-D N=512^2, M=512^2 spiral nodes, PRE_PSI, against the reference."""
+    N, n, m, M = [512, 512], [1024, 1024], 6, 512 * 512
+    flags = abi.PRE_PHI_HUT | abi.PRE_PSI | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+    real = np.float64 if precision == "double" else np.float32
+    x = _mri_spiral(M, 512).astype(real)
+    if precision == "float":
+        x = np.clip(x, -0.5, np.nextafter(np.float32(0.5), np.float32(0)))
+    _, fh, f = _inputs(N, M, precision, 20260102)
+    ref_f, ref_fh, _ = _run(dict(api=common.ref_api(precision)), N, n, m, M, flags, x, fh, f)
+    out_f, out_fh, _ = _run(dict(precision=precision), N, n, m, M, flags, x, fh, f)
+    assert rel_l2(out_f, ref_f) <= TOL[precision]
+    assert rel_l2(out_fh, ref_fh) <= TOL[precision]

@@ -29,7 +29,22 @@ FULL_METRICS = [
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    # tensor / FP64 pipe evidence for the DMMA (fp64) and HMMA-TF32 (fp32) kernels
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+    "smsp__warps_eligible.avg.per_cycle_active",
 ]
+# every warp-stall reason ncu reports (warps per issue-active cycle), sorted by value in the summary
+STALL_PREFIX = "smsp__average_warps_issue_stalled_"
+STALL_SUFFIX = "_per_issue_active.ratio"
 
 
 def launches(src, dst):
@@ -72,6 +87,17 @@ def full(src, dst):
             for mname in FULL_METRICS:
                 if mname in idx:
                     f.write(f"| {mname} | {r[idx[mname]]} | {units[idx[mname]]} |\n")
+            stalls = []
+            for h, i in idx.items():
+                if h.startswith(STALL_PREFIX) and h.endswith(STALL_SUFFIX) and "_not_issued" not in h:
+                    try:
+                        stalls.append((float(r[i].replace(",", "")), h[len(STALL_PREFIX):-len(STALL_SUFFIX)]))
+                    except ValueError:
+                        pass
+            if stalls:
+                f.write("\nwarp stall reasons (warps per issue-active cycle, largest first):\n\n| reason | value |\n|---|---:|\n")
+                for v, nm in sorted(stalls, reverse=True)[:8]:
+                    f.write(f"| {nm} | {v:.3f} |\n")
             if "dram__bytes_read.sum" in idx:
                 def gb(name):
                     v = float(r[idx[name]].replace(",", ""))
