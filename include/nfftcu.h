@@ -42,6 +42,11 @@ extern "C" {
 #define NFFTCU_ESTATE (-5)   /* call order violated (e.g. transform before set_nodes) */
 
 #define NFFTCU_MAX_D 8
+/* window family: the reference fixes it at configure time (--with-window, include/infft.h:146-222); here it is a
+ * create-time flag OR-ed into `flags` (bits the reference's plan flags do not use) */
+#define NFFTCU_WINDOW_KAISER_BESSEL 0
+#define NFFTCU_WINDOW_GAUSSIAN 1
+#define NFFTCU_FLAG_GAUSSIAN (1u << 30)   /* Gaussian window (include/infft.h:154-173) instead of Kaiser-Bessel */
 #define NFFTCU_MAX_PEERS 8            /* GPUs of one NVSwitch domain that can share an adjoint reduction */
 #define NFFTCU_PEER_HANDLE_BYTES 192  /* opaque per-rank blob of nfftcu_peer_export (three CUDA IPC handles) */
 
@@ -71,6 +76,12 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
 /* replaces the device side of nfft_finalize (nfft.c:6209-6270) */
 int nfftcu_destroy(nfftcu_ctx *ctx);
 
+/* Units of the internal grid (single-stage calls only; nfftcu_trafo / nfftcu_adjoint are unaffected): the device
+ * window values of dimension t carry an exact power-of-two factor s_t (1 for fp64 plans; for fp32 plans
+ * 2^-round(log2 phi_hat_t(0)), which keeps the fp32 grid from overflowing where the reference's does) and c_t carries
+ * 1/s_t.  With S = prod s_t: stage_D writes g_ref / S, stage_B returns S * B g, stage_BT writes S * B^T f, stage_DT
+ * returns D^T g / S.  scale_host receives s_t, t < d, as doubles. */
+int nfftcu_get_window_scale(nfftcu_ctx *ctx, double *scale_host);
 /* c_phi_inv[t] (N_t reals, host) for plans with PRE_PHI_HUT: plan member c_phi_inv */
 int nfftcu_get_c_phi_inv(nfftcu_ctx *ctx, int t, void *out_host);
 /* b[t], sigma[t] as the reference stores them in the plan (R-typed, host) */

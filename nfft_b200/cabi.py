@@ -18,11 +18,12 @@ _LIBPATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libn
 DOUBLE, FLOAT = 0, 1
 PEER_HANDLE_BYTES = 192
 OPT_TIMING, OPT_PSI_TABLE, OPT_B_KERNEL, OPT_NODE_ORDER, OPT_B_FLUSH, OPT_FFT_PRUNE, OPT_FFT_KERNEL, OPT_WINDOW_IMAGES = 1, 2, 3, 4, 5, 6, 7, 8
+FLAG_GAUSSIAN = 1 << 30
 
 # every symbol include/nfftcu.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = (
     "nfftcu_last_error", "nfftcu_device_count", "nfftcu_create", "nfftcu_destroy",
-    "nfftcu_get_c_phi_inv", "nfftcu_get_window_params", "nfftcu_set_nodes", "nfftcu_set_nodes_dev",
+    "nfftcu_get_c_phi_inv", "nfftcu_get_window_params", "nfftcu_get_window_scale", "nfftcu_set_nodes", "nfftcu_set_nodes_dev",
     "nfftcu_nodes_version", "nfftcu_get_index_x", "nfftcu_trafo", "nfftcu_adjoint",
     "nfftcu_trafo_direct", "nfftcu_adjoint_direct", "nfftcu_trafo_dev", "nfftcu_adjoint_dev",
     "nfftcu_trafo_direct_dev", "nfftcu_adjoint_direct_dev", "nfftcu_stage_D", "nfftcu_stage_F",
@@ -60,6 +61,7 @@ def lib() -> C.CDLL:
         L.nfftcu_destroy.argtypes = [vp]
         L.nfftcu_get_c_phi_inv.argtypes = [vp, ci, vp]
         L.nfftcu_get_window_params.argtypes = [vp, vp, vp]
+        L.nfftcu_get_window_scale.argtypes = [vp, C.POINTER(C.c_double)]
         for name in ("nfftcu_set_nodes", "nfftcu_set_nodes_dev", "nfftcu_get_index_x",
                      "nfftcu_stage_D", "nfftcu_stage_B", "nfftcu_stage_BT", "nfftcu_stage_DT",
                      "nfftcu_set_stream"):
@@ -220,6 +222,13 @@ class Engine:
         out = np.empty((max(self.M, 1), 2), dtype=np.int64)
         _ck(self.L.nfftcu_get_index_x(self.ctx, _ptr(out)))
         return out[: self.M]
+
+    def window_scale(self) -> float:
+        """S = prod_t s_t: the power-of-two factor the device window carries (1.0 for fp64 plans); single-stage calls
+        see the grid in these units (include/nfftcu.h, nfftcu_get_window_scale)"""
+        s = (C.c_double * self.d)()
+        _ck(self.L.nfftcu_get_window_scale(self.ctx, s))
+        return float(np.prod([float(v) for v in s]))
 
     def c_phi_inv(self, t: int) -> np.ndarray:
         out = np.empty(self.N[t], dtype=self.real)

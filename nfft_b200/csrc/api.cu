@@ -316,7 +316,8 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
   c->device = device;
   c->m = m;
   c->M = M;
-  c->flags = flags;
+  c->flags = flags & ~NFFTCU_FLAG_GAUSSIAN;
+  c->window = (flags & NFFTCU_FLAG_GAUSSIAN) ? NFFTCU_WINDOW_GAUSSIAN : NFFTCU_WINDOW_KAISER_BESSEL;
   c->nodes_only = nodes_only;
   c->N_total = 1;
   c->n_total = 1;
@@ -331,14 +332,19 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
     c->n_total *= n[t];
     if (N[t] <= m || n[t] <= 2 * m + 2) c->direct_only = true;
     // sigma and b in the plan precision like init_help (nfft.c:5961-5964, infft.h:216-222)
+    // Gaussian: b = 2 sigma / (2 sigma - 1) * m / pi (WINDOW_HELP_INIT, infft.h:157-165)
+    const double kPi = 3.1415926535897932384626433832795028841971693993751;
     if (precision == NFFTCU_DOUBLE) {
       c->sigma[t] = (double) n[t] / (double) N[t];
-      c->b[t] = 3.1415926535897932384626433832795028841971693993751 * (2.0 - 1.0 / c->sigma[t]);
+      c->b[t] = c->window == NFFTCU_WINDOW_GAUSSIAN
+                    ? (2.0 * c->sigma[t]) / (2.0 * c->sigma[t] - 1.0) * ((double) m / kPi)
+                    : kPi * (2.0 - 1.0 / c->sigma[t]);
     } else {
       const float sg = (float) n[t] / (float) N[t];
       c->sigma[t] = sg;
-      c->b[t] = (double) ((float) 3.1415926535897932384626433832795028841971693993751 *
-                          (2.0f - 1.0f / sg));
+      c->b[t] = c->window == NFFTCU_WINDOW_GAUSSIAN
+                    ? (double) ((2.0f * sg) / (2.0f * sg - 1.0f) * ((float) m / (float) kPi))
+                    : (double) ((float) kPi * (2.0f - 1.0f / sg));
     }
   }
   cudaDeviceProp prop;
@@ -349,16 +355,28 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
   for (int i = 0; i < 4; i++) NFFTCU_CUDA(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < 2; i++) NFFTCU_CUDA(cudaEventCreate(&c->evk[i]));
 
-  // c_t[k+N/2] = 1/I0(m sqrt(b^2 - (2 pi k/n)^2)), k = -N/2..  (precompute_phi_hut, nfft.c:5754-5770)
+  // c_t[k+N/2] = 1/phi_hat_t(k), k = -N/2..  (precompute_phi_hut, nfft.c:5754-5770):
+  //   Kaiser-Bessel 1/I0(m sqrt(b^2 - (2 pi k/n)^2)) (infft.h:208), Gaussian exp((pi k/n)^2 b) (infft.h:154)
   const long double two_pi = 6.283185307179586476925286766559005768394L;
   for (int t = 0; t < d; t++) {
     c->c_host[t].resize((size_t) N[t]);
     for (long long ks = 0; ks < N[t]; ks++) {
       const long double w = two_pi * (long double) (ks - N[t] / 2) / (long double) n[t];
       const long double bb = (long double) c->b[t];
-      const long double arg2 = bb * bb - w * w;
-      const long double arg = (long double) m * sqrtl(arg2 > 0 ? arg2 : 0.0L);
-      c->c_host[t][(size_t) ks] = (double) (1.0L / bessel_i0_series(arg));
+      if (c->window == NFFTCU_WINDOW_GAUSSIAN) {
+        c->c_host[t][(size_t) ks] = (double) expl(0.25L * w * w * bb);
+      } else {
+        const long double arg2 = bb * bb - w * w;
+        const long double arg = (long double) m * sqrtl(arg2 > 0 ? arg2 : 0.0L);
+        c->c_host[t][(size_t) ks] = (double) (1.0L / bessel_i0_series(arg));
+      }
+    }
+    // fp32 plans: move phi_hat_t(0) ~ 1e11 (Kaiser-Bessel, m = 6) out of the window and into c as an exact power of two
+    c->wscale[t] = 1.0;
+    if (precision == NFFTCU_FLOAT) {
+      int e = 0;
+      frexp(c->c_host[t][(size_t) (N[t] / 2)], &e);   // c(0) = f * 2^e, f in [0.5, 1)
+      c->wscale[t] = ldexp(1.0, e);
     }
     const size_t bytes = real_size(c) * (size_t) N[t];
     NFFTCU_CUDA(pool_malloc(&c->c_dev[t], bytes));
@@ -366,7 +384,8 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
       NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], c->c_host[t].data(), bytes, cudaMemcpyHostToDevice));
     } else {
       std::vector<float> tmp((size_t) N[t]);
-      for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float) c->c_host[t][i];
+      // round to float FIRST (the value the reference multiplies with), then scale exactly
+      for (size_t i = 0; i < tmp.size(); i++) tmp[i] = (float) ((double) (float) c->c_host[t][i] / c->wscale[t]);
       NFFTCU_CUDA(cudaMemcpy(c->c_dev[t], tmp.data(), bytes, cudaMemcpyHostToDevice));
     }
   }
@@ -423,6 +442,12 @@ int nfftcu_get_c_phi_inv(nfftcu_ctx *c, int t, void *out_host) {
     if (c->prec == NFFTCU_DOUBLE) ((double *) out_host)[i] = c->c_host[t][i];
     else ((float *) out_host)[i] = (float) c->c_host[t][i];
   }
+  return NFFTCU_OK;
+}
+
+int nfftcu_get_window_scale(nfftcu_ctx *c, double *scale_host) {
+  NFFTCU_TRY(check_ctx(c));
+  for (int t = 0; t < c->d; t++) scale_host[t] = c->wscale[t];
   return NFFTCU_OK;
 }
 

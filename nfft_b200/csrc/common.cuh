@@ -55,9 +55,14 @@ template <> __host__ __device__ inline float2 make_c<float>(float re, float im) 
 struct FftLine {
   int64_t len = 0;
   void *tw = nullptr;   // len complex (plan precision): exp(-2 pi i q / len)
-  int kind = 0;         // 0: len==1, 1: radix-4/2 Stockham (power of two), 2: O(len^2) table DFT, 3: mixed radix
+  int kind = 0;         // 0: len==1, 1: radix-4/2 Stockham (power of two), 2: O(len^2) table DFT, 3: mixed radix, 4: Bluestein
   int nst = 0;          // kind 3: radix per stage
   int radix[24] = {0};
+  // kind 4 (a prime factor > 61): chirp-z through a power-of-two convolution of length P >= 2 len - 1
+  int64_t blu_P = 0;
+  void *blu_chirp = nullptr;   // len complex: exp(-i pi k^2 / len)
+  void *blu_bhat = nullptr;    // P complex: DFT_P of the wrapped conjugate chirp, scaled by 1/P
+  void *blu_tw = nullptr;      // P complex: exp(-2 pi i q / P)
 };
 struct FftAxis {
   int64_t len = 0;
@@ -80,6 +85,12 @@ struct nfftcu_ctx_s {
   unsigned flags = 0;
   bool direct_only = false;           // any N_t <= m or n_t <= 2m+2 (nfft.c:5658-5664)
   double b[NFFTCU_MAX_D] = {0}, sigma[NFFTCU_MAX_D] = {0};
+  int window = NFFTCU_WINDOW_KAISER_BESSEL;   // window family (create flag NFFTCU_FLAG_GAUSSIAN)
+  // Power-of-two factor folded into the device window values of dimension t (and out of c_dev[t]): fp32 plans use
+  // 2^-round(log2 phi_hat_t(0)) so that grid values stay O(data) instead of O(1e11^d * data) -- the reference's
+  // unscaled fp32 Kaiser-Bessel adjoint overflows to inf at cfg3 (M = 1e7, positive samples).  Exact (powers of
+  // two), 1.0 for fp64 plans.
+  double wscale[NFFTCU_MAX_D] = {1, 1, 1, 1, 1, 1, 1, 1};
   std::vector<double> c_host[NFFTCU_MAX_D];   // c_phi_inv in double
   void *c_dev[NFFTCU_MAX_D] = {nullptr};      // c_phi_inv in plan precision
   void *grid = nullptr;                       // n_total complex
@@ -220,6 +231,13 @@ __device__ __forceinline__ double kb_phi(double t, double m2, double b) {
     return sin(b * r) * kInvPi / r;
   }
   return b * kInvPi;
+}
+
+// window value at distance t (grid units) for the plan's window family, times the plan's power-of-two scale:
+//   Kaiser-Bessel: kb_phi;   Gaussian (include/infft.h:154-157): exp(-t^2/b) / sqrt(pi b), b = 2 sigma/(2 sigma-1) m/pi
+__device__ __forceinline__ double window_phi(double t, double m2, double b, int window, double scale) {
+  if (window == NFFTCU_WINDOW_GAUSSIAN) return scale * exp(-t * t / b) * rsqrt(3.14159265358979323846264338327950288 * b);
+  return scale * kb_phi(t, m2, b);
 }
 
 // c = floor(x*n) evaluated in the plan's precision exactly as the reference's uo()

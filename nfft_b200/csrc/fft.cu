@@ -9,8 +9,9 @@
 // every global access is a contiguous segment of bundle*sizeof(complex) bytes.
 // Twiddles come from a per-axis table exp(-2 pi i q/len) computed on the host in long double.
 // Lengths that are not a power of two run a mixed-radix Stockham (radix 4, 2, 3, 5, 7 in registers, any
-// other prime factor <= 61 as a direct r-point stage); a length with a larger prime factor uses the O(len^2)
-// table DFT in shared memory.  An axis too long for one CTA's shared memory is split len = L1 * L2
+// other prime factor <= 61 as a direct r-point stage); a length with a larger prime factor runs Bluestein's
+// chirp-z through a power-of-two convolution inside the CTA (fft_bluestein_kernel) when the padded length fits
+// (len <= 2048 fp64 / 4096 fp32), else the O(len^2) table DFT in shared memory.  An axis too long for one CTA's shared memory is split len = L1 * L2
 // (four-step): L1-point transforms down the columns with the twiddle W_len^(l2 k1) fused into their store
 // (two-level table, one extra complex multiply), then L2-point transforms along the rows whose store
 // transposes into a second grid buffer; the two buffers are swapped afterwards.
@@ -166,6 +167,59 @@ __device__ __forceinline__ int bundle_count(const LineGeom &g, long long b) {
 }
 
 // ---- power-of-two lengths: Stockham autosort in shared memory -----------------------------------
+// radix-4 (+ one radix-2) Stockham autosort of `cnt` lines of length L = 2^log2len between two shared buffers;
+// returns the buffer that holds the result.  tw = exp(-2 pi i q / L).
+template <typename T>
+__device__ __forceinline__ typename Cplx<T>::type *pow2_stockham_smem(typename Cplx<T>::type *buf0,
+                                                                      typename Cplx<T>::type *buf1,
+                                                                      const typename Cplx<T>::type *__restrict__ tw,
+                                                                      int L, int log2len, int cnt, int pitch, int sign) {
+  typedef typename Cplx<T>::type C;
+  C *src = buf0, *dst = buf1;
+  int Ns = 1;
+  if (log2len & 1) {   // one radix-2 stage first
+    const int half = L >> 1;
+    for (int w = threadIdx.x; w < cnt * half; w += blockDim.x) {
+      const int cl = w / half, j = w - cl * half;
+      const C a = src[cl * pitch + j], bb = src[cl * pitch + j + half];
+      dst[cl * pitch + 2 * j] = cadd(a, bb);
+      dst[cl * pitch + 2 * j + 1] = csub(a, bb);
+    }
+    __syncthreads();
+    C *t = src; src = dst; dst = t;
+    Ns = 2;
+  }
+  const int quarter = L >> 2;
+  for (; Ns < L; Ns <<= 2) {
+    const int tstep = L / (Ns * 4);   // table stride: W_{4Ns} = W_L^tstep
+    for (int w = threadIdx.x; w < cnt * quarter; w += blockDim.x) {
+      const int cl = w / quarter, j = w - cl * quarter;
+      const int k = j & (Ns - 1);
+      const C *in = src + cl * pitch + j;
+      C v0 = in[0], v1 = in[quarter], v2 = in[2 * quarter], v3 = in[3 * quarter];
+      if (k) {
+        C w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
+        if (sign > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        v1 = cmul(v1, w1);
+        v2 = cmul(v2, w2);
+        v3 = cmul(v3, w3);
+      }
+      const C t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
+      C t3 = csub(v1, v3);
+      // multiply by sign*i: forward (-i): (x,y)->(y,-x); backward (+i): (x,y)->(-y,x)
+      { const T x = t3.x, y = t3.y; if (sign < 0) { t3.x = y; t3.y = -x; } else { t3.x = -y; t3.y = x; } }
+      C *out = dst + cl * pitch + ((j - k) << 2) + k;
+      out[0] = cadd(t0, t2);
+      out[Ns] = cadd(t1, t3);
+      out[2 * Ns] = csub(t0, t2);
+      out[3 * Ns] = csub(t1, t3);
+    }
+    __syncthreads();
+    C *t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kFftThreads)
 fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::type *__restrict__ out_data,
@@ -182,48 +236,7 @@ fft_stockham_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>:
   stage_lines<C, false>(data, buf0, g, b);
   __syncthreads();
 
-  C *src = buf0, *dst = buf1;
-  int Ns = 1;
-  if (log2len & 1) {   // one radix-2 stage first
-    const int half = L >> 1;
-    for (int w = threadIdx.x; w < cnt * half; w += blockDim.x) {
-      const int cl = w / half, j = w - cl * half;
-      const C a = src[cl * g.pitch + j], bb = src[cl * g.pitch + j + half];
-      dst[cl * g.pitch + 2 * j] = cadd(a, bb);
-      dst[cl * g.pitch + 2 * j + 1] = csub(a, bb);
-    }
-    __syncthreads();
-    C *t = src; src = dst; dst = t;
-    Ns = 2;
-  }
-  const int quarter = L >> 2;
-  for (; Ns < L; Ns <<= 2) {
-    const int tstep = L / (Ns * 4);   // table stride: W_{4Ns} = W_L^tstep
-    for (int w = threadIdx.x; w < cnt * quarter; w += blockDim.x) {
-      const int cl = w / quarter, j = w - cl * quarter;
-      const int k = j & (Ns - 1);
-      const C *in = src + cl * g.pitch + j;
-      C v0 = in[0], v1 = in[quarter], v2 = in[2 * quarter], v3 = in[3 * quarter];
-      if (k) {
-        C w1 = tw[k * tstep], w2 = tw[2 * k * tstep], w3 = tw[3 * k * tstep];
-        if (sign > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-        v1 = cmul(v1, w1);
-        v2 = cmul(v2, w2);
-        v3 = cmul(v3, w3);
-      }
-      const C t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3);
-      C t3 = csub(v1, v3);
-      // multiply by sign*i: forward (-i): (x,y)->(y,-x); backward (+i): (x,y)->(-y,x)
-      { const T x = t3.x, y = t3.y; if (sign < 0) { t3.x = y; t3.y = -x; } else { t3.x = -y; t3.y = x; } }
-      C *out = dst + cl * g.pitch + ((j - k) << 2) + k;
-      out[0] = cadd(t0, t2);
-      out[Ns] = cadd(t1, t3);
-      out[2 * Ns] = csub(t0, t2);
-      out[3 * Ns] = csub(t1, t3);
-    }
-    __syncthreads();
-    C *t = src; src = dst; dst = t;
-  }
+  C *src = pow2_stockham_smem<T>(buf0, buf1, tw, L, log2len, cnt, g.pitch, sign);
   stage_lines<C, true>(out_data, src, g, b, sign);
 }
 
@@ -539,6 +552,55 @@ dft_table_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::ty
   stage_lines<C, true>(out_data, buf1, g, b, sign);
 }
 
+// ---- lengths with a prime factor > 61: Bluestein (chirp-z) inside one CTA -----------------------------------------
+// X[k] = w[k] * sum_l (x[l] w[l]) conj(w)[k - l],  w[k] = exp(-i pi k^2 / L): a cyclic convolution of length
+// P = 2^p >= 2L - 1, done with the power-of-two Stockham above: a = x.w zero-padded, A = DFT_P(a), A *= Bhat
+// (= DFT_P of the wrapped conj(w), tabulated on the host in long double, 1/P folded in), y = IDFT_P(A),
+// X[k] = w[k] y[k].  The backward transform is conj(DFT(conj x)).
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads)
+fft_bluestein_kernel(typename Cplx<T>::type *__restrict__ data, typename Cplx<T>::type *__restrict__ out_data,
+                     const typename Cplx<T>::type *__restrict__ chirp, const typename Cplx<T>::type *__restrict__ bhat,
+                     const typename Cplx<T>::type *__restrict__ twP, LineGeom g, int sign, int P, int log2P) {
+  typedef typename Cplx<T>::type C;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C *buf0 = reinterpret_cast<C *>(smem_raw);
+  C *buf1 = buf0 + (size_t) g.bundle * g.pitch;
+  const int L = (int) g.len;
+  const long long b = blockIdx.x;
+  const int cnt = bundle_count<C>(g, b);
+  stage_lines<C, false>(data, buf0, g, b);
+  __syncthreads();
+  for (int w = threadIdx.x; w < cnt * P; w += blockDim.x) {
+    const int cl = w / P, k = w - cl * P;
+    C v = C{0, 0};
+    if (k < L) {
+      v = buf0[cl * g.pitch + k];
+      if (sign > 0) v.y = -v.y;
+      v = cmul(v, chirp[k]);
+    }
+    buf0[cl * g.pitch + k] = v;
+  }
+  __syncthreads();
+  C *A = pow2_stockham_smem<T>(buf0, buf1, twP, P, log2P, cnt, g.pitch, -1);
+  for (int w = threadIdx.x; w < cnt * P; w += blockDim.x) {
+    const int cl = w / P, k = w - cl * P;
+    A[cl * g.pitch + k] = cmul(A[cl * g.pitch + k], bhat[k]);
+  }
+  __syncthreads();
+  C *other = (A == buf0) ? buf1 : buf0;
+  C *y = pow2_stockham_smem<T>(A, other, twP, P, log2P, cnt, g.pitch, +1);
+  C *res = (y == buf0) ? buf1 : buf0;
+  for (int w = threadIdx.x; w < cnt * L; w += blockDim.x) {
+    const int cl = w / L, k = w - cl * L;
+    C v = cmul(y[cl * g.pitch + k], chirp[k]);
+    if (sign > 0) v.y = -v.y;
+    res[cl * g.pitch + k] = v;
+  }
+  __syncthreads();
+  stage_lines<C, true>(out_data, res, g, b, sign);
+}
+
 int ilog2_exact(long long v) {
   int l = 0;
   while ((1ll << l) < v) l++;
@@ -586,11 +648,82 @@ int upload_twiddles(const nfftcu_ctx *c, long long count, long long num_stride, 
   return NFFTCU_OK;
 }
 
+int upload_complex(const nfftcu_ctx *c, const std::vector<long double> &re, const std::vector<long double> &im, void **out) {
+  const size_t esz = 2 * real_size(c), count = re.size();
+  std::vector<unsigned char> host(esz * count);
+  for (size_t q = 0; q < count; q++) {
+    if (c->prec == NFFTCU_DOUBLE) {
+      ((double *) host.data())[2 * q] = (double) re[q];
+      ((double *) host.data())[2 * q + 1] = (double) im[q];
+    } else {
+      ((float *) host.data())[2 * q] = (float) re[q];
+      ((float *) host.data())[2 * q + 1] = (float) im[q];
+    }
+  }
+  NFFTCU_CUDA(pool_malloc(out, host.size()));
+  NFFTCU_CUDA(cudaMemcpy(*out, host.data(), host.size(), cudaMemcpyHostToDevice));
+  return NFFTCU_OK;
+}
+
+// Bluestein tables of a line of length len (host, long double): chirp w[k] = exp(-i pi k^2/len) with k^2 reduced
+// mod 2 len, and Bhat = DFT_P(b)/P for b[j] = conj(w[|j|]), |j| < len, wrapped into P points.
+int plan_bluestein(const nfftcu_ctx *c, FftLine &ln) {
+  const long long L = ln.len, P = ln.blu_P;
+  const long double pi = 3.141592653589793238462643383279502884L;
+  std::vector<long double> wr((size_t) L), wi((size_t) L), br((size_t) P, 0.0L), bi((size_t) P, 0.0L);
+  for (long long k = 0; k < L; k++) {
+    const long long r = (long long) (((__int128) k * k) % (2 * L));
+    const long double ang = pi * (long double) r / (long double) L;
+    wr[(size_t) k] = cosl(ang);
+    wi[(size_t) k] = -sinl(ang);
+  }
+  for (long long j = 0; j < L; j++) {
+    br[(size_t) j] = wr[(size_t) j];
+    bi[(size_t) j] = -wi[(size_t) j];
+    if (j) { br[(size_t) (P - j)] = wr[(size_t) j]; bi[(size_t) (P - j)] = -wi[(size_t) j]; }
+  }
+  // in-place iterative radix-2 DFT (sign -1) of b in long double
+  for (long long i = 1, j = 0; i < P; i++) {
+    long long bit = P >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(br[(size_t) i], br[(size_t) j]); std::swap(bi[(size_t) i], bi[(size_t) j]); }
+  }
+  for (long long len2 = 2; len2 <= P; len2 <<= 1) {
+    for (long long i = 0; i < P; i += len2)
+      for (long long k = 0; k < len2 / 2; k++) {
+        const long double ang = -2.0L * pi * (long double) k / (long double) len2;
+        const long double cr = cosl(ang), ci = sinl(ang);
+        const size_t u = (size_t) (i + k), v = (size_t) (i + k + len2 / 2);
+        const long double tr = br[v] * cr - bi[v] * ci, ti = br[v] * ci + bi[v] * cr;
+        br[v] = br[u] - tr; bi[v] = bi[u] - ti;
+        br[u] += tr; bi[u] += ti;
+      }
+  }
+  for (long long k = 0; k < P; k++) { br[(size_t) k] /= (long double) P; bi[(size_t) k] /= (long double) P; }
+  NFFTCU_TRY(upload_complex(c, wr, wi, &ln.blu_chirp));
+  NFFTCU_TRY(upload_complex(c, br, bi, &ln.blu_bhat));
+  return upload_twiddles(c, P, 1, P, &ln.blu_tw);
+}
+
 int plan_line(const nfftcu_ctx *c, long long len, FftLine &ln) {
   ln.len = len;
   if (len == 1) { ln.kind = 0; return NFFTCU_OK; }
   if (ilog2_exact(len) >= 0) ln.kind = 1;
-  else ln.kind = factorize(len, ln) ? 3 : 2;
+  else if (factorize(len, ln)) ln.kind = 3;
+  else {
+    // a prime factor > 61: Bluestein when the padded convolution (two buffers of P + 1 points) fits one CTA,
+    // else the O(len^2) table DFT
+    long long P = 1;
+    while (P < 2 * len - 1) P <<= 1;
+    if (2 * (size_t) (P + 1) * 2 * real_size(c) <= kSmemBudget) {
+      ln.kind = 4;
+      ln.blu_P = P;
+      NFFTCU_TRY(plan_bluestein(c, ln));
+    } else {
+      ln.kind = 2;
+    }
+  }
   return upload_twiddles(c, len, 1, len, &ln.tw);
 }
 
@@ -653,7 +786,7 @@ int run_pass(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *src, 
   }
   const int pad = 1;
   g.len = ln.len;
-  g.pitch = (int) ln.len + pad;
+  g.pitch = (int) (ln.kind == 4 ? ln.blu_P : ln.len) + pad;
   const size_t line_bytes = 2 * (size_t) g.pitch * sizeof(C);   // two buffers
   int pref = (int) (128 / sizeof(C));                           // 128-byte global segments
   if (g.inner == 1) pref = (int) max(1ll, min(8ll, 2048ll / ln.len));
@@ -687,6 +820,12 @@ int run_pass(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *src, 
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
     fft_mixed_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>((C *) src, (C *) dst, (const C *) ln.tw, g,
                                                                          sign, rp);
+  } else if (ln.kind == 4) {
+    NFFTCU_CUDA(cudaFuncSetAttribute(fft_bluestein_kernel<T>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
+    fft_bluestein_kernel<T><<<(unsigned) nb, kFftThreads, smem, c->stream>>>(
+        (C *) src, (C *) dst, (const C *) ln.blu_chirp, (const C *) ln.blu_bhat, (const C *) ln.blu_tw, g, sign,
+        (int) ln.blu_P, ilog2_exact(ln.blu_P));
   } else {
     NFFTCU_CUDA(cudaFuncSetAttribute(dft_table_kernel<T>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBudget));
@@ -785,7 +924,9 @@ int fft_plan_axes(nfftcu_ctx *c) {
 void fft_free_axes(nfftcu_ctx *c) {
   for (int t = 0; t < c->d; t++) {
     FftAxis &ax = c->fft[t];
-    void **ptrs[] = {&ax.whole.tw, &ax.sub1.tw, &ax.sub2.tw, &ax.twA, &ax.twB};
+    void **ptrs[] = {&ax.whole.tw, &ax.sub1.tw, &ax.sub2.tw, &ax.twA, &ax.twB,
+                     &ax.whole.blu_chirp, &ax.whole.blu_bhat, &ax.whole.blu_tw, &ax.sub1.blu_chirp, &ax.sub1.blu_bhat,
+                     &ax.sub1.blu_tw, &ax.sub2.blu_chirp, &ax.sub2.blu_bhat, &ax.sub2.blu_tw};
     for (void **p : ptrs) {
       if (*p) pool_free(*p);
       *p = nullptr;

@@ -121,7 +121,7 @@ __global__ void psi_table_kernel(const T *__restrict__ xs, T *__restrict__ table
     const T x = xs[k * geo.d + t];
     const long long u = cell_of(x, geo.n[t]) - geo.m;
     const double dist = (double) x * (double) geo.n[t] - (double) (u + l);
-    table[i] = (T) kb_phi(dist, geo.m2, geo.b[t]);
+    table[i] = (T) window_phi(dist, geo.m2, geo.b[t], geo.window, geo.ws[t]);
   }
 }
 

@@ -25,7 +25,8 @@ namespace {
 
 const long double kPiL = 3.141592653589793238462643383279502884L;
 
-long double phi_ld(long double t, long double m, long double b) {
+long double phi_ld(long double t, long double m, long double b, int window) {
+  if (window == NFFTCU_WINDOW_GAUSSIAN) return expl(-t * t / b) / sqrtl(kPiL * b);   // include/infft.h:155-156
   const long double s = m * m - t * t;
   if (s > 0) { const long double r = sqrtl(s); return sinhl(b * r) / (kPiL * r); }
   if (s < 0) { const long double r = sqrtl(-s); return sinl(b * r) / (kPiL * r); }
@@ -33,11 +34,11 @@ long double phi_ld(long double t, long double m, long double b) {
 }
 
 // monomial coefficients (in y) of the degree-p Chebyshev interpolant of f on [-1,1]
-void cheb_fit_monomial(int p, long double m, long double b, int l, std::vector<long double> &mono) {
+void cheb_fit_monomial(int p, long double m, long double b, int window, int l, std::vector<long double> &mono) {
   std::vector<long double> c((size_t) p + 1), fj((size_t) p + 1);
   for (int j = 0; j <= p; j++) {
     const long double yj = cosl(kPiL * (j + 0.5L) / (p + 1));
-    fj[(size_t) j] = phi_ld((yj + 1) / 2 + m - l, m, b);
+    fj[(size_t) j] = phi_ld((yj + 1) / 2 + m - l, m, b, window);
   }
   for (int k = 0; k <= p; k++) {
     long double s = 0;
@@ -70,12 +71,12 @@ void cheb_fit_monomial(int p, long double m, long double b, int l, std::vector<l
 // The fit depends on (precision, m, b_t) only and costs ~20 ms of long-double arithmetic: plan-per-coil callers create
 // many identical plans, so the results are cached per process.
 struct FitKey {
-  int prec, d;
+  int prec, d, window;
   long long m;
-  double b[NFFTCU_MAX_D];
+  double b[NFFTCU_MAX_D], ws[NFFTCU_MAX_D];
   bool operator==(const FitKey &o) const {
-    if (prec != o.prec || d != o.d || m != o.m) return false;
-    for (int t = 0; t < d; t++) if (b[t] != o.b[t]) return false;
+    if (prec != o.prec || d != o.d || m != o.m || window != o.window) return false;
+    for (int t = 0; t < d; t++) if (b[t] != o.b[t] || ws[t] != o.ws[t]) return false;
     return true;
   }
 };
@@ -98,8 +99,8 @@ int build_kb_poly(nfftcu_ctx *c) {
   c->kbpoly_deg = -1;
   c->kbpoly_fit = -1;
   FitKey key;
-  key.prec = c->prec; key.d = c->d; key.m = c->m;
-  for (int t = 0; t < c->d; t++) key.b[t] = c->b[t];
+  key.prec = c->prec; key.d = c->d; key.m = c->m; key.window = c->window;
+  for (int t = 0; t < c->d; t++) { key.b[t] = c->b[t]; key.ws[t] = c->wscale[t]; }
   {
     std::lock_guard<std::mutex> lock(g_fit_mutex);
     for (const FitEntry &e : g_fit_cache)
@@ -120,17 +121,18 @@ int build_kb_poly(nfftcu_ctx *c) {
     long double worst = 0;
     for (int t = 0; t < c->d; t++) {
       const long double b = (long double) c->b[t];
-      const long double peak = phi_ld(0, m, b);
+      const long double peak = phi_ld(0, m, b, c->window);
+      const long double ws = (long double) c->wscale[t];   // exact power of two, folded into the coefficients
       for (int l = 0; l < W; l++) {
         std::vector<long double> mono;
-        cheb_fit_monomial(p, m, b, l, mono);
-        for (int k = 0; k <= p; k++) coef[((size_t) t * (kKbPolyDeg + 1) + k) * W + l] = (double) mono[(size_t) k];
+        cheb_fit_monomial(p, m, b, c->window, l, mono);
+        for (int k = 0; k <= p; k++) coef[((size_t) t * (kKbPolyDeg + 1) + k) * W + l] = (double) (mono[(size_t) k] * ws);
         for (int q = 0; q <= 64; q++) {   // check the double-precision Horner value itself
           const double y = -1.0 + 2.0 * q / 64.0;
           double acc = coef[((size_t) t * (kKbPolyDeg + 1) + kKbPolyDeg) * W + l];
           for (int k = kKbPolyDeg - 1; k >= 0; k--) acc = fma(acc, y, coef[((size_t) t * (kKbPolyDeg + 1) + k) * W + l]);
-          const long double ref = phi_ld(((long double) y + 1) / 2 + m - l, m, b);
-          const long double e = fabsl((long double) acc - ref) / peak;
+          const long double ref = phi_ld(((long double) y + 1) / 2 + m - l, m, b, c->window) * ws;
+          const long double e = fabsl((long double) acc - ref) / (peak * ws);
           if (e > worst) worst = e;
         }
       }

@@ -86,8 +86,22 @@ INT X(next_power_of_2)(const INT x)
   return v;
 }
 
-INT X(get_default_window_cut_off)(void) { return DEFAULT_M; }
-const char *X(get_window_name)(void) { return "kaiserbessel"; }
+/* The reference fixes the window family at configure time (--with-window=..., include/infft.h:146-222); this build
+ * carries Kaiser-Bessel (default) and Gaussian and selects per process with NFFT_B200_WINDOW=gaussian. */
+static int gaussian_window(void)
+{
+  const char *w = getenv("NFFT_B200_WINDOW");
+  return w && (strcmp(w, "gaussian") == 0 || strcmp(w, "GAUSSIAN") == 0);
+}
+
+#ifdef NFFT_B200_SINGLE
+#define DEFAULT_M_GAUSSIAN 5   /* WINDOW_HELP_ESTIMATE_m, include/infft.h:166-172 */
+#else
+#define DEFAULT_M_GAUSSIAN 13
+#endif
+
+INT X(get_default_window_cut_off)(void) { return gaussian_window() ? DEFAULT_M_GAUSSIAN : DEFAULT_M; }
+const char *X(get_window_name)(void) { return gaussian_window() ? "gaussian" : "kaiserbessel"; }
 
 /* ---- plan <-> context ------------------------------------------------------------------------ */
 static nfftcu_ctx *ctx_of(const X(plan) *ths) { return (nfftcu_ctx*) ths->my_fftw_plan1; }
@@ -163,9 +177,11 @@ static void init_help(X(plan) *ths)
   int device = 0, ndev = 0, devs[NFFTCU_MAX_PEERS], grid_plan = 1;
   const char *dev_env = getenv("NFFT_B200_DEVICE");
   const char *devs_env = getenv("NFFT_B200_DEVICES");   /* "0,1,2,3": node-sharded over these GPUs (nfftcu_group_*) */
+  unsigned cu_flags;
 
   if (ths->d < 1 || ths->d > NFFTCU_MAX_D) X(die)("nfft_init: rank d out of range [1,8]");
   if (ths->flags & NFFT_OMP_BLOCKWISE_ADJOINT) ths->flags |= NFFT_SORT_NODES;   /* nfft.c:5955 */
+  cu_flags = ths->flags;
 
   ths->N_total = 1;
   ths->n_total = 1;
@@ -177,6 +193,7 @@ static void init_help(X(plan) *ths)
     n64[t] = ths->n[t];
   }
   if (dev_env) device = atoi(dev_env);
+  if (gaussian_window()) cu_flags |= NFFTCU_FLAG_GAUSSIAN;
   for (t = 0; t < ths->d; t++)
     if (ths->N[t] <= ths->m || ths->n[t] <= 2 * ths->m + 2) grid_plan = 0;   /* NDFT fallback plans stay on one device */
   if (devs_env && grid_plan && ths->M_total >= 1024)
@@ -194,7 +211,7 @@ static void init_help(X(plan) *ths)
   if (ndev >= 2)
   {
     /* plans the group cannot take (an FFT axis long enough to be split) fall back to the first listed device */
-    if (nfftcu_group_create(&grp, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total, ths->flags, devs, ndev)
+    if (nfftcu_group_create(&grp, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total, cu_flags, devs, ndev)
         == NFFTCU_OK)
       ctx = nfftcu_group_ctx(grp, 0);
     else
@@ -202,7 +219,7 @@ static void init_help(X(plan) *ths)
   }
   if (!grp)
     check_cu(nfftcu_create(&ctx, PRECISION, (int) ths->d, N64, n64, ths->m, ths->M_total,
-        ths->flags, device));
+        cu_flags, device));
   ths->my_fftw_plan1 = ctx;
   ths->my_fftw_plan2 = grp;
 
@@ -276,7 +293,7 @@ void X(init)(X(plan) *ths, int d, int *N, int M_total)
 {
   copy_dims(ths, d, N, NULL);
   ths->M_total = (INT) M_total;
-  ths->m = DEFAULT_M;
+  ths->m = X(get_default_window_cut_off)();
   /* defaults of the reference's OpenMP build (nfft.c:6068-6081) */
   if (d > 1)
     ths->flags = PRE_PHI_HUT | PRE_PSI | MALLOC_X | MALLOC_F_HAT | MALLOC_F | FFTW_INIT |

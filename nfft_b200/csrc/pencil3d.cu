@@ -78,6 +78,8 @@ struct TileParams {
   int m;
   int deg;          // kKbPolyDeg when the polynomial window is available, -1: closed form
   double m2, b0, b1, b2;
+  double ws0, ws1, ws2;   // power-of-two window scale per dimension
+  int window;
 };
 
 __device__ __forceinline__ int wrap_fast(long long v, int n) {
@@ -236,6 +238,7 @@ expand_nodes_kernel(T *__restrict__ rec, const T *__restrict__ xt,
           cf[k] = (l < W) ? spoly[((size_t) t * (kKbPolyDeg + 1) + k) * W + l] : 0.0;
       }
       const double bt = (t == 0) ? P.b0 : (t == 1) ? P.b1 : P.b2;
+      const double wst = (t == 0) ? P.ws0 : (t == 1) ? P.ws1 : P.ws2;
 #pragma unroll 4
       for (int i0 = 0; i0 < CF::NB; i0 += CF::IPP) {
         const int i = i0 + half;
@@ -250,7 +253,7 @@ expand_nodes_kernel(T *__restrict__ rec, const T *__restrict__ xt,
 #pragma unroll
           for (int k = kKbPolyDeg - 1; k >= 0; k--) acc = fma(acc, y, cf[k]);
         } else {
-          acc = (l < W) ? kb_phi((double) xi * (double) nt - (double) (cc - P.m + l), P.m2, bt) : 0.0;
+          acc = (l < W) ? window_phi((double) xi * (double) nt - (double) (cc - P.m + l), P.m2, bt, P.window, wst) : 0.0;
         }
         if (i < nb) {
           T *dst = rec + (kb + i) * CF::REC + vb;
@@ -632,6 +635,10 @@ TileParams make_params(const nfftcu_ctx *c) {
   P.b0 = c->b[0];
   P.b1 = c->b[1];
   P.b2 = c->b[2];
+  P.ws0 = c->wscale[0];
+  P.ws1 = c->wscale[1];
+  P.ws2 = c->wscale[2];
+  P.window = c->window;
   return P;
 }
 

@@ -34,6 +34,8 @@ struct Tile2Params {
   int NT0, NT1;
   int use_poly, deg;
   double b0, b1, m2;
+  double ws0, ws1;   // power-of-two window scale per dimension
+  int window;
 };
 
 __device__ __forceinline__ int wrap2(int v, int n) {
@@ -137,7 +139,7 @@ __device__ __forceinline__ void chunk_windows(const TS *__restrict__ xt, const t
         for (int k = P.deg - 1; k >= 0; k--) v = fma(v, y, cf[(size_t) k * P.W]);
       } else {
         const double dist = (double) x * (double) n - (double) (c - P.m + l);
-        v = kb_phi(dist, P.m2, t == 0 ? P.b0 : P.b1);
+        v = window_phi(dist, P.m2, t == 0 ? P.b0 : P.b1, P.window, t == 0 ? P.ws0 : P.ws1);
       }
     }
     if (t == 0) psi0[j * kMaxW2 + l] = v;
@@ -286,6 +288,9 @@ Tile2Params make_params2(const nfftcu_ctx *c) {
   P.deg = c->kbpoly_fit;
   P.b0 = c->b[0];
   P.b1 = c->b[1];
+  P.ws0 = c->wscale[0];
+  P.ws1 = c->wscale[1];
+  P.window = c->window;
   P.m2 = (double) c->m * (double) c->m;
   return P;
 }

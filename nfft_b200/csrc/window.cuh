@@ -12,6 +12,8 @@ struct NodeGeom {
   long long n[NFFTCU_MAX_D];
   long long stride[NFFTCU_MAX_D];   // row-major element stride of each dimension
   double b[NFFTCU_MAX_D];
+  double ws[NFFTCU_MAX_D];          // power-of-two window scale (ctx->wscale)
+  int window;                       // window family
   double m2;                        // m*m
   int d;
   int m;
@@ -24,10 +26,12 @@ inline NodeGeom make_node_geom(const nfftcu_ctx *c) {
   g.m = (int) c->m;
   g.W = 2 * (int) c->m + 2;
   g.m2 = (double) c->m * (double) c->m;
+  g.window = c->window;
   long long s = 1;
   for (int t = c->d - 1; t >= 0; t--) {
     g.n[t] = c->n[t];
     g.b[t] = c->b[t];
+    g.ws[t] = c->wscale[t];
     g.stride[t] = s;
     s *= c->n[t];
   }
@@ -49,7 +53,7 @@ __device__ __forceinline__ void warp_node_window(const T *__restrict__ xj, const
     if (table) psi[i] = table[i];
     else {
       const double dist = (double) x * (double) n - (double) (u + l);
-      psi[i] = (T) kb_phi(dist, g.m2, g.b[t]);
+      psi[i] = (T) window_phi(dist, g.m2, g.b[t], g.window, g.ws[t]);
     }
     long long idx = (u + l) % n;
     if (idx < 0) idx += n;

@@ -31,8 +31,13 @@
 #define SIZEOF_INT 4
 #define SIZEOF_LONG 8
 #define SIZEOF_LONG_LONG 8
+#ifdef ORACLE_REF_GAUSSIAN   /* --with-window=gaussian (configure.ac:239-260) */
+#define GAUSSIAN 1
+#define WINDOW_NAME gaussian
+#else
 #define KAISER_BESSEL 1
 #define WINDOW_NAME kaiserbessel
+#endif
 #define NFFT_VERSION_MAJOR 3
 #define NFFT_VERSION_MINOR 5
 #define NFFT_VERSION_PATCH 4

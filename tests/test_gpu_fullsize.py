@@ -32,6 +32,11 @@ def _inputs(N, M, precision, seed):
         x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
     fh = rng.random((NN, 2)).astype(real)
     f = rng.random((M, 2)).astype(real)
+    if precision == "float":
+        # zero-mean data in fp32: with U[0,1) samples the reference's own nfftf_adjoint overflows to inf at M = 1e7
+        # (k = 0 bin of the oversampled spectrum = sum_j f_j * phi_hat(0)^3 > FLT_MAX; see test_fp32_adjoint_...)
+        fh -= real(0.5)
+        f -= real(0.5)
     return x, fh, f
 
 
@@ -80,6 +85,30 @@ def test_cfg4_full_size_vs_reference():
     assert e_t <= 1e-12
     assert e_a <= 1e-12
     assert np.array_equal(idx, ref_idx)
+
+
+def test_fp32_adjoint_stays_finite_where_the_reference_overflows():
+    """U[0,1) samples, cfg3, fp32: the reference's nfftf_adjoint returns inf in the k = 0 bin (the unscaled
+    Kaiser-Bessel window puts phi_hat(0)^3 = 3e33 on the grid); the engine keeps phi_hat(0) out of its fp32 window as
+    an exact power of two, stays finite, and agrees with the fp64 reference to fp32 accuracy everywhere."""
+    N, n, m, M = [128] * 3, [256] * 3, 6, 10_000_000
+    rng = np.random.Generator(np.random.Philox(7))
+    x = (rng.random((M, 3)) - 0.5).astype(np.float32)
+    x = np.minimum(x, np.nextafter(np.float32(0.5), np.float32(0)))
+    f = rng.random((M, 2)).astype(np.float32)
+    outs = {}
+    for name, kw, xx, ff in (("ref32", dict(api=common.ref_api("float")), x, f),
+                             ("ref64", dict(api=common.ref_api("double")), x.astype(np.float64), f.astype(np.float64)),
+                             ("ours32", dict(precision="float"), x, f)):
+        p = Plan.init_guru(3, N, M, n, m, FLAGS3, **kw)
+        p.x[:] = xx
+        p.f.view(p.api.real)[:] = ff.ravel()
+        p.adjoint()
+        outs[name] = p.f_hat.copy()
+        p.finalize()
+    assert not np.isfinite(outs["ref32"].view(np.float32)).all()     # the documented overflow of the reference
+    assert np.isfinite(outs["ours32"].view(np.float32)).all()
+    assert rel_l2(outs["ours32"], outs["ref64"]) <= 1e-5
 
 
 def _mri_spiral(M, N):

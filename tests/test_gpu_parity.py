@@ -195,9 +195,12 @@ def test_stages(N, n, m, precision):
     assert np.allclose(eng.c_phi_inv(0), o.c_phi_inv(N[0], n[0], m), rtol=4e-16 if precision == "double" else 3e-7)
     fh_d = cabi.DeviceBuffer(fh.nbytes).upload(fh)
     f_d = cabi.DeviceBuffer(f.nbytes).upload(f)
+    # grid units of the single-stage calls: the device window carries an exact power-of-two factor S (1 in fp64)
+    S = eng.window_scale()
+    assert S == 1.0 or precision == "float"
     # D
     eng.stage_D(fh_d)
-    assert rel_l2(eng.grid_to_host(), o.stage_D(N, n, m, fh)) <= tol
+    assert rel_l2(eng.grid_to_host().astype(np.complex128) * S, o.stage_D(N, n, m, fh)) <= tol
     # F, both signs, on random data
     for sign in (-1, +1):
         eng.grid_from_host(g_in)
@@ -207,16 +210,16 @@ def test_stages(N, n, m, precision):
     eng.grid_from_host(g_in)
     eng.stage_B(f_d)
     eng.sync()
-    assert rel_l2(f_d.download(o.cplx, M), o.stage_B(N, n, m, x, g_in)) <= tol * 10
+    assert rel_l2(f_d.download(o.cplx, M).astype(np.complex128) / S, o.stage_B(N, n, m, x, g_in)) <= tol * 10
     # B^T
     f_d.upload(f)
     eng.stage_BT(f_d)
-    assert rel_l2(eng.grid_to_host(), o.stage_BT(N, n, m, x, f)) <= tol * 10
+    assert rel_l2(eng.grid_to_host().astype(np.complex128) / S, o.stage_BT(N, n, m, x, f)) <= tol * 10
     # D^T
     eng.grid_from_host(g_in)
     eng.stage_DT(fh_d)
     eng.sync()
-    assert rel_l2(fh_d.download(o.cplx, NN), o.stage_DT(N, n, m, g_in)) <= tol
+    assert rel_l2(fh_d.download(o.cplx, NN).astype(np.complex128) * S, o.stage_DT(N, n, m, g_in)) <= tol
     eng.close()
 
 
@@ -824,7 +827,12 @@ def test_cfg4_grid_subsample_and_adjointness():
 @pytest.mark.parametrize("N,n,m,M", [
     ([33], [66], 4, 500),                 # 2 * 3 * 11: radix 11 as a direct stage
     ([60], [122], 5, 500),                # 2 * 61
-    ([64], [134], 5, 500),                # 2 * 67: prime factor > 61 -> O(len^2) table DFT
+    ([64], [134], 5, 500),                # 2 * 67: prime factor > 61 -> Bluestein, P = 512
+    ([100], [254], 5, 800),               # 2 * 127 -> Bluestein, P = 512
+    ([500], [1009], 6, 2000),             # prime length -> Bluestein, P = 2048 (odd n: sigma not an integer)
+    ([1000], [2062], 6, 3000),            # 2 * 1031: Bluestein in fp32 (P = 8192), O(len^2) table DFT in fp64
+    ([40, 36], [134, 79], 4, 2000),       # Bluestein on both axes of a 2-D grid (strided and contiguous lines)
+    ([16, 20, 12], [32, 67, 24], 3, 1500),   # a Bluestein axis in the middle of a 3-D grid
     ([30, 42], [105, 90], 4, 2000),       # 3 * 5 * 7 and 2 * 3^2 * 5
     ([1000], [2100], 6, 3000),            # 2^2 * 3 * 5^2 * 7
     ([8192], [16384], 6, 5000),           # four-step, 128 x 128
