@@ -157,6 +157,36 @@ NFFT_B200_DEFINE_API(NFFT_B200_MANGLE_FLOAT, float, nfft_b200_cfloat)
 NFFT_B200_DEFINE_SOLVER_API(NFFT_B200_SOLVER_MANGLE_DOUBLE, NFFT_B200_MANGLE_DOUBLE, double, nfft_b200_cdouble)
 NFFT_B200_DEFINE_SOLVER_API(NFFT_B200_SOLVER_MANGLE_FLOAT, NFFT_B200_MANGLE_FLOAT, float, nfft_b200_cfloat)
 
+/* ---- field-inhomogeneity transforms (layout and names of include/nfft3.h:510-541, MRI_DEFINE_API; double only,
+ * like kernel/mri/mri.c) -----------------------------------------------------------------------------------------
+ * mri_inh_2d1d_* / mri_inh_3d_* of libnfft3_b200.so keep the N3 + 1 NFFTs and the PHI / PHI_HUT / cexp scaling
+ * between them on the device (nfft_b200/csrc/mri_host.c -> mri.cu); host-visible side effects of the reference
+ * (buffer replacement in the 2d1d transforms, in-place scaling of f in the 3d adjoint) are preserved. */
+typedef struct {
+  NFFT_INT N_total;
+  NFFT_INT M_total;
+  nfft_b200_cdouble *f_hat;
+  nfft_b200_cdouble *f;
+  void (*mv_trafo)(void *);
+  void (*mv_adjoint)(void *);
+  nfft_plan plan;
+  int N3;
+  double sigma3;
+  double *t;
+  double *w;
+} mri_inh_2d1d_plan;
+typedef mri_inh_2d1d_plan mri_inh_3d_plan;   /* identical member lists in the reference */
+void mri_inh_2d1d_trafo(mri_inh_2d1d_plan *ths);
+void mri_inh_2d1d_adjoint(mri_inh_2d1d_plan *ths);
+void mri_inh_2d1d_init_guru(mri_inh_2d1d_plan *ths, int *N, int M, int *n, int m, double sigma, unsigned nfft_flags,
+    unsigned fftw_flags);
+void mri_inh_2d1d_finalize(mri_inh_2d1d_plan *ths);
+void mri_inh_3d_trafo(mri_inh_3d_plan *ths);
+void mri_inh_3d_adjoint(mri_inh_3d_plan *ths);
+void mri_inh_3d_init_guru(mri_inh_3d_plan *ths, int *N, int M, int *n, int m, double sigma, unsigned nfft_flags,
+    unsigned fftw_flags);
+void mri_inh_3d_finalize(mri_inh_3d_plan *ths);
+
 /* solver flags (values of include/nfft3.h:823-829) */
 #ifndef LANDWEBER
 #define LANDWEBER (1U << 0)

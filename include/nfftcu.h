@@ -130,6 +130,24 @@ int nfftcu_adjoint_dev(nfftcu_ctx *ctx, const void *f_dev, void *f_hat_dev);
 int nfftcu_trafo_direct_dev(nfftcu_ctx *ctx, const void *f_hat_dev, void *f_dev);
 int nfftcu_adjoint_direct_dev(nfftcu_ctx *ctx, const void *f_dev, void *f_hat_dev);
 
+/* ---- batched transforms: K right-hand sides on one node set --------------------------------
+ * No reference API exists for this; the consumer is the per-coil loop of applications/mri/mri2d/
+ * reconstruct_data_2d.c:52-139 (every coil: the same trajectory, its own data).  Layout: f_hat [K][N_total],
+ * f [K][M], interleaved complex.  The node-dependent state (sort, tile binning, window images) is built once per
+ * node set and shared by all K; D, the FFT passes, the 2-D tile kernels and D^T process the K right-hand sides in
+ * one launch each (right-hand side = one more grid dimension). */
+int nfftcu_trafo_batch(nfftcu_ctx *ctx, int K, const void *f_hat_host, void *f_host);
+int nfftcu_adjoint_batch(nfftcu_ctx *ctx, int K, const void *f_host, void *f_hat_host);
+int nfftcu_trafo_batch_dev(nfftcu_ctx *ctx, int K, const void *f_hat_dev, void *f_dev);
+int nfftcu_adjoint_batch_dev(nfftcu_ctx *ctx, int K, const void *f_dev, void *f_hat_dev);
+
+/* f_dst = A_dst ( b .* (A_src^H f_src) ) with the intermediate coefficients kept in HBM: the far field of
+ * applications/fastsum/fastsum.c:1196-1220 (nfft_adjoint(&mv1); mv2.f_hat[k] = b[k] * mv1.f_hat[k]; nfft_trafo(&mv2)),
+ * which on the host-pointer API moves f_hat across PCIe three times.  src and dst: two plans with the same N on
+ * the same device (source nodes x, target nodes y); b_host: N_total complex (NULL = no multiply). */
+int nfftcu_adjoint_mul_trafo(nfftcu_ctx *src, nfftcu_ctx *dst, const void *f_src_host, const void *b_host,
+                             void *f_dst_host);
+
 /* ---- single stages on the plan's internal grid (kernel-level parity tests, profiling) ------
  * D   (nfft.c:5415-5513): grid := zero-padded, fftshifted f_hat * c
  * F   (nfft.c:5516/5557): grid := DFT(grid), sign -1 forward / +1 backward, unnormalised
@@ -222,6 +240,20 @@ nfftcu_ctx *nfftcu_group_ctx(nfftcu_group *g, int rank);                 /* the 
 /* milliseconds of the last group transform: [0] host->device copies, [1] device compute incl. the peer exchange,
  * [2] device->host copies (wall clock of the slowest device each) */
 int nfftcu_group_times(nfftcu_group *g, float ms[3]);
+
+/* ---- field-inhomogeneity transforms kept on the device ----------------------------------------
+ * Replace the host loops of kernel/mri/mri.c: mri_inh_2d1d_trafo 57-103 / _adjoint 105-150 (N3 + 1 two-dimensional
+ * NFFTs with cexp / PHI_HUT scaling of f_hat and PHI-weighted accumulation of f between them) on a 2-D plan, and
+ * mri_inh_3d_trafo 197-228 / _adjoint 230-255 (one 3-D NFFT, the window applied along the third frequency axis
+ * before and 1/PHI_HUT(N3, N3 x_j2) after) on a 3-D plan with N[2] = N3.  Double-precision plans only, window =
+ * the reference's window_funct_plan (Kaiser-Bessel, n = N3, b = pi (2 - 1/sigma3), m = the plan's m).
+ * w: N_total (2d1d) resp. N[0]*N[1] (3d) doubles; t: M doubles; x_host: the plan's nodes (M x 3); adjoint = 0: in =
+ * f_hat, out = f; adjoint = 1: in = f, out = f_hat.  f_scaled_host (3d adjoint, may be NULL) receives f / PHI_HUT,
+ * which the reference leaves in that->f. */
+int nfftcu_mri_inh_2d1d(nfftcu_ctx *ctx, int adjoint, int N3, double sigma3, const double *w_host,
+                        const double *t_host, const void *in_host, void *out_host);
+int nfftcu_mri_inh_3d(nfftcu_ctx *ctx, int adjoint, int N3, double sigma3, const double *w_host,
+                      const double *x_host, const void *in_host, void *out_host, void *f_scaled_host);
 
 /* ---- device-resident inverse-NFFT iterations --------------------------------------------------------------
  * Replaces the host loops of kernel/solver/solver.c (solver_before_loop_complex 81-125, solver_loop_one_step_complex

@@ -34,6 +34,8 @@ SYMBOLS = (
     "nfftcu_solver_create", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
     "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
     "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim",
+    "nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev",
+    "nfftcu_mri_inh_2d1d", "nfftcu_mri_inh_3d", "nfftcu_adjoint_mul_trafo",
     "nfftcu_get_sorted_slab", "nfftcu_peer_export", "nfftcu_peer_attach", "nfftcu_peer_detach",
     "nfftcu_adjoint_dev_peer", "nfftcu_peer_error", "nfftcu_peer_reduce_only",
     "nfftcu_group_create", "nfftcu_group_destroy", "nfftcu_group_set_nodes", "nfftcu_group_nodes_version",
@@ -95,6 +97,9 @@ def lib() -> C.CDLL:
         L.nfftcu_host_free.argtypes = [vp]
         L.nfftcu_host_free.restype = None
         L.nfftcu_pool_trim.restype = None
+        for name in ("nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev"):
+            getattr(L, name).argtypes = [vp, ci, vp, vp]
+        L.nfftcu_adjoint_mul_trafo.argtypes = [vp, vp, vp, vp, vp]
         L.nfftcu_get_sorted_slab.argtypes = [vp, i64, i64, vp, vp]
         L.nfftcu_peer_export.argtypes = [vp, vp]
         L.nfftcu_peer_attach.argtypes = [vp, ci, ci, vp]
@@ -246,6 +251,30 @@ class Engine:
     def adjoint(self, f): return self._host(self.L.nfftcu_adjoint, f, self.N_total)
     def trafo_direct(self, f_hat): return self._host(self.L.nfftcu_trafo_direct, f_hat, self.M)
     def adjoint_direct(self, f): return self._host(self.L.nfftcu_adjoint_direct, f, self.N_total)
+
+    # ---- K right-hand sides on one node set ([K][N_total] / [K][M]) ----
+    def trafo_batch(self, f_hat) -> np.ndarray:
+        f_hat = np.ascontiguousarray(f_hat, dtype=self.cplx).reshape(-1, self.N_total)
+        out = np.empty((f_hat.shape[0], max(self.M, 1)), dtype=self.cplx)
+        _ck(self.L.nfftcu_trafo_batch(self.ctx, f_hat.shape[0], _ptr(f_hat), _ptr(out)))
+        return out[:, : self.M]
+
+    def adjoint_batch(self, f) -> np.ndarray:
+        f = np.ascontiguousarray(f, dtype=self.cplx).reshape(-1, self.M)
+        out = np.empty((f.shape[0], self.N_total), dtype=self.cplx)
+        _ck(self.L.nfftcu_adjoint_batch(self.ctx, f.shape[0], _ptr(f), _ptr(out)))
+        return out
+
+    def trafo_batch_dev(self, K, f_hat_dev, f_dev): _ck(self.L.nfftcu_trafo_batch_dev(self.ctx, K, _ptr(f_hat_dev), _ptr(f_dev)))
+    def adjoint_batch_dev(self, K, f_dev, f_hat_dev): _ck(self.L.nfftcu_adjoint_batch_dev(self.ctx, K, _ptr(f_dev), _ptr(f_hat_dev)))
+
+    def adjoint_mul_trafo(self, dst: "Engine", f_src, b=None) -> np.ndarray:
+        """f_dst = A_dst (b .* A_self^H f_src), f_hat never leaves the device (fastsum far field)"""
+        f_src = np.ascontiguousarray(f_src, dtype=self.cplx)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=self.cplx)
+        out = np.empty(max(dst.M, 1), dtype=self.cplx)
+        _ck(self.L.nfftcu_adjoint_mul_trafo(self.ctx, dst.ctx, _ptr(f_src), _ptr(bb), _ptr(out)))
+        return out[: dst.M]
 
     # ---- device-pointer transforms (async on the plan's stream) ----
     def trafo_dev(self, f_hat_dev, f_dev): _ck(self.L.nfftcu_trafo_dev(self.ctx, _ptr(f_hat_dev), _ptr(f_dev)))

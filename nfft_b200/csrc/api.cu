@@ -112,6 +112,10 @@ bool exact_node_check() {
   return v;
 }
 
+}  // namespace
+long double bessel_i0_ld(long double x) { return bessel_i0_series(x); }   // for mri.cu
+namespace {
+
 int check_ctx(const nfftcu_ctx *c) {
   if (!c) {
     set_error("null context");
@@ -128,8 +132,8 @@ int bind_device(const nfftcu_ctx *c) {
 size_t cbytes(const nfftcu_ctx *c, long long count) { return 2 * real_size(c) * (size_t) count; }
 
 int ensure_staging(nfftcu_ctx *c) {
-  if (!c->fhat_dev && c->N_total > 0) NFFTCU_CUDA(pool_malloc(&c->fhat_dev, cbytes(c, c->N_total)));
-  if (!c->f_dev && c->M > 0) NFFTCU_CUDA(pool_malloc(&c->f_dev, cbytes(c, c->M)));
+  if (!c->fhat_dev && c->N_total > 0) NFFTCU_CUDA(pool_malloc(&c->fhat_dev, cbytes(c, c->N_total) * (size_t) c->batch_cap));
+  if (!c->f_dev && c->M > 0) NFFTCU_CUDA(pool_malloc(&c->f_dev, cbytes(c, c->M) * (size_t) c->batch_cap));
   return NFFTCU_OK;
 }
 
@@ -192,6 +196,33 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
 }
 
 }  // namespace
+
+// make room for K right-hand sides: the grid(s), the gathered-sample buffer of the spreading kernels and the
+// host-pointer staging buffers grow to K slices (contents are scratch between transforms)
+int ensure_batch(nfftcu_ctx *c, int K) {
+  if (K < 1) { set_error("batched transform: K = %d", K); return NFFTCU_EINVAL; }
+  if (K <= c->batch_cap) return NFFTCU_OK;
+  if (c->direct_only || !c->grid) { set_error("batched transform: plan has no grid (NDFT fallback plan)"); return NFFTCU_ESTATE; }
+  if (c->peer) { set_error("batched transform on a peer-attached (multi-GPU) plan is not supported"); return NFFTCU_ESTATE; }
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  const size_t gb = cbytes(c, c->n_total) * (size_t) K;
+  void *g = nullptr;
+  NFFTCU_CUDA(pool_malloc(&g, gb));
+  pool_free(c->grid);
+  c->grid = g;
+  if (c->grid2) {
+    void *g2 = nullptr;
+    NFFTCU_CUDA(pool_malloc(&g2, gb));
+    pool_free(c->grid2);
+    c->grid2 = g2;
+  }
+  if (c->f_tile) { pool_free(c->f_tile); c->f_tile = nullptr; NFFTCU_CUDA(pool_malloc(&c->f_tile, cbytes(c, c->M) * (size_t) K)); }
+  if (c->fhat_dev) { pool_free(c->fhat_dev); c->fhat_dev = nullptr; }
+  if (c->f_dev) { pool_free(c->f_dev); c->f_dev = nullptr; }
+  c->batch_cap = K;
+  return NFFTCU_OK;
+}
+
 int nodes_ready(nfftcu_ctx *c) {
   if (c->nodes_only) {   // sorter of a multi-GPU group: the reference order is all that is needed
     NFFTCU_TRY(sort_nodes(c));
@@ -226,6 +257,18 @@ int nodes_ready(nfftcu_ctx *c) {
 }
 
 namespace {
+template <typename C>
+__global__ void cmul_diag_kernel(C *__restrict__ x, const C *__restrict__ b, long long n) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const C a = x[k], bb = b[k];
+    C r;
+    r.x = bb.x * a.x - bb.y * a.y;     // b[k] * f_hat[k], operand order of fastsum.c:1206
+    r.y = bb.x * a.y + bb.y * a.x;
+    x[k] = r;
+  }
+}
+
 __global__ void differs_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                                long long words, int *flag) {
   const long long stride = (long long) gridDim.x * blockDim.x;
@@ -685,6 +728,91 @@ int nfftcu_trafo_direct(nfftcu_ctx *c, const void *f_hat_host, void *f_host) {
 }
 int nfftcu_adjoint_direct(nfftcu_ctx *c, const void *f_host, void *f_hat_host) {
   return host_transform(c, f_host, f_hat_host, 3);
+}
+
+// ---- K right-hand sides on ONE node set -----------------------------------------------------------
+// The node-dependent state -- sort, tile binning, chunk lists, window images / psi tables -- is built once and
+// serves every right-hand side; D, the FFT passes, the 2-D tile kernels and D^T take the right-hand side as one more
+// grid dimension (one launch for all K), the 3-D kernel families walk the batch launch by launch.
+int nfftcu_trafo_batch_dev(nfftcu_ctx *c, int K, const void *f_hat_dev, void *f_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(ensure_batch(c, K));
+  c->cur_batch = K;
+  const int r = trafo_dev_impl(c, f_hat_dev, f_dev);
+  c->cur_batch = 1;
+  return r;
+}
+int nfftcu_adjoint_batch_dev(nfftcu_ctx *c, int K, const void *f_dev, void *f_hat_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(ensure_batch(c, K));
+  c->cur_batch = K;
+  const int r = adjoint_dev_impl(c, f_dev, f_hat_dev);
+  c->cur_batch = 1;
+  return r;
+}
+static int host_batch(nfftcu_ctx *c, int K, const void *in_host, void *out_host, bool forward) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  NFFTCU_TRY(ensure_batch(c, K));
+  NFFTCU_TRY(ensure_staging(c));
+  const size_t in_bytes = (forward ? cbytes(c, c->N_total) : cbytes(c, c->M)) * (size_t) K;
+  const size_t out_bytes = (forward ? cbytes(c, c->M) : cbytes(c, c->N_total)) * (size_t) K;
+  void *in_dev = forward ? c->fhat_dev : c->f_dev, *out_dev = forward ? c->f_dev : c->fhat_dev;
+  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  c->cur_batch = K;
+  const int r = forward ? trafo_dev_impl(c, in_dev, out_dev) : adjoint_dev_impl(c, in_dev, out_dev);
+  c->cur_batch = 1;
+  if (r != NFFTCU_OK) return r;
+  if (out_bytes) NFFTCU_CUDA(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  return NFFTCU_OK;
+}
+int nfftcu_trafo_batch(nfftcu_ctx *c, int K, const void *f_hat_host, void *f_host) {
+  return host_batch(c, K, f_hat_host, f_host, true);
+}
+int nfftcu_adjoint_batch(nfftcu_ctx *c, int K, const void *f_host, void *f_hat_host) {
+  return host_batch(c, K, f_host, f_hat_host, false);
+}
+
+// ---- adjoint -> diagonal multiply -> trafo without leaving the device (fastsum far field) ----------
+int nfftcu_adjoint_mul_trafo(nfftcu_ctx *src, nfftcu_ctx *dst, const void *f_src_host, const void *b_host,
+                             void *f_dst_host) {
+  NFFTCU_TRY(check_ctx(src));
+  NFFTCU_TRY(check_ctx(dst));
+  if (src->prec != dst->prec || src->N_total != dst->N_total || src->device != dst->device) {
+    set_error("nfftcu_adjoint_mul_trafo: the two plans must share precision, bandwidths and device");
+    return NFFTCU_EINVAL;
+  }
+  NFFTCU_TRY(bind_device(src));
+  NFFTCU_TRY(need_nodes(src));
+  NFFTCU_TRY(need_nodes(dst));
+  NFFTCU_TRY(ensure_staging(src));
+  NFFTCU_TRY(ensure_staging(dst));
+  const size_t nb = cbytes(src, src->N_total);
+  if (src->M) NFFTCU_CUDA(cudaMemcpyAsync(src->f_dev, f_src_host, cbytes(src, src->M), cudaMemcpyHostToDevice, src->stream));
+  if (b_host) NFFTCU_CUDA(cudaMemcpyAsync(dst->fhat_dev, b_host, nb, cudaMemcpyHostToDevice, src->stream));   // b parks in dst's staging
+  NFFTCU_TRY(adjoint_dev_impl(src, src->f_dev, src->fhat_dev));
+  if (b_host) {
+    long long blocks = (src->N_total + 255) / 256;
+    if (blocks > (long long) src->sm_count * 16) blocks = (long long) src->sm_count * 16;
+    if (src->prec == NFFTCU_DOUBLE)
+      cmul_diag_kernel<double2><<<(unsigned) blocks, 256, 0, src->stream>>>((double2 *) src->fhat_dev, (const double2 *) dst->fhat_dev, src->N_total);
+    else
+      cmul_diag_kernel<float2><<<(unsigned) blocks, 256, 0, src->stream>>>((float2 *) src->fhat_dev, (const float2 *) dst->fhat_dev, src->N_total);
+    src->launches++;
+    NFFTCU_CUDA(cudaGetLastError());
+  }
+  // hand over from the source plan's stream to the target plan's
+  if (!src->ev_side) NFFTCU_CUDA(cudaEventCreateWithFlags(&src->ev_side, cudaEventDisableTiming));
+  NFFTCU_CUDA(cudaEventRecord(src->ev_side, src->stream));
+  NFFTCU_CUDA(cudaStreamWaitEvent(dst->stream, src->ev_side, 0));
+  NFFTCU_TRY(trafo_dev_impl(dst, src->fhat_dev, dst->f_dev));
+  if (dst->M) NFFTCU_CUDA(cudaMemcpyAsync(f_dst_host, dst->f_dev, cbytes(dst, dst->M), cudaMemcpyDeviceToHost, dst->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(dst->stream));
+  return NFFTCU_OK;
 }
 
 int nfftcu_trafo_dev(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {

@@ -93,7 +93,9 @@ struct nfftcu_ctx_s {
   double wscale[NFFTCU_MAX_D] = {1, 1, 1, 1, 1, 1, 1, 1};
   std::vector<double> c_host[NFFTCU_MAX_D];   // c_phi_inv in double
   void *c_dev[NFFTCU_MAX_D] = {nullptr};      // c_phi_inv in plan precision
-  void *grid = nullptr;                       // n_total complex
+  void *grid = nullptr;                       // batch_cap x n_total complex (slice 0 serves the single transforms)
+  int batch_cap = 1;                          // right-hand sides the grid / staging buffers can hold (nfftcu_*_batch)
+  int cur_batch = 1;                          // right-hand sides of the transform in flight: every stage reads it
   void *grid2 = nullptr;                      // second buffer, only for plans with a split (four-step) FFT axis
   bool fft_no_prune = false;                  // a split axis runs unpruned passes
   nfftcu::FftAxis fft[NFFTCU_MAX_D];
@@ -213,6 +215,7 @@ void *peer_slice_ptr(nfftcu_ctx *c, long long *k_begin, long long *k_end);   // 
 int create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n, int64_t m, int64_t M,
                unsigned flags, int device, bool nodes_only);        // api.cu
 int nodes_ready(nfftcu_ctx *c);                                     // api.cu
+int ensure_batch(nfftcu_ctx *c, int K);                             // api.cu: grow grid / f_tile for K right-hand sides
 uint64_t fingerprint(const void *data, size_t bytes);               // api.cu
 
 // ---- Kaiser-Bessel window, evaluated in double for both precisions ----------------------------

@@ -26,8 +26,10 @@ template <typename T> struct CPtrs { const T *c[NFFTCU_MAX_D]; };
 template <typename T>
 __global__ void deconv_pad_kernel(const typename Cplx<T>::type *__restrict__ f_hat,
                                   typename Cplx<T>::type *__restrict__ g, DGeom geo, CPtrs<T> cp,
-                                  long long n_total) {
+                                  long long n_total, long long N_total) {
   typedef typename Cplx<T>::type C;
+  f_hat += (size_t) blockIdx.y * N_total;   // right-hand side blockIdx.y of a batched transform
+  g += (size_t) blockIdx.y * n_total;
   const long long stride = (long long) gridDim.x * blockDim.x;
   for (long long gi = (long long) blockIdx.x * blockDim.x + threadIdx.x; gi < n_total; gi += stride) {
     long long rem = gi;
@@ -60,8 +62,10 @@ __global__ void deconv_pad_kernel(const typename Cplx<T>::type *__restrict__ f_h
 template <typename T>
 __global__ void deconv_crop_kernel(const typename Cplx<T>::type *__restrict__ g,
                                    typename Cplx<T>::type *__restrict__ f_hat, DGeom geo,
-                                   CPtrs<T> cp, long long N_total) {
+                                   CPtrs<T> cp, long long N_total, long long n_total) {
   typedef typename Cplx<T>::type C;
+  f_hat += (size_t) blockIdx.y * N_total;
+  g += (size_t) blockIdx.y * n_total;
   const long long stride = (long long) gridDim.x * blockDim.x;
   for (long long kl = (long long) blockIdx.x * blockDim.x + threadIdx.x; kl < N_total; kl += stride) {
     long long rem = kl;
@@ -88,8 +92,10 @@ __global__ void deconv_crop_kernel(const typename Cplx<T>::type *__restrict__ g,
 template <typename T>
 __global__ void deconv_band_kernel(const typename Cplx<T>::type *__restrict__ f_hat,
                                    typename Cplx<T>::type *__restrict__ g, DGeom geo, CPtrs<T> cp,
-                                   long long N_total) {
+                                   long long N_total, long long n_total) {
   typedef typename Cplx<T>::type C;
+  f_hat += (size_t) blockIdx.y * N_total;
+  g += (size_t) blockIdx.y * n_total;
   const long long stride = (long long) gridDim.x * blockDim.x;
   for (long long kl = (long long) blockIdx.x * blockDim.x + threadIdx.x; kl < N_total; kl += stride) {
     long long rem = kl;
@@ -128,18 +134,16 @@ int run(nfftcu_ctx *c, const void *f_hat_in, void *f_hat_out, bool transposed, b
   const long long cap = (long long) c->sm_count * 16;   // grid-stride above 16 resident CTAs/SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  const dim3 grid((unsigned) blocks, (unsigned) c->cur_batch);   // y: right-hand sides of a batched transform
   if (!transposed && band_only)
-    deconv_band_kernel<T><<<(unsigned) blocks, threads, 0, c->stream>>>((const C *) f_hat_in,
-                                                                       (C *) c->grid, geo, cp,
-                                                                       c->N_total);
+    deconv_band_kernel<T><<<grid, threads, 0, c->stream>>>((const C *) f_hat_in, (C *) c->grid, geo, cp, c->N_total,
+                                                          c->n_total);
   else if (!transposed)
-    deconv_pad_kernel<T><<<(unsigned) blocks, threads, 0, c->stream>>>((const C *) f_hat_in,
-                                                                      (C *) c->grid, geo, cp,
-                                                                      c->n_total);
+    deconv_pad_kernel<T><<<grid, threads, 0, c->stream>>>((const C *) f_hat_in, (C *) c->grid, geo, cp, c->n_total,
+                                                         c->N_total);
   else
-    deconv_crop_kernel<T><<<(unsigned) blocks, threads, 0, c->stream>>>((const C *) c->grid,
-                                                                       (C *) f_hat_out, geo, cp,
-                                                                       c->N_total);
+    deconv_crop_kernel<T><<<grid, threads, 0, c->stream>>>((const C *) c->grid, (C *) f_hat_out, geo, cp, c->N_total,
+                                                          c->n_total);
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;

@@ -846,6 +846,10 @@ int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
   long long inner = 1, outer_full = 1;
   for (int t2 = t + 1; t2 < c->d; t2++) inner *= c->n[t2];
   for (int s2 = 0; s2 < t; s2++) outer_full *= c->n[s2];
+  // a batched transform (nfftcu_*_batch): the grid is [K][n_0]...[n_{d-1}], the right-hand side is one more
+  // (unpruned) axis in front of all others
+  const long long K = c->cur_batch;
+  outer_full *= K;
   if (ax.split) {
     // column pass: [outer][L1][L2 * inner], transform over L1, twiddle at the store, in place
     const long long L1 = ax.sub1.len, L2 = ax.sub2.len;
@@ -871,13 +875,20 @@ int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
   }
   g.inner = inner;
   g.prune = pruned ? (sign < 0 ? 1 : 2) : 0;
-  g.nouter = t;
   long long outer = 1;
+  int o0 = 0;
+  if (K > 1) {
+    if (t + 1 > NFFTCU_MAX_D) { set_error("batched FFT: d = %d leaves no room for the batch axis", c->d); return NFFTCU_EINVAL; }
+    g.oN[0] = g.olow[0] = g.on[0] = K;
+    outer = K;
+    o0 = 1;
+  }
+  g.nouter = t + o0;
   for (int s2 = 0; s2 < t; s2++) {
-    g.oN[s2] = pruned ? c->N[s2] : c->n[s2];
-    g.olow[s2] = pruned ? c->N[s2] - c->N[s2] / 2 : c->n[s2];
-    g.on[s2] = c->n[s2];
-    outer *= g.oN[s2];
+    g.oN[o0 + s2] = pruned ? c->N[s2] : c->n[s2];
+    g.olow[o0 + s2] = pruned ? c->N[s2] - c->N[s2] / 2 : c->n[s2];
+    g.on[o0 + s2] = c->n[s2];
+    outer *= g.oN[o0 + s2];
   }
   g.elow = c->N[t] - c->N[t] / 2;
   g.ehigh = c->n[t] - c->N[t] / 2;

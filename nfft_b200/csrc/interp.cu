@@ -154,8 +154,23 @@ int run_generic(nfftcu_ctx *c, void *f_dev) {
 
 int stage_B(nfftcu_ctx *c, void *f_dev) {
   if (c->M == 0) return NFFTCU_OK;
+  if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_interp(c, f_dev);   // batch = gridDim.y
+  if (c->cur_batch > 1) {
+    // the other kernel families take one right-hand side per launch: walk the batch with the grid pointer moved
+    const int K = c->cur_batch;
+    const size_t C = 2 * real_size(c);
+    char *g0 = (char *) c->grid;
+    int r = NFFTCU_OK;
+    c->cur_batch = 1;
+    for (int k = 0; k < K && r == NFFTCU_OK; k++) {
+      c->grid = g0 + C * (size_t) c->n_total * k;
+      r = stage_B(c, (char *) f_dev + C * (size_t) c->M * k);
+    }
+    c->grid = g0;
+    c->cur_batch = K;
+    return r;
+  }
   if (c->mma_ready) return mma3d_interp(c, f_dev);
-  if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_interp(c, f_dev);
   if (c->tile_ready && c->opt_b_kernel != 1) return tile3d_interp(c, f_dev);
   if (!c->ref_sorted) {
     set_error("stage_B: generic kernel needs the reference node order (set NFFTCU_OPT_B_KERNEL before set_nodes)");

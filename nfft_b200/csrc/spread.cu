@@ -133,7 +133,22 @@ int run_generic(nfftcu_ctx *c, const void *f_dev) {
 }  // namespace
 
 int stage_BT(nfftcu_ctx *c, const void *f_dev) {
-  NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, 2 * real_size(c) * (size_t) c->n_total, c->stream));
+  if (c->cur_batch > 1 && !(c->tile2_ready && c->opt_b_kernel != 1)) {
+    // kernel families without a batch dimension: one right-hand side per launch, grid pointer moved along the batch
+    const int K = c->cur_batch;
+    const size_t C = 2 * real_size(c);
+    char *g0 = (char *) c->grid;
+    int r = NFFTCU_OK;
+    c->cur_batch = 1;
+    for (int k = 0; k < K && r == NFFTCU_OK; k++) {
+      c->grid = g0 + C * (size_t) c->n_total * k;
+      r = stage_BT(c, (const char *) f_dev + C * (size_t) c->M * k);
+    }
+    c->grid = g0;
+    c->cur_batch = K;
+    return r;
+  }
+  NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, 2 * real_size(c) * (size_t) c->n_total * (size_t) c->cur_batch, c->stream));
   if (c->M == 0) return NFFTCU_OK;
   if (c->mma_ready) return mma3d_spread(c, f_dev);
   if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_spread(c, f_dev);

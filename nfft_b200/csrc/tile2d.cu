@@ -109,7 +109,8 @@ template <typename C2>
 __global__ void tile2_gather_f_kernel(const C2 *__restrict__ f, const uint32_t *__restrict__ perm, C2 *__restrict__ ft,
                                       long long M) {
   const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < M) ft[k] = f[perm[k]];
+  const size_t off = (size_t) blockIdx.y * (size_t) M;   // right-hand side of a batched transform
+  if (k < M) ft[off + k] = f[off + perm[k]];
 }
 
 // shared memory: tile [F][pitch] double2 | psi0 [kChunkNodes][kMaxW2] double | psi1 (interp: double, spread: double2)
@@ -161,8 +162,11 @@ template <typename TS>
 __global__ void __launch_bounds__(kThreads2)
 interp_tile2_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                     const uint32_t *__restrict__ perm, typename Cplx<TS>::type *__restrict__ f,
-                    const uint4 *__restrict__ chunks, const double *__restrict__ poly, Tile2Params P) {
+                    const uint4 *__restrict__ chunks, const double *__restrict__ poly, Tile2Params P,
+                    long long gstride, long long fstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  G += (size_t) blockIdx.y * gstride;   // right-hand side blockIdx.y of a batched transform
+  f += (size_t) blockIdx.y * fstride;
   double2 *tile = reinterpret_cast<double2 *>(smem_raw);
   double *psi0 = reinterpret_cast<double *>(tile + (size_t) P.F * P.pitch);
   double *psi1 = psi0 + kChunkNodes * kMaxW2;
@@ -224,8 +228,10 @@ template <typename TS>
 __global__ void __launch_bounds__(kThreads2)
 spread_tile2_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restrict__ xt,
                     const typename Cplx<TS>::type *__restrict__ ft, const uint4 *__restrict__ chunks,
-                    const double *__restrict__ poly, Tile2Params P) {
+                    const double *__restrict__ poly, Tile2Params P, long long gstride, long long fstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  G += (size_t) blockIdx.y * gstride;
+  ft += (size_t) blockIdx.y * fstride;
   double2 *tile = reinterpret_cast<double2 *>(smem_raw);
   double *psi0 = reinterpret_cast<double *>(tile + (size_t) P.F * P.pitch);
   double *psi1 = psi0 + kChunkNodes * kMaxW2;                       // (psi1 * f) complex
@@ -304,8 +310,8 @@ template <typename TS>
 int run2(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
   typedef typename Cplx<TS>::type C2;
   const Tile2Params P = make_params2(c);
-  const unsigned grid = (unsigned) c->mma_nchunks;
-  if (grid == 0) return NFFTCU_OK;
+  const dim3 grid((unsigned) c->mma_nchunks, (unsigned) c->cur_batch);
+  if (grid.x == 0) return NFFTCU_OK;
   const size_t smem = smem2(P, spread);
   const uint4 *chunks = (const uint4 *) c->mma_chunks;
   const double *poly = (const double *) c->kbpoly_dev;
@@ -313,17 +319,17 @@ int run2(nfftcu_ctx *c, const void *f_in, void *f_out, bool spread) {
     NFFTCU_CUDA(cudaFuncSetAttribute(interp_tile2_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     interp_tile2_kernel<TS><<<grid, kThreads2, smem, c->stream>>>((const C2 *) c->grid, (const TS *) c->tile_x, c->tile_perm,
-                                                                 (C2 *) f_out, chunks, poly, P);
+                                                                 (C2 *) f_out, chunks, poly, P, c->n_total, c->M);
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches++;
   } else {
     const int kb = 256;
-    tile2_gather_f_kernel<C2><<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>((const C2 *) f_in, c->tile_perm,
-                                                                                      (C2 *) c->f_tile, c->M);
+    tile2_gather_f_kernel<C2><<<dim3((unsigned) ((c->M + kb - 1) / kb), grid.y), kb, 0, c->stream>>>(
+        (const C2 *) f_in, c->tile_perm, (C2 *) c->f_tile, c->M);
     NFFTCU_CUDA(cudaFuncSetAttribute(spread_tile2_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
     spread_tile2_kernel<TS><<<grid, kThreads2, smem, c->stream>>>((C2 *) c->grid, (const TS *) c->tile_x,
-                                                                 (const C2 *) c->f_tile, chunks, poly, P);
+                                                                 (const C2 *) c->f_tile, chunks, poly, P, c->n_total, c->M);
     if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
     c->launches += 2;
   }
@@ -352,7 +358,7 @@ int tile2d_bin_nodes(nfftcu_ctx *c) {
   if (!c->tile_keys) NFFTCU_CUDA(pool_malloc(&c->tile_keys, sizeof(uint64_t) * (size_t) M));
   if (!c->tile_perm) NFFTCU_CUDA(pool_malloc((void **) &c->tile_perm, sizeof(uint32_t) * (size_t) M));
   if (!c->tile_x) NFFTCU_CUDA(pool_malloc(&c->tile_x, real_size(c) * (size_t) M * 2));
-  if (!c->f_tile) NFFTCU_CUDA(pool_malloc(&c->f_tile, 2 * real_size(c) * (size_t) M));
+  if (!c->f_tile) NFFTCU_CUDA(pool_malloc(&c->f_tile, 2 * real_size(c) * (size_t) M * (size_t) c->batch_cap));
   if (!c->bin_start || c->tile_nbins != tiles) {
     if (c->bin_start) pool_free(c->bin_start);
     if (c->mma_counts) pool_free(c->mma_counts);

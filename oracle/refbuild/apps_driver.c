@@ -19,8 +19,10 @@
 
 #include "config.h"
 #include "nfft3.h"
+#ifndef APPS_MRI_ONLY   /* libapps_dev_b200.so: only the mri drivers, on the product's own device-resident mri_inh_* */
 #include "fastsum.h"
 #include "kernels.h"
+#endif
 
 /* mri_inh_2d1d: f = trafo(f_hat) then f_hat_adj = adjoint(f_in) on the same plan.
  * N = {N0, N1, N3}, n = {n0, n1, N3}; x: M x 2, t: M, w: N0*N1. */
@@ -68,6 +70,7 @@ int apps_mri_inh_3d(const int *N, int M, const int *n, int m, double sigma, unsi
   return 0;
 }
 
+#ifndef APPS_MRI_ONLY
 /* fastsum: f(y_j) = sum_k alpha_k K(|y_j - x_k|); kernel_id: 0 gaussian, 1 multiquadric, 2 one_over_x,
  * 3 inverse_multiquadric.  f_exact may be NULL (direct sum skipped). */
 int apps_fastsum(int d, int N_total, int M_total, int nn, int m, int p, int kernel_id, double c,
@@ -94,3 +97,4 @@ int apps_fastsum(int d, int N_total, int M_total, int nn, int m, int p, int kern
   fastsum_finalize(&fs);
   return 0;
 }
+#endif /* APPS_MRI_ONLY */
