@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <thread>
 
 namespace nfftcu {
@@ -332,8 +333,74 @@ int nfftcu_create(nfftcu_ctx **out, int precision, int d, const int64_t *N, cons
 
 }  // extern "C"
 
+// ---- plan cache: finalized plans parked for the next identical nfft_init ------------------------------------------
+// Plan-per-coil callers (applications/mri/mri2d/reconstruct_data_2d.c:38-139; BASELINE configs[4]) run
+// nfft_init_guru -> x -> nfft_precompute_one_psi -> solver -> nfft_finalize once per coil, every time with the same
+// geometry and the SAME nodes.  A finalized plan is therefore parked (at most kPlanCacheSlots, small plans only)
+// and handed out again by the next create with an identical key; its resident nodes keep their fingerprint, so the
+// following set_nodes on an unchanged x is a no-op and the sort / binning / window tables are reused -- the
+// "many vectors, one node set" sharing of SURVEY 8f rank 2 for callers that cannot use the batch API.
+// NFFT_B200_PLAN_CACHE=0 disables it; nfftcu_pool_trim() empties it.
+namespace nfftcu {
+namespace {
+constexpr int kPlanCacheSlots = 2;
+std::mutex g_plan_cache_mu;
+std::vector<nfftcu_ctx *> g_plan_cache;
+
+bool plan_cache_enabled() {
+  static const bool v = [] { const char *e = getenv("NFFT_B200_PLAN_CACHE"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+bool same_plan(const nfftcu_ctx *c, int precision, int d, const int64_t *N, const int64_t *n, int64_t m, int64_t M,
+               unsigned flags, int device, bool nodes_only) {
+  const int window = (flags & NFFTCU_FLAG_GAUSSIAN) ? NFFTCU_WINDOW_GAUSSIAN : NFFTCU_WINDOW_KAISER_BESSEL;
+  if (c->prec != precision || c->d != d || c->m != m || c->M != M || c->flags != (flags & ~NFFTCU_FLAG_GAUSSIAN) ||
+      c->device != device || c->nodes_only != nodes_only || c->window != window)
+    return false;
+  for (int t = 0; t < d; t++)
+    if (c->N[t] != N[t] || c->n[t] != n[t]) return false;
+  return true;
+}
+size_t plan_device_bytes(const nfftcu_ctx *c) {   // rough: what parking this plan keeps allocated
+  const size_t r = real_size(c);
+  return 2 * r * (size_t) c->n_total * (size_t) c->batch_cap * (c->grid2 ? 2 : 1) + c->mma_images_bytes +
+         (size_t) c->M * (size_t) (r * c->d * 4 + 48);
+}
+}  // namespace
+void plan_cache_clear() {
+  std::vector<nfftcu_ctx *> victims;
+  {
+    std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+    victims.swap(g_plan_cache);
+  }
+  for (nfftcu_ctx *c : victims) { c->no_cache = true; nfftcu_destroy(c); }
+}
+}  // namespace nfftcu
+
 int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N, const int64_t *n,
                        int64_t m, int64_t M, unsigned flags, int device, bool nodes_only) {
+  if (out && N && n && d >= 1 && d <= NFFTCU_MAX_D && plan_cache_enabled()) {
+    std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+    for (size_t i = 0; i < g_plan_cache.size(); i++)
+      if (same_plan(g_plan_cache[i], precision, d, N, n, m, M, flags, device, nodes_only)) {
+        nfftcu_ctx *c = g_plan_cache[i];
+        g_plan_cache.erase(g_plan_cache.begin() + (long) i);
+        // a revived plan starts with the defaults a new one has; its node state (and fingerprint) is kept
+        c->opt_timing = 0;
+        c->opt_psi_table = 0;
+        c->opt_b_flush = 0;
+        c->opt_fft_prune = 1;
+        c->cur_batch = 1;
+        // to its new owner the plan has no nodes yet; the parked ones are adopted by the first nfftcu_set_nodes
+        // whose host array has the same fingerprint
+        c->parked_nodes = c->have_nodes && c->x_fp_valid;
+        c->have_nodes = false;
+        c->nodes_version = 0;
+        c->launches = 0;
+        *out = c;
+        return NFFTCU_OK;
+      }
+  }
   if (!out || !N || !n || d < 1 || d > NFFTCU_MAX_D || m < 0 || M < 0 ||
       (precision != NFFTCU_DOUBLE && precision != NFFTCU_FLOAT)) {
     set_error("nfftcu_create: invalid argument (d=%d, m=%lld, M=%lld, precision=%d)", d,
@@ -455,6 +522,24 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   if (!c) return NFFTCU_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  // park small, plain plans for the next identical create (see "plan cache" above)
+  if (!c->no_cache && plan_cache_enabled() && !c->peer && c->own_stream && !c->direct_only &&
+      c->opt_b_kernel == 0 && c->opt_node_order == 0 && c->opt_fft_kernel == 0 && c->opt_window_images == 0 &&
+      plan_device_bytes(c) <= ((size_t) 1 << 30)) {
+    nfftcu_ctx *evict = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_plan_cache_mu);
+      g_plan_cache.push_back(c);
+      if (g_plan_cache.size() > (size_t) kPlanCacheSlots) {
+        evict = g_plan_cache.front();
+        g_plan_cache.erase(g_plan_cache.begin());
+      }
+    }
+    if (!evict) return NFFTCU_OK;
+    c = evict;
+    c->no_cache = true;
+    cudaSetDevice(c->device);
+  }
   peer_detach(c);
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
@@ -518,11 +603,20 @@ int nfftcu_set_nodes(nfftcu_ctx *c, const void *x_host) {
   const size_t xbytes = real_size(c) * (size_t) c->M * c->d;
   uint64_t fp = 0;
   bool have_fp = false;
-  if (c->have_nodes && c->x_fp_valid && !exact_node_check()) {
+  if ((c->have_nodes || c->parked_nodes) && c->x_fp_valid && !exact_node_check()) {
     fp = fingerprint(x_host, xbytes);
     have_fp = true;
-    if (fp == c->x_fp) return NFFTCU_OK;   // same nodes as the resident ones: nothing to upload, nothing to sort
+    if (fp == c->x_fp) {   // same nodes as the resident ones: nothing to upload, nothing to sort
+      if (c->parked_nodes) {   // a revived plan (plan cache) adopts the node state its predecessor left
+        c->parked_nodes = false;
+        c->have_nodes = true;
+        c->nodes_version++;
+      }
+      return NFFTCU_OK;
+    }
+    have_fp = c->have_nodes;   // parked nodes that do not match: a fresh upload, nothing to swap with
   }
+  c->parked_nodes = false;
   bool changed = true;
   if (have_fp) {   // known to differ: upload straight into the resident buffer's partner and swap
     if (xbytes) {
@@ -544,6 +638,7 @@ int nfftcu_set_nodes_dev(nfftcu_ctx *c, const void *x_dev) {
   NFFTCU_TRY(check_ctx(c));
   NFFTCU_TRY(bind_device(c));
   bool changed = true;
+  c->parked_nodes = false;
   NFFTCU_TRY(stage_and_compare(c, x_dev, cudaMemcpyDefault, &changed, nullptr));   // x_dev may live on a peer device
   c->x_fp_valid = false;   // no host array to fingerprint: transforms with a node refresh compare on the device
   if (changed) NFFTCU_TRY(nodes_ready(c));
@@ -968,7 +1063,7 @@ void nfftcu_host_free(void *p) {
   if (pool_owns_host(p)) pool_free_host(p);
   else free(p);
 }
-void nfftcu_pool_trim(void) { pool_trim(); }
+void nfftcu_pool_trim(void) { plan_cache_clear(); pool_trim(); }
 
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
   NFFTCU_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));

@@ -114,6 +114,7 @@ struct nfftcu_ctx_s {
   bool psi_table_valid = false;     // table was built for the current nodes (nodes_ready clears it)
   uint64_t x_fp = 0;                // fingerprint of the HOST array the resident nodes were uploaded from
   bool x_fp_valid = false;
+  bool parked_nodes = false;        // revived from the plan cache: node state of the previous owner, not yet adopted
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;
   bool tile2_ready = false;         // tile_* hold the tile order of the 2-D kernels (tile2d.cu)
@@ -149,6 +150,7 @@ struct nfftcu_ctx_s {
 
   nfftcu::PeerState *peer = nullptr;   // fused D^T + cross-GPU reduce (peer.cu)
   bool nodes_only = false;             // sorter of a multi-GPU group: no grid, no FFT plan, never transforms
+  bool no_cache = false;               // nfftcu_destroy really destroys (plan cache eviction / trim)
 
   // staging buffers for the host-pointer API
   void *fhat_dev = nullptr;
@@ -217,6 +219,7 @@ int create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N, const i
 int nodes_ready(nfftcu_ctx *c);                                     // api.cu
 int ensure_batch(nfftcu_ctx *c, int K);                             // api.cu: grow grid / f_tile for K right-hand sides
 uint64_t fingerprint(const void *data, size_t bytes);               // api.cu
+void plan_cache_clear();                                            // api.cu
 
 // ---- Kaiser-Bessel window, evaluated in double for both precisions ----------------------------
 // phi(t) with t = n*(x - l/n) the distance in grid units, s = m^2 - t^2:

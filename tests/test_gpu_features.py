@@ -101,6 +101,8 @@ def test_batched_transforms_vs_independent_plans(case, K, precision):
     """nfftcu_trafo_batch / nfftcu_adjoint_batch with K right-hand sides on one node set against K independent
     transforms of the oracle (= K reference plans with the same nodes)."""
     spec = BATCH_CASES[case]
+    if precision == "float" and spec["d"] == 3 and spec["m"] > 6:
+        pytest.skip("the fp32 checker itself overflows: psi^3 ~ (sinh(8 b)/(8 pi))^3 > FLT_MAX for m = 8 in 3-D")
     x, _, _ = make_case(spec, precision)
     rng = np.random.default_rng(spec["seed"] + K)
     NN, M = int(np.prod(spec["N"])), spec["M"]
@@ -192,3 +194,35 @@ def test_adjoint_mul_trafo_vs_oracle(d, N, n, m, Ms, Mt, precision):
     src.close()
     dst.close()
     assert rel_l2(got, want) <= (1e-12 if precision == "double" else 2e-5)
+
+
+# ---- plan cache: plan-per-coil life cycles reuse the node state of the previous identical plan ---------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_plan_cache_reuses_nodes_and_stays_correct(precision):
+    """init -> x -> precompute -> trafo -> finalize, three times with the same geometry: same nodes (node state of the
+    parked plan adopted, index_x still delivered), then different nodes (full rebuild); every result against the
+    oracle.  A fresh plan must still refuse to transform before it was given nodes."""
+    spec = dict(d=2, N=[64, 64], n=[128, 128], m=6, M=20000, seed=81)
+    flags = BASE | abi.PRE_PSI | abi.NFFT_SORT_NODES
+    x, fh, f = make_case(spec, precision)
+    x2 = np.ascontiguousarray(x[::-1])
+    o = common.oracle(precision)
+    for xx in (x, x, x2, x):
+        p = Plan.init_guru(2, spec["N"], spec["M"], spec["n"], 6, flags, precision=precision)
+        p.x[:] = xx
+        p.precompute_one_psi()
+        p.f_hat[:] = fh
+        p.trafo()
+        assert rel_l2(p.f, o.trafo(spec["N"], spec["n"], 6, xx, fh)) <= TOL[precision]
+        p.f[:] = f
+        p.adjoint()
+        assert rel_l2(p.f_hat, o.adjoint(spec["N"], spec["n"], 6, xx, f, True)) <= TOL[precision]
+        assert np.array_equal(p.index_x, o.sort_nodes(spec["n"], 6, xx))
+        p.finalize()
+    eng = cabi.Engine(spec["N"], spec["n"], 6, spec["M"], precision=precision, flags=flags)   # revived from the cache
+    with pytest.raises(cabi.NfftCuError):
+        eng.trafo(fh)            # "transform called before nfftcu_set_nodes": parked nodes are not this plan's nodes
+    eng.set_nodes(x2)
+    assert rel_l2(eng.trafo(fh), o.trafo(spec["N"], spec["n"], 6, x2, fh)) <= TOL[precision]
+    eng.close()
+    cabi.lib().nfftcu_pool_trim()

@@ -132,13 +132,87 @@ def cfg5(coils, cpu_coils, iters=20):
     return out
 
 
+def cfg5_multi_gpu(coils, gpus, iters=20):
+    """cfg5 distributed plan-per-GPU (SURVEY 8e "Batched / multi-coil": replicas only, no collective): coil c runs on
+    GPU c mod gpus, one worker process per GPU (env NFFT_B200_DEVICE), each driving the device-resident solver
+    through the unmodified plan-per-coil call sequence of reconstruct_data_2d.c.  Wall clock of the slowest worker,
+    after every worker has warmed up (context creation, module load) and all have passed a start barrier (a file)."""
+    import subprocess
+    import tempfile
+    go = tempfile.NamedTemporaryFile(delete=False).name
+    os.unlink(go)
+    procs = []
+    for r in range(gpus):
+        mine = [c for c in range(coils) if c % gpus == r]
+        env = dict(os.environ, NFFT_B200_DEVICE=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cfg5-worker",
+                                       ",".join(map(str, mine)), "--go-file", go, "--iters", str(iters)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    # workers print READY after warm-up; release them together
+    for p_ in procs:
+        line = p_.stdout.readline()
+        assert line.startswith("READY"), (line, p_.stderr.read()[-2000:])
+    t0 = time.perf_counter()
+    open(go, "w").close()
+    outs = [p_.communicate(timeout=1200) for p_ in procs]
+    wall = time.perf_counter() - t0
+    os.unlink(go)
+    per = []
+    for p_, (so, se) in zip(procs, outs):
+        assert p_.returncode == 0, se[-2000:]
+        per.append(json.loads([ln for ln in so.splitlines() if ln.startswith("{")][-1]))
+    return dict(gpus=gpus, coils=coils, iters=iters, seconds_wall=wall, seconds_slowest_worker=max(w["seconds"] for w in per),
+                seconds_per_coil=wall / coils, coils_per_s=coils / wall, workers=per)
+
+
+def cfg5_worker(coil_ids, go_file, iters):
+    from nfft_b200 import plan_abi as abi
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsolver_dev_b200.so"), mode=os.RTLD_LOCAL)
+    fn = L.solver_driver_run
+    fn.restype = C.c_int
+    N, n, m, M = [512, 512], [1024, 1024], 6, 512 * 512
+    x = spiral(M, 512)
+    NN = 512 * 512
+    k = np.stack(np.meshgrid(*[np.arange(-v // 2, v // 2) / v for v in N], indexing="ij"), -1)
+    w_hat = np.ascontiguousarray((np.sqrt((k ** 2).sum(-1)) <= 0.5).astype(np.float64).ravel())
+    w = np.ones(M)
+    CGNR, PRE_D = 1 << 2, 1 << 6
+    flags = abi.PRE_PHI_HUT | abi.PRE_PSI | abi.MALLOC_X | abi.MALLOC_F_HAT | abi.MALLOC_F | abi.FFTW_INIT
+    ia = lambda a: (C.c_int * len(a))(*a)          # noqa: E731
+    p = lambda a: a.ctypes.data_as(C.c_void_p)     # noqa: E731
+    rng = np.random.default_rng(5)
+    ys = {c: np.ascontiguousarray(rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)) for c in coil_ids}
+    f_hat, dots = np.zeros(NN, dtype=np.complex128), np.zeros(iters)
+    y0 = next(iter(ys.values())) if ys else np.zeros(M, dtype=np.complex128)
+    fn(C.c_int(2), ia(N), C.c_int(M), ia(n), C.c_int(m), C.c_uint(flags), C.c_uint(CGNR | PRE_D), p(x), p(y0), p(w),
+       p(w_hat), C.c_int(1), p(f_hat), p(dots), C.c_double(0.0), None)
+    print("READY", flush=True)
+    while not os.path.exists(go_file):
+        time.sleep(0.0005)
+    t0 = time.perf_counter()
+    for c in coil_ids:
+        rc = fn(C.c_int(2), ia(N), C.c_int(M), ia(n), C.c_int(m), C.c_uint(flags), C.c_uint(CGNR | PRE_D), p(x),
+                p(ys[c]), p(w), p(w_hat), C.c_int(iters), p(f_hat), p(dots), C.c_double(0.0), None)
+        assert rc == 0
+    dt = time.perf_counter() - t0
+    print(json.dumps(dict(device=os.environ.get("NFFT_B200_DEVICE", "0"), coils=len(coil_ids), seconds=dt,
+                          last_dot_r=float(dots[-1]))), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1, help="cfg5: distribute the coils plan-per-GPU over this many GPUs")
+    ap.add_argument("--cfg5-worker", default=None)
+    ap.add_argument("--go-file", default=None)
+    ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--configs", default="cfg1,cfg2,cfg4,cfg5")
     ap.add_argument("--coils", type=int, default=32)
     ap.add_argument("--cpu-coils", type=int, default=1)
     ap.add_argument("--cfg4-nodes", type=int, default=100_000_000)
     args = ap.parse_args()
+    if args.cfg5_worker is not None:
+        cfg5_worker([int(v) for v in args.cfg5_worker.split(",") if v], args.go_file, args.iters)
+        return
     want = args.configs.split(",")
     rng = np.random.default_rng(20260101)
     if "cfg1" in want:
@@ -169,6 +243,10 @@ def main():
     if "cfg5" in want:
         print(json.dumps(dict(config="cfg5: 2-D CGNR 20 iterations x %d coils, 512^2 spiral, reference solver.c on the engine"
                                      % args.coils, **cfg5(args.coils, args.cpu_coils))), flush=True)
+    if "cfg5mg" in want:
+        print(json.dumps(dict(config="cfg5 plan-per-GPU: 2-D CGNR 20 iterations x %d coils over %d GPUs, 512^2 spiral, "
+                                     "device-resident solver_*_complex, one worker process per GPU, no collective"
+                                     % (args.coils, args.gpus), **cfg5_multi_gpu(args.coils, args.gpus))), flush=True)
 
 
 if __name__ == "__main__":
