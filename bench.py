@@ -434,12 +434,19 @@ def run_ours(args, rank, world, local_rank):
                 p.adjoint()
                 return fh_res.numpy().ravel()
 
+        if world > 1:   # the cross-rank sum of the e2e step: page-locked staging on both sides of the collective
+            g_dev = torch.empty(fh_h.size, dtype=torch.float64 if prec == "double" else torch.float32, device=dev)
+            g_res = torch.empty(fh_h.size, dtype=g_dev.dtype).pin_memory()
+            g_src = torch.empty(fh_h.size, dtype=g_dev.dtype).pin_memory()
+
         def full():
             r = one()
             if world > 1:
-                g = torch.from_numpy(np.asarray(r)).to(dev, non_blocking=True)
-                dist.all_reduce(g, op=dist.ReduceOp.SUM)
-                g.cpu()
+                g_src.numpy()[:] = np.asarray(r).ravel()      # caller-side copy into its send buffer
+                g_dev.copy_(g_src, non_blocking=True)
+                dist.all_reduce(g_dev, op=dist.ReduceOp.SUM)
+                g_res.copy_(g_dev, non_blocking=True)
+                torch.cuda.synchronize()
             return r
 
         full()

@@ -181,7 +181,7 @@ int trafo_dev_impl(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
   return NFFTCU_OK;
 }
 
-int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
+int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev, bool peer_reduce = false) {
   NFFTCU_TRY(need_nodes(c));
   if (c->direct_only) return ndft_adjoint(c, f_dev, f_hat_dev);
   StageTimer tm(c);
@@ -190,7 +190,8 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
   tm.mark(1);
   NFFTCU_TRY(stage_F(c, +1, c->opt_fft_prune != 0 && !c->fft_no_prune));
   tm.mark(2);
-  NFFTCU_TRY(stage_DT(c, f_hat_dev));
+  // peer_reduce: D^T with the cross-GPU sum taken inside the kernel through peer pointers (peer.cu)
+  NFFTCU_TRY(peer_reduce ? peer_reduce_DT(c, f_hat_dev) : stage_DT(c, f_hat_dev));
   tm.mark(3);
   tm.finish(2, 1, 0);
   return NFFTCU_OK;
@@ -919,6 +920,14 @@ int nfftcu_adjoint_dev(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
   NFFTCU_TRY(check_ctx(c));
   NFFTCU_TRY(bind_device(c));
   return adjoint_dev_impl(c, f_dev, f_hat_dev);
+}
+// f_hat := sum over ranks of D^T F^H B_r^T f_r, every rank gets the full result (the collective is part of D^T)
+int nfftcu_adjoint_dev_peer(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  if (!c->peer) { set_error("nfftcu_adjoint_dev_peer: plan is not attached to its peers"); return NFFTCU_ESTATE; }
+  if (c->direct_only) { set_error("nfftcu_adjoint_dev_peer: NDFT-fallback plan"); return NFFTCU_ESTATE; }
+  return adjoint_dev_impl(c, f_dev, f_hat_dev, true);
 }
 int nfftcu_trafo_direct_dev(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev) {
   NFFTCU_TRY(check_ctx(c));

@@ -302,18 +302,6 @@ int nfftcu_peer_detach(nfftcu_ctx *c) {
   return NFFTCU_OK;
 }
 
-// f_hat := sum over ranks of D^T F^H B_r^T f_r, every rank gets the full result (the collective is part of D^T)
-int nfftcu_adjoint_dev_peer(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev) {
-  if (!c) { set_error("null context"); return NFFTCU_EINVAL; }
-  NFFTCU_CUDA(cudaSetDevice(c->device));
-  if (!c->have_nodes) { set_error("transform called before nfftcu_set_nodes"); return NFFTCU_ESTATE; }
-  if (!c->peer) { set_error("nfftcu_adjoint_dev_peer: plan is not attached to its peers"); return NFFTCU_ESTATE; }
-  const bool pruned = c->opt_fft_prune != 0 && !c->fft_no_prune;
-  NFFTCU_TRY(stage_BT(c, f_dev));
-  NFFTCU_TRY(stage_F(c, +1, pruned));
-  return peer_reduce_DT(c, f_hat_dev);
-}
-
 // the fused D^T + reduce alone, on whatever the grids hold (profiling: the collective's own cost)
 int nfftcu_peer_reduce_only(nfftcu_ctx *c, void *f_hat_dev) {
   if (!c || !c->peer) { set_error("nfftcu_peer_reduce_only: plan is not attached to its peers"); return NFFTCU_ESTATE; }
