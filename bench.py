@@ -360,6 +360,7 @@ def run_ours(args, rank, world, local_rank):
     f_timed = f_out.cpu().numpy()
     fh_timed = fh_out.cpu().numpy()
     collective_ms = sp.collective_ms(fh_out, reps=5) if world > 1 else 0.0
+    reduce_mode = sp.reduce
 
     # ---- rel l2 err of the timed outputs against the reference's own transforms (same inputs, full size) ----
     rel = None
@@ -391,12 +392,37 @@ def run_ours(args, rank, world, local_rank):
                                   "%.3f s, measured in this process; FFT stage = shim, not FFTW; "
                                   "`--impl reference` times K pairs" % (M_local, t_tr, t_ad)}
 
-    # ---- e2e: reference-facing plan API on HOST buffers (H2D/D2H inside the timed region) ----
-    del sp, x_d, f_d, f_out
-    eng.close()
+    # ---- e2e: the public API on HOST buffers, H2D / D2H inside the timed region ----
+    # N = 1: the reference-facing plan API (nfft_trafo / nfft_adjoint of libnfft3_b200.so).  N > 1: the process-per-GPU
+    # API a multi-GPU application calls (ShardedPlan.trafo_host / adjoint_host: H2D, transform, on-device reduction
+    # of f_hat, D2H); the one-process C path (NFFT_B200_DEVICES) is timed by tools/bench_group.py.
     flags = abi.PRE_PHI_HUT | abi.NFFT_SORT_NODES | abi.NFFT_OMP_BLOCKWISE_ADJOINT | abi.FFTW_INIT
     os.environ["NFFT_B200_DEVICE"] = str(local_rank)
     e2e_steps = max(1, min(args.steps, 5))
+
+    def time_loop(fn):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([te], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def e2e_sharded():
+        keep = [torch.from_numpy(a).pin_memory() for a in (fh_h, f_h)]
+        fh_res, f_res = torch.empty_like(keep[0]).pin_memory(), torch.empty_like(keep[1]).pin_memory()
+
+        def one():
+            sp.trafo_host(keep[0], f_res, local_rank)
+            sp.adjoint_host(keep[1], fh_res, local_rank)
+        return time_loop(one)
 
     def e2e_run(lib_buffers):
         """lib_buffers: the plan API's own MALLOC_X/F_HAT/F buffers (what an unmodified C caller uses);
@@ -418,7 +444,6 @@ def run_ours(args, rank, world, local_rank):
             def one():
                 p.trafo()
                 q.adjoint()
-                return q.f_hat.view(q.api.real)
         else:
             def ptr(tn):
                 return C.cast(C.c_void_p(tn.data_ptr()), C.POINTER(creal))
@@ -432,42 +457,21 @@ def run_ours(args, rank, world, local_rank):
                 p.trafo()
                 p.c.f, p.c.f_hat = ptr(keep[2]), ptr(fh_res)
                 p.adjoint()
-                return fh_res.numpy().ravel()
-
-        if world > 1:   # the cross-rank sum of the e2e step: page-locked staging on both sides of the collective
-            g_dev = torch.empty(fh_h.size, dtype=torch.float64 if prec == "double" else torch.float32, device=dev)
-            g_res = torch.empty(fh_h.size, dtype=g_dev.dtype).pin_memory()
-            g_src = torch.empty(fh_h.size, dtype=g_dev.dtype).pin_memory()
-
-        def full():
-            r = one()
-            if world > 1:
-                g_src.numpy()[:] = np.asarray(r).ravel()      # caller-side copy into its send buffer
-                g_dev.copy_(g_src, non_blocking=True)
-                dist.all_reduce(g_dev, op=dist.ReduceOp.SUM)
-                g_res.copy_(g_dev, non_blocking=True)
-                torch.cuda.synchronize()
-            return r
-
-        full()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            full()
-        torch.cuda.synchronize()
-        te = (time.perf_counter() - t0) / e2e_steps
+        te = time_loop(one)
         p.finalize()
         for q in extra:
             q.finalize()
-        tt = torch.tensor([te], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+        return te
 
-    te_lib = e2e_run(True)
-    te_pin = e2e_run(False)
+    if world > 1:
+        te_lib = te_pin = e2e_sharded()
+        del x_d, f_d, f_out
+        sp.close()
+    else:
+        del sp, x_d, f_d, f_out
+        eng.close()
+        te_lib = e2e_run(True)
+        te_pin = e2e_run(False)
     h2d = fh_h.nbytes + f_h.nbytes           # x is resident: changes are detected by a host-side fingerprint
     d2h = f_h.nbytes + fh_h.nbytes
 
@@ -526,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
                            "precompute_psi, streamed by TMA every launch)" % (eng_images_gb(M_local))
                            if (dmma or tf32) else ("psi table" if args.psi_table else "psi on the fly")),
                 "multi_gpu": ("node-sharded x%d: trafo replicates f_hat and the grid; adjoint reduces f_hat (%s, "
-                              "%.3f ms per call measured alone)" % (world, sp_reduce_name(args.reduce), collective_ms)
+                              "%.3f ms per D^T + reduction measured alone)" % (world, sp_reduce_name(reduce_mode), collective_ms)
                               if world > 1 else "single GPU"),
                 "nodes_setup_s": t_nodes},
             "stage_ms": {"trafo": {"D": stage[0][0], "F": stage[0][1], "B": stage[0][2]},
@@ -540,9 +544,13 @@ def run_ours(args, rank, world, local_rank):
                                    "device_copy_gbs": copy_now},
             "e2e": {"value": M_all / te_lib, "unit": "points/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": te_lib * 1e3,
-                    "buffers": "allocated by the plan API itself (MALLOC_X|MALLOC_F_HAT|MALLOC_F through nfft_malloc, "
-                               "page-locked); the caller fills f_hat / f and reads f / f_hat every step; x stays "
-                               "resident (host-side fingerprint, re-upload only when it changes)",
+                    "buffers": ("allocated by the plan API itself (MALLOC_X|MALLOC_F_HAT|MALLOC_F through nfft_malloc, "
+                                "page-locked); nfft_trafo reads f_hat and writes f, nfft_adjoint reads f and writes "
+                                "f_hat, all on the host; x stays resident (host-side fingerprint, re-upload only when "
+                                "it changes)" if world == 1 else
+                                "process-per-GPU API (ShardedPlan.trafo_host / adjoint_host) on page-locked host "
+                                "tensors: H2D of f_hat / the rank's f, transform, on-device reduction of f_hat, D2H of "
+                                "the rank's f / the reduced f_hat"),
                     "caller_pinned_ms_per_step": te_pin * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -115,11 +115,33 @@ int launch_blocks(const nfftcu_ctx *c, long long count) {
 
 int group_trafo(nfftcu_group_s *g, const void *f_hat_host, void *f_host) {
   const size_t C = csize(g);
-  // phase 1: inputs (may block on pageable memory: nothing that could wait for another device is queued yet)
+  // phase 1: inputs (may block on pageable memory: nothing that could wait for another device is queued yet).
+  // f_hat crosses the host link ONCE: device r uploads slice r and the devices all-gather the slices over NVLink
+  // (P - 1 peer copies of N_total / P coefficients into every device); uploading the whole f_hat to every device
+  // made the 8-GPU trafo host-link-bound (8 x 268 MB at cfg4 against ~95 GB/s of aggregate host bandwidth).
   for (int r = 0; r < g->P; r++) {
     NFFTCU_CUDA(cudaSetDevice(g->dev[r]));
     mark(g, r, 0);
-    NFFTCU_CUDA(cudaMemcpyAsync(g->fhat[r], f_hat_host, C * (size_t) g->N_total, cudaMemcpyHostToDevice, g->shard[r]->stream));
+    const int64_t kb = g->N_total * r / g->P, ke = g->N_total * (r + 1) / g->P;
+    if (ke > kb)
+      NFFTCU_CUDA(cudaMemcpyAsync((char *) g->fhat[r] + C * (size_t) kb, (const char *) f_hat_host + C * (size_t) kb,
+                                  C * (size_t) (ke - kb), cudaMemcpyHostToDevice, g->shard[r]->stream));
+  }
+  if (g->P > 1) {
+    all_wait_all(g);
+    for (int r = 0; r < g->P; r++) {
+      NFFTCU_CUDA(cudaSetDevice(g->dev[r]));
+      for (int q = 1; q < g->P; q++) {   // staggered start: device r first pulls from r + 1
+        const int s = (r + q) % g->P;
+        const int64_t kb = g->N_total * s / g->P, ke = g->N_total * (s + 1) / g->P;
+        if (ke > kb)
+          NFFTCU_CUDA(cudaMemcpyAsync((char *) g->fhat[r] + C * (size_t) kb, (const char *) g->fhat[s] + C * (size_t) kb,
+                                      C * (size_t) (ke - kb), cudaMemcpyDefault, g->shard[r]->stream));
+      }
+    }
+  }
+  for (int r = 0; r < g->P; r++) {
+    NFFTCU_CUDA(cudaSetDevice(g->dev[r]));
     mark(g, r, 1);
   }
   // phase 2: D + F + B per device, then the all-to-all into caller order

@@ -150,6 +150,35 @@ class ShardedPlan:
         if self.world > 1:
             self.dist.all_reduce(f_hat, op=self.dist.ReduceOp.SUM, group=self.group)
 
+    # ---- host-buffer face (what a process-per-GPU application calls): page-locked torch tensors in and out ----
+    def _staging(self, like_fhat, like_f, device):
+        import torch
+        if getattr(self, "_st", None) is None:
+            dev = torch.device("cuda", device)
+            self._st = (torch.empty(like_fhat.shape, dtype=like_fhat.dtype, device=dev),
+                        torch.empty(like_f.shape, dtype=like_f.dtype, device=dev))
+        return self._st
+
+    def trafo_host(self, f_hat_host, f_local_host, device: int = 0):
+        """f_local_host := B_local F D f_hat_host; H2D of f_hat, the transform and D2H of the rank's slice of f, in
+        stream order; returns after completion."""
+        import torch
+        fh_d, f_d = self._staging(f_hat_host, f_local_host, device)
+        fh_d.copy_(f_hat_host, non_blocking=True)
+        self.trafo(fh_d, f_d)
+        f_local_host.copy_(f_d, non_blocking=True)
+        torch.cuda.current_stream(fh_d.device).synchronize()
+
+    def adjoint_host(self, f_local_host, f_hat_host, device: int = 0):
+        """f_hat_host := sum over ranks of the adjoints; the reduction runs on the device (fused into D^T or NCCL), so
+        every rank moves its samples up once and the reduced f_hat down once."""
+        import torch
+        fh_d, f_d = self._staging(f_hat_host, f_local_host, device)
+        f_d.copy_(f_local_host, non_blocking=True)
+        self.adjoint(f_d, fh_d)
+        f_hat_host.copy_(fh_d, non_blocking=True)
+        torch.cuda.current_stream(fh_d.device).synchronize()
+
     def collective_ms(self, f_hat, reps: int = 5) -> float:
         """Device time of D^T + cross-rank reduction alone (on whatever the grids hold), max over ranks."""
         import torch

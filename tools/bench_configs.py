@@ -161,8 +161,12 @@ def cfg5_multi_gpu(coils, gpus, iters=20):
     for p_, (so, se) in zip(procs, outs):
         assert p_.returncode == 0, se[-2000:]
         per.append(json.loads([ln for ln in so.splitlines() if ln.startswith("{")][-1]))
-    return dict(gpus=gpus, coils=coils, iters=iters, seconds_wall=wall, seconds_slowest_worker=max(w["seconds"] for w in per),
-                seconds_per_coil=wall / coils, coils_per_s=coils / wall, workers=per)
+    # the workers start together (go file) and time their own coil loops; the wall clock of this parent also contains
+    # process teardown (CUDA context destruction), so the job time is the slowest worker's
+    slowest = max(w["seconds"] for w in per)
+    return dict(gpus=gpus, coils=coils, iters=iters, seconds=slowest, seconds_per_coil=slowest / coils,
+                coils_per_s=coils / slowest, transforms_per_s=coils * iters * 2 / slowest, parent_wall_seconds=wall,
+                workers=per)
 
 
 def cfg5_worker(coil_ids, go_file, iters):

@@ -74,6 +74,12 @@ def main():
             tt.append(t1 - t0)
             ta.append(t3 - t2)
         fh_out = p.f_hat.copy()
+        phases = None
+        if P > 1 and p.c.my_fftw_plan2:      # nfftcu_group_times of the last transform (the adjoint)
+            import ctypes as C
+            ms = (C.c_float * 3)()
+            cabi.lib().nfftcu_group_times(C.c_void_p(p.c.my_fftw_plan2), ms)
+            phases = dict(adjoint_h2d_ms=float(ms[0]), adjoint_compute_and_exchange_ms=float(ms[1]), adjoint_d2h_ms=float(ms[2]))
         line = dict(config=bench.workload_config(cfg, P, "strong")["workload"], n_gpus=P, precision=prec,
                     path="nfft_trafo + nfft_adjoint of libnfft3_b200.so on plan-API (page-locked) host buffers, "
                          "NFFT_B200_DEVICES=%s" % os.environ.get("NFFT_B200_DEVICES", "(unset: one device)"),
@@ -84,6 +90,8 @@ def main():
         if base is None:
             base = line["ms_pair"]
         line["speedup_vs_first_listed"] = base / line["ms_pair"]
+        if phases:
+            line["phases_slowest_device"] = phases
         if ref is not None:
             line["rel_l2"] = dict(trafo=bench.rel_l2(f_out.view(p.api.real), ref[0].view(p.api.real)),
                                   adjoint=bench.rel_l2(fh_out.view(p.api.real), ref[1].view(p.api.real)))
