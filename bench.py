@@ -463,9 +463,30 @@ def run_ours(args, rank, world, local_rank):
             q.finalize()
         return te
 
+    host_link = None
     if world > 1:
         te_lib = te_pin = e2e_sharded()
-        del x_d, f_d, f_out
+        # what the host links deliver when all ranks copy at once (the e2e step moves h2d + d2h bytes per rank through
+        # them): 160 MB up and 160 MB down per rank, concurrently on all ranks, both directions in flight together
+        up = torch.empty(20_000_000, dtype=torch.float64).pin_memory()
+        dn = torch.empty(20_000_000, dtype=torch.float64).pin_memory()
+        du, dd = torch.empty_like(up, device=dev), torch.empty_like(dn, device=dev)
+        s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def both():
+            with torch.cuda.stream(s_up):
+                du.copy_(up, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                dn.copy_(dd, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+        t_link = time_loop(both)
+        host_link = {"bytes_per_rank": 2 * up.numel() * 8, "seconds": t_link,
+                     "per_gpu_gbs": 2 * up.numel() * 8 / t_link / 1e9,
+                     "aggregate_gbs": world * 2 * up.numel() * 8 / t_link / 1e9,
+                     "note": "all ranks copying 160 MB up + 160 MB down at the same time (page-locked memory); the e2e step "
+                             "of every rank needs h2d + d2h bytes through these links on top of the device time"}
+        del up, dn, du, dd, x_d, f_d, f_out
         sp.close()
     else:
         del sp, x_d, f_d, f_out
@@ -551,7 +572,7 @@ def run_ours(args, rank, world, local_rank):
                                 "process-per-GPU API (ShardedPlan.trafo_host / adjoint_host) on page-locked host "
                                 "tensors: H2D of f_hat / the rank's f, transform, on-device reduction of f_hat, D2H of "
                                 "the rank's f / the reduced f_hat"),
-                    "caller_pinned_ms_per_step": te_pin * 1e3},
+                    "caller_pinned_ms_per_step": te_pin * 1e3, "host_link": host_link},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1:
