@@ -192,6 +192,9 @@ void nfftcu_host_free(void *ptr);
 /* device and page-locked buffers freed by finalized plans are cached per process (mempool.cu, NFFT_B200_POOL_MB);
  * this returns the cache to the driver, for processes that share the GPU with other CUDA users */
 void nfftcu_pool_trim(void);
+/* the 64-bit fingerprint of a host array that decides whether nodes have changed (host threads; independent of the
+ * thread count: 1 MiB chunks hashed separately and combined in order) */
+uint64_t nfftcu_fingerprint(const void *data, size_t bytes);
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int nfftcu_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 

@@ -33,7 +33,7 @@ SYMBOLS = (
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
     "nfftcu_solver_create", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
     "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
-    "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim",
+    "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim", "nfftcu_fingerprint",
     "nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev",
     "nfftcu_mri_inh_2d1d", "nfftcu_mri_inh_3d", "nfftcu_adjoint_mul_trafo",
     "nfftcu_get_sorted_slab", "nfftcu_peer_export", "nfftcu_peer_attach", "nfftcu_peer_detach",
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
         L.nfftcu_host_free.argtypes = [vp]
         L.nfftcu_host_free.restype = None
         L.nfftcu_pool_trim.restype = None
+        L.nfftcu_fingerprint.argtypes = [vp, C.c_size_t]
+        L.nfftcu_fingerprint.restype = C.c_uint64
         for name in ("nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev"):
             getattr(L, name).argtypes = [vp, ci, vp, vp]
         L.nfftcu_adjoint_mul_trafo.argtypes = [vp, vp, vp, vp, vp]

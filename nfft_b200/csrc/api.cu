@@ -1073,6 +1073,8 @@ void nfftcu_host_free(void *p) {
   else free(p);
 }
 void nfftcu_pool_trim(void) { plan_cache_clear(); pool_trim(); }
+// the 64-bit fingerprint nfftcu_set_nodes / nfftcu_*_refresh use to detect a changed node array (host only)
+uint64_t nfftcu_fingerprint(const void *data, size_t bytes) { return fingerprint(data, bytes); }
 
 int nfftcu_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
   NFFTCU_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
