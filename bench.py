@@ -570,8 +570,9 @@ def run_ours(args, rank, world, local_rank):
                                 "f_hat, all on the host; x stays resident (host-side fingerprint, re-upload only when "
                                 "it changes)" if world == 1 else
                                 "process-per-GPU API (ShardedPlan.trafo_host / adjoint_host) on page-locked host "
-                                "tensors: H2D of f_hat / the rank's f, transform, on-device reduction of f_hat, D2H of "
-                                "the rank's f / the reduced f_hat"),
+                                "tensors: rank 0 uploads f_hat and broadcasts it over NVLink, every rank uploads its f, "
+                                "transform, on-device reduction of f_hat, every rank downloads its f, rank 0 the "
+                                "reduced f_hat; the byte counts are rank 0's"),
                     "caller_pinned_ms_per_step": te_pin * 1e3, "host_link": host_link},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -159,24 +159,32 @@ class ShardedPlan:
                         torch.empty(like_f.shape, dtype=like_f.dtype, device=dev))
         return self._st
 
-    def trafo_host(self, f_hat_host, f_local_host, device: int = 0):
-        """f_local_host := B_local F D f_hat_host; H2D of f_hat, the transform and D2H of the rank's slice of f, in
-        stream order; returns after completion."""
+    def trafo_host(self, f_hat_host, f_local_host, device: int = 0, root: int = 0):
+        """f_local_host := B_local F D f_hat.  f_hat is the same on every rank, so it crosses a host link ONCE: rank
+        ``root`` uploads its ``f_hat_host`` and broadcasts it over NVLink (``root=None``: every rank uploads its own
+        copy); then the transform and the D2H of the rank's slice of f, in stream order; returns after completion."""
         import torch
         fh_d, f_d = self._staging(f_hat_host, f_local_host, device)
-        fh_d.copy_(f_hat_host, non_blocking=True)
+        if root is None or self.world == 1:
+            fh_d.copy_(f_hat_host, non_blocking=True)
+        else:
+            if self.rank == root:
+                fh_d.copy_(f_hat_host, non_blocking=True)
+            self.dist.broadcast(fh_d, src=root, group=self.group)
         self.trafo(fh_d, f_d)
         f_local_host.copy_(f_d, non_blocking=True)
         torch.cuda.current_stream(fh_d.device).synchronize()
 
-    def adjoint_host(self, f_local_host, f_hat_host, device: int = 0):
-        """f_hat_host := sum over ranks of the adjoints; the reduction runs on the device (fused into D^T or NCCL), so
-        every rank moves its samples up once and the reduced f_hat down once."""
+    def adjoint_host(self, f_local_host, f_hat_host, device: int = 0, root: int = 0):
+        """f_hat_host (on rank ``root``; ``root=None``: on every rank) := sum over ranks of the adjoints.  The reduction
+        runs on the device (fused into D^T or NCCL); every rank moves its samples up once, and only the root moves the
+        reduced f_hat down."""
         import torch
         fh_d, f_d = self._staging(f_hat_host, f_local_host, device)
         f_d.copy_(f_local_host, non_blocking=True)
         self.adjoint(f_d, fh_d)
-        f_hat_host.copy_(fh_d, non_blocking=True)
+        if root is None or self.rank == root or self.world == 1:
+            f_hat_host.copy_(fh_d, non_blocking=True)
         torch.cuda.current_stream(fh_d.device).synchronize()
 
     def collective_ms(self, f_hat, reps: int = 5) -> float:
