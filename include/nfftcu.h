@@ -277,6 +277,11 @@ typedef struct nfftcu_solver_s nfftcu_solver;
 /* scal[8] = alpha_iter, beta_iter, dot_r_iter, dot_r_iter_old, dot_z_hat_iter, dot_z_hat_iter_old, dot_p_hat_iter,
  * dot_v_iter (the scalar members of solver_plan_complex, include/nfft3.h:772-779), as doubles */
 int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags);
+/* K right-hand sides iterated in lock-step on ONE plan (multi-coil reconstruction: the coils of
+ * applications/mri/mri2d/reconstruct_data_2d.c:52-139 share the trajectory): vectors are [K][M] / [K][N_total], the
+ * weights w / w_hat are shared, scal is [K][8]; the transforms of a step are nfftcu_*_batch_dev.  Every right-hand side
+ * follows exactly the iteration of a K = 1 solver (own alpha / beta). */
+int nfftcu_solver_create_batch(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags, int K);
 int nfftcu_solver_destroy(nfftcu_solver *s);
 int nfftcu_solver_upload(nfftcu_solver *s, int which, const void *host);      /* host -> device vector */
 int nfftcu_solver_download(nfftcu_solver *s, int which, void *host);          /* device vector -> host */

@@ -31,7 +31,7 @@ SYMBOLS = (
     "nfftcu_set_stream", "nfftcu_get_stream", "nfftcu_sync", "nfftcu_stage_times", "nfftcu_b_kernel_time", "nfftcu_trafo_refresh", "nfftcu_adjoint_refresh",
     "nfftcu_launch_count", "nfftcu_malloc_device", "nfftcu_free_device", "nfftcu_malloc_pinned",
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
-    "nfftcu_solver_create", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
+    "nfftcu_solver_create", "nfftcu_solver_create_batch", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
     "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
     "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim", "nfftcu_fingerprint",
     "nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev",
@@ -327,6 +327,50 @@ class Engine:
         assert g.size == self.n_total
         self.sync()
         _ck(self.L.nfftcu_memcpy_h2d(C.c_void_p(self.grid_ptr()), _ptr(g), g.nbytes))
+
+
+SOLVER_Y, SOLVER_W, SOLVER_W_HAT, SOLVER_F_HAT_ITER, SOLVER_R_ITER, SOLVER_Z_HAT_ITER, SOLVER_P_HAT_ITER, SOLVER_V_ITER = range(8)
+LANDWEBER, STEEPEST_DESCENT, CGNR, CGNE, NORMS_FOR_LANDWEBER, PRECOMPUTE_WEIGHT, PRECOMPUTE_DAMP = (1 << i for i in range(7))
+
+
+class BatchSolver:
+    """Device-resident inverse NFFT for K right-hand sides on one plan (``nfftcu_solver_create_batch``)."""
+
+    def __init__(self, engine: "Engine", flags: int, K: int):
+        self.L, self.eng, self.K, self.flags = lib(), engine, int(K), flags
+        self.s = C.c_void_p(0)
+        self.L.nfftcu_solver_create_batch.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint, C.c_int]
+        for name in ("nfftcu_solver_upload", "nfftcu_solver_download"):
+            getattr(self.L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        for name in ("nfftcu_solver_before_loop", "nfftcu_solver_step"):
+            getattr(self.L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        self.L.nfftcu_solver_destroy.argtypes = [C.c_void_p]
+        _ck(self.L.nfftcu_solver_create_batch(C.byref(self.s), engine.ctx, flags, self.K))
+        self.scal = np.zeros((self.K, 8))
+
+    def upload(self, which: int, a: np.ndarray):
+        real = which in (SOLVER_W, SOLVER_W_HAT)
+        a = np.ascontiguousarray(a, dtype=self.eng.real if real else self.eng.cplx)
+        _ck(self.L.nfftcu_solver_upload(self.s, which, _ptr(a)))
+
+    def download(self, which: int) -> np.ndarray:
+        n = self.eng.M if which in (SOLVER_Y, SOLVER_R_ITER, SOLVER_V_ITER) else self.eng.N_total
+        out = np.empty((self.K, n), dtype=self.eng.cplx)
+        _ck(self.L.nfftcu_solver_download(self.s, which, _ptr(out)))
+        return out
+
+    def before_loop(self):
+        _ck(self.L.nfftcu_solver_before_loop(self.s, None, None, self.scal.ctypes.data_as(C.POINTER(C.c_double))))
+        return self.scal.copy()
+
+    def step(self):
+        _ck(self.L.nfftcu_solver_step(self.s, None, None, self.scal.ctypes.data_as(C.POINTER(C.c_double))))
+        return self.scal.copy()
+
+    def close(self):
+        if self.s:
+            _ck(self.L.nfftcu_solver_destroy(self.s))
+            self.s = C.c_void_p(0)
 
 
 class Group:

@@ -21,6 +21,8 @@
 struct nfftcu_solver_s {
   nfftcu_ctx *plan = nullptr;
   int device = 0;                // cached: nfftcu_solver_destroy works after the plan is gone
+  int K = 1;                     // right-hand sides iterated in lock-step (nfftcu_solver_create_batch): vectors are
+                                 // [K][len], scalars [K][8], weights w / w_hat shared
   unsigned flags = 0;
   void *vec[8] = {nullptr};      // device vectors, index NFFTCU_SOLVER_*; Z may alias P
   void *fhat_in = nullptr;       // N_total complex: argument of the transform
@@ -51,6 +53,8 @@ inline unsigned blocks_for(long long n) {
 template <typename T>
 __global__ void cp_w_kernel(typename Cplx<T>::type *__restrict__ x, const T *__restrict__ w,
                             const typename Cplx<T>::type *__restrict__ y, long long n) {
+  x += (size_t) blockIdx.y * (size_t) n;   // right-hand side blockIdx.y
+  y += (size_t) blockIdx.y * (size_t) n;
   for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long) gridDim.x * blockDim.x) {
     typename Cplx<T>::type v = y[k];
     if (w) { const T wk = w[k]; v.x = wk * v.x; v.y = wk * v.y; }
@@ -62,6 +66,9 @@ __global__ void cp_w_kernel(typename Cplx<T>::type *__restrict__ x, const T *__r
 template <typename T>
 __global__ void xpawy_kernel(typename Cplx<T>::type *__restrict__ x, const double *__restrict__ sc, int ia, T s,
                              const T *__restrict__ w, const typename Cplx<T>::type *__restrict__ y, long long n) {
+  x += (size_t) blockIdx.y * (size_t) n;
+  y += (size_t) blockIdx.y * (size_t) n;
+  sc += 8 * blockIdx.y;
   const T a = s * (ia >= 0 ? (T) sc[ia] : (T) 1);
   for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long) gridDim.x * blockDim.x) {
     typename Cplx<T>::type xv = x[k];
@@ -80,6 +87,9 @@ __global__ void xpawy_kernel(typename Cplx<T>::type *__restrict__ x, const doubl
 template <typename T>
 __global__ void axpy_kernel(typename Cplx<T>::type *__restrict__ x, const double *__restrict__ sc, int ia, T aconst,
                             const typename Cplx<T>::type *__restrict__ y, long long n) {
+  x += (size_t) blockIdx.y * (size_t) n;
+  y += (size_t) blockIdx.y * (size_t) n;
+  sc += 8 * blockIdx.y;
   const T a = ia >= 0 ? (T) sc[ia] : aconst;
   for (long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long) gridDim.x * blockDim.x) {
     typename Cplx<T>::type xv = x[k];
@@ -97,6 +107,13 @@ __global__ void dot_kernel(typename Cplx<T>::type *__restrict__ x, const T *__re
                            double *__restrict__ partial, const double *__restrict__ sc, int ia, T s,
                            const typename Cplx<T>::type *v, typename Cplx<T>::type *out) {   // out may alias v
   __shared__ double red[kVecThreads / 32];
+  x += (size_t) blockIdx.y * (size_t) n;
+  partial += (size_t) blockIdx.y * kMaxBlocks;
+  if (MODE == 1) {
+    v += (size_t) blockIdx.y * (size_t) n;
+    out += (size_t) blockIdx.y * (size_t) n;
+    sc += 8 * blockIdx.y;
+  }
   double acc = 0.0;
   T a = 0;
   if (MODE == 1) a = s * (T) sc[ia];
@@ -131,6 +148,8 @@ template <typename T>
 __global__ void dot_final_kernel(const double *__restrict__ partial, int nb, double *__restrict__ sc, int dst, int save,
                                  int q, int qn, int qd, int copy_to) {
   __shared__ double red[kVecThreads / 32];
+  partial += (size_t) blockIdx.x * kMaxBlocks;   // one block per right-hand side
+  sc += 8 * blockIdx.x;
   double acc = 0.0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += partial[i];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -147,6 +166,7 @@ __global__ void dot_final_kernel(const double *__restrict__ partial, int nb, dou
 }
 
 __global__ void quotient_kernel(double *sc, int q, int qn, int qd, int is_float) {
+  sc += 8 * blockIdx.x;
   if (is_float) sc[q] = (double) ((float) sc[qn] / (float) sc[qd]);
   else sc[q] = sc[qn] / sc[qd];
 }
@@ -157,40 +177,48 @@ struct Ops {
   nfftcu_solver_s *s;
   cudaStream_t st;
   long long N, M;
-  explicit Ops(nfftcu_solver_s *s_) : s(s_), st(s_->plan->stream), N(s_->plan->N_total), M(s_->plan->M) {}
+  int K;
+  explicit Ops(nfftcu_solver_s *s_) : s(s_), st(s_->plan->stream), N(s_->plan->N_total), M(s_->plan->M), K(s_->K) {}
+  dim3 grid(long long n) const { return dim3(blocks_for(n), (unsigned) K); }
+  int trafo(const void *fh, void *f) {
+    return K > 1 ? nfftcu_trafo_batch_dev(s->plan, K, fh, f) : nfftcu_trafo_dev(s->plan, fh, f);
+  }
+  int adjoint(const void *f, void *fh) {
+    return K > 1 ? nfftcu_adjoint_batch_dev(s->plan, K, f, fh) : nfftcu_adjoint_dev(s->plan, f, fh);
+  }
   C *v(int i) const { return (C *) s->vec[i]; }
   const T *w() const { return (s->flags & PRECOMPUTE_WEIGHT) ? (const T *) s->vec[NFFTCU_SOLVER_W] : nullptr; }
   const T *wh() const { return (s->flags & PRECOMPUTE_DAMP) ? (const T *) s->vec[NFFTCU_SOLVER_W_HAT] : nullptr; }
 
   void cp_w(C *x, const T *wv, const C *y, long long n) {
-    cp_w_kernel<T><<<blocks_for(n), kVecThreads, 0, st>>>(x, wv, y, n);
+    cp_w_kernel<T><<<grid(n), kVecThreads, 0, st>>>(x, wv, y, n);
     s->plan->launches++;
   }
   void xpawy(C *x, int ia, T sgn, const T *wv, const C *y, long long n) {
-    xpawy_kernel<T><<<blocks_for(n), kVecThreads, 0, st>>>(x, s->sc, ia, sgn, wv, y, n);
+    xpawy_kernel<T><<<grid(n), kVecThreads, 0, st>>>(x, s->sc, ia, sgn, wv, y, n);
     s->plan->launches++;
   }
   void axpy(C *x, int ia, T aconst, const C *y, long long n) {
-    axpy_kernel<T><<<blocks_for(n), kVecThreads, 0, st>>>(x, s->sc, ia, aconst, y, n);
+    axpy_kernel<T><<<grid(n), kVecThreads, 0, st>>>(x, s->sc, ia, aconst, y, n);
     s->plan->launches++;
   }
   // sc[dst] = sum w |x|^2, with the bookkeeping of dot_final_kernel
   void dot(C *x, const T *wv, long long n, int dst, int save = -1, int q = -1, int qn = -1, int qd = -1, int copy_to = -1) {
     const unsigned nb = blocks_for(n);
-    dot_kernel<T, 0><<<nb, kVecThreads, 0, st>>>(x, wv, n, s->partial, nullptr, -1, (T) 0, nullptr, nullptr);
-    dot_final_kernel<T><<<1, kVecThreads, 0, st>>>(s->partial, (int) nb, s->sc, dst, save, q, qn, qd, copy_to);
+    dot_kernel<T, 0><<<dim3(nb, (unsigned) K), kVecThreads, 0, st>>>(x, wv, n, s->partial, nullptr, -1, (T) 0, nullptr, nullptr);
+    dot_final_kernel<T><<<K, kVecThreads, 0, st>>>(s->partial, (int) nb, s->sc, dst, save, q, qn, qd, copy_to);
     s->plan->launches += 2;
   }
   // r <- r + sgn * sc[ia] * vv;  sc[dst] = sum w |r|^2;  out <- w .* r
   void upd_dot_cp(C *r, int ia, T sgn, const C *vv, const T *wv, long long n, C *out, int dst, int save = -1, int q = -1,
                   int qn = -1, int qd = -1) {
     const unsigned nb = blocks_for(n);
-    dot_kernel<T, 1><<<nb, kVecThreads, 0, st>>>(r, wv, n, s->partial, s->sc, ia, sgn, vv, out);
-    dot_final_kernel<T><<<1, kVecThreads, 0, st>>>(s->partial, (int) nb, s->sc, dst, save, q, qn, qd, -1);
+    dot_kernel<T, 1><<<dim3(nb, (unsigned) K), kVecThreads, 0, st>>>(r, wv, n, s->partial, s->sc, ia, sgn, vv, out);
+    dot_final_kernel<T><<<K, kVecThreads, 0, st>>>(s->partial, (int) nb, s->sc, dst, save, q, qn, qd, -1);
     s->plan->launches += 2;
   }
   void quotient(int q, int qn, int qd) {
-    quotient_kernel<<<1, 1, 0, st>>>(s->sc, q, qn, qd, sizeof(T) == 4);
+    quotient_kernel<<<K, 1, 0, st>>>(s->sc, q, qn, qd, sizeof(T) == 4);
     s->plan->launches++;
   }
   int mirror(cudaEvent_t ev, void *host, const void *dev, size_t bytes) {
@@ -201,11 +229,11 @@ struct Ops {
     return NFFTCU_OK;
   }
   int finish(double *scal) {
-    NFFTCU_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NFFTCU_CUDA(cudaMemcpyAsync(s->sc_host, s->sc, 8 * sizeof(double) * (size_t) K, cudaMemcpyDeviceToHost, st));
     NFFTCU_CUDA(cudaStreamSynchronize(st));
     NFFTCU_CUDA(cudaStreamSynchronize(s->side));
     NFFTCU_CUDA(cudaGetLastError());
-    if (scal) memcpy(scal, s->sc_host, 8 * sizeof(double));
+    if (scal) memcpy(scal, s->sc_host, 8 * sizeof(double) * (size_t) K);
     return NFFTCU_OK;
   }
 
@@ -213,12 +241,12 @@ struct Ops {
   int before_loop(void *fhat_host, void *r_host, double *scal) {
     const bool norms = !(s->flags & LANDWEBER) || (s->flags & NORMS_FOR_LANDWEBER);
     C *r = v(NFFTCU_SOLVER_R_ITER), *z = v(NFFTCU_SOLVER_Z_HAT_ITER), *p = v(NFFTCU_SOLVER_P_HAT_ITER);
-    NFFTCU_TRY(nfftcu_trafo_dev(s->plan, v(NFFTCU_SOLVER_F_HAT_ITER), r));
+    NFFTCU_TRY(trafo(v(NFFTCU_SOLVER_F_HAT_ITER), r));
     axpy(r, -1, (T) -1, v(NFFTCU_SOLVER_Y), M);
     if (norms) dot(r, w(), M, SC_DOT_R);
-    NFFTCU_TRY(mirror(s->ev_r, r_host, r, sizeof(C) * (size_t) M));
+    NFFTCU_TRY(mirror(s->ev_r, r_host, r, sizeof(C) * (size_t) M * (size_t) K));
     cp_w((C *) s->f_in, w(), r, M);
-    NFFTCU_TRY(nfftcu_adjoint_dev(s->plan, s->f_in, z));
+    NFFTCU_TRY(adjoint(s->f_in, z));
     if (norms) dot(z, wh(), N, SC_DOT_Z, -1, -1, -1, -1, (s->flags & CGNE) ? SC_DOT_P : -1);
     if (s->flags & CGNR) cp_w(p, nullptr, z, N);
     (void) fhat_host;
@@ -229,29 +257,30 @@ struct Ops {
     C *fh = v(NFFTCU_SOLVER_F_HAT_ITER), *r = v(NFFTCU_SOLVER_R_ITER), *z = v(NFFTCU_SOLVER_Z_HAT_ITER);
     C *p = v(NFFTCU_SOLVER_P_HAT_ITER), *vv = v(NFFTCU_SOLVER_V_ITER), *y = v(NFFTCU_SOLVER_Y);
     C *fhat_in = (C *) s->fhat_in, *f_in = (C *) s->f_in;
-    const size_t nb_fh = sizeof(C) * (size_t) N, nb_r = sizeof(C) * (size_t) M;
+    const size_t nb_fh = sizeof(C) * (size_t) N * (size_t) K, nb_r = sizeof(C) * (size_t) M * (size_t) K;
     if (s->flags & LANDWEBER) {                                                         // solver.c:128-174
-      NFFTCU_CUDA(cudaMemcpyAsync(s->sc + SC_ALPHA, scal + SC_ALPHA, sizeof(double), cudaMemcpyHostToDevice, st));
+      NFFTCU_CUDA(cudaMemcpy2DAsync(s->sc + SC_ALPHA, 8 * sizeof(double), scal + SC_ALPHA, 8 * sizeof(double),
+                                    sizeof(double), (size_t) K, cudaMemcpyHostToDevice, st));
       xpawy(fh, SC_ALPHA, (T) 1, wh(), z, N);
       NFFTCU_TRY(mirror(s->ev_fhat, fhat_host, fh, nb_fh));
-      NFFTCU_TRY(nfftcu_trafo_dev(s->plan, fh, r));
+      NFFTCU_TRY(trafo(fh, r));
       axpy(r, -1, (T) -1, y, M);
       if (s->flags & NORMS_FOR_LANDWEBER) dot(r, w(), M, SC_DOT_R);
       NFFTCU_TRY(mirror(s->ev_r, r_host, r, nb_r));
       cp_w(f_in, w(), r, M);
-      NFFTCU_TRY(nfftcu_adjoint_dev(s->plan, f_in, z));
+      NFFTCU_TRY(adjoint(f_in, z));
       if (s->flags & NORMS_FOR_LANDWEBER) dot(z, wh(), N, SC_DOT_Z);
     }
     if (s->flags & (STEEPEST_DESCENT | CGNR)) {                                         // solver.c:177-229, 232-292
       C *dir = (s->flags & CGNR) ? p : z;     // search direction
       cp_w(fhat_in, wh(), dir, N);
-      NFFTCU_TRY(nfftcu_trafo_dev(s->plan, fhat_in, vv));
+      NFFTCU_TRY(trafo(fhat_in, vv));
       dot(vv, w(), M, SC_DOT_V, -1, SC_ALPHA, SC_DOT_Z, SC_DOT_V);                       // alpha = dot_z / dot_v
       xpawy(fh, SC_ALPHA, (T) 1, wh(), dir, N);
       NFFTCU_TRY(mirror(s->ev_fhat, fhat_host, fh, nb_fh));
       upd_dot_cp(r, SC_ALPHA, (T) -1, vv, w(), M, f_in, SC_DOT_R);                       // r -= alpha v; dot_r; f_in = w r
       NFFTCU_TRY(mirror(s->ev_r, r_host, r, nb_r));
-      NFFTCU_TRY(nfftcu_adjoint_dev(s->plan, f_in, z));
+      NFFTCU_TRY(adjoint(f_in, z));
       if (s->flags & CGNR) {
         dot(z, wh(), N, SC_DOT_Z, SC_DOT_Z_OLD, SC_BETA, SC_DOT_Z, SC_DOT_Z_OLD);        // beta = dot_z / dot_z_old
         axpy(p, SC_BETA, (T) 0, z, N);
@@ -264,11 +293,11 @@ struct Ops {
       xpawy(fh, SC_ALPHA, (T) 1, wh(), p, N);
       NFFTCU_TRY(mirror(s->ev_fhat, fhat_host, fh, nb_fh));
       cp_w(fhat_in, wh(), p, N);
-      NFFTCU_TRY(nfftcu_trafo_dev(s->plan, fhat_in, f_in));
+      NFFTCU_TRY(trafo(fhat_in, f_in));
       // r -= alpha (A w_hat p); dot_r_old = dot_r; dot_r; beta = dot_r / dot_r_old; f_in = w r (in place: out == v)
       upd_dot_cp(r, SC_ALPHA, (T) -1, f_in, w(), M, f_in, SC_DOT_R, SC_DOT_R_OLD, SC_BETA, SC_DOT_R, SC_DOT_R_OLD);
       NFFTCU_TRY(mirror(s->ev_r, r_host, r, nb_r));
-      NFFTCU_TRY(nfftcu_adjoint_dev(s->plan, f_in, fhat_in));
+      NFFTCU_TRY(adjoint(f_in, fhat_in));
       axpy(p, SC_BETA, (T) 0, fhat_in, N);
       dot(p, wh(), N, SC_DOT_P);
     }
@@ -276,13 +305,13 @@ struct Ops {
   }
 };
 
-size_t vec_bytes(const nfftcu_solver_s *s, int which) {
-  const size_t r = real_size(s->plan);
+size_t vec_bytes(const nfftcu_solver_s *s, int which) {   // the weights are shared by all right-hand sides
+  const size_t r = real_size(s->plan), K = (size_t) s->K;
   switch (which) {
     case NFFTCU_SOLVER_W: return r * (size_t) s->plan->M;
     case NFFTCU_SOLVER_W_HAT: return r * (size_t) s->plan->N_total;
-    case NFFTCU_SOLVER_Y: case NFFTCU_SOLVER_R_ITER: case NFFTCU_SOLVER_V_ITER: return 2 * r * (size_t) s->plan->M;
-    default: return 2 * r * (size_t) s->plan->N_total;
+    case NFFTCU_SOLVER_Y: case NFFTCU_SOLVER_R_ITER: case NFFTCU_SOLVER_V_ITER: return 2 * r * (size_t) s->plan->M * K;
+    default: return 2 * r * (size_t) s->plan->N_total * K;
   }
 }
 
@@ -294,7 +323,11 @@ using namespace nfftcu;
 extern "C" {
 
 int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) {
-  if (!out || !plan) { set_error("nfftcu_solver_create: null argument"); return NFFTCU_EINVAL; }
+  return nfftcu_solver_create_batch(out, plan, flags, 1);
+}
+
+int nfftcu_solver_create_batch(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags, int K) {
+  if (!out || !plan || K < 1) { set_error("nfftcu_solver_create: null argument or K < 1"); return NFFTCU_EINVAL; }
   const unsigned methods = flags & (LANDWEBER | STEEPEST_DESCENT | CGNR | CGNE);
   if (methods == 0 || (methods & (methods - 1))) {
     set_error("nfftcu_solver_create: exactly one of LANDWEBER, STEEPEST_DESCENT, CGNR, CGNE must be set (flags 0x%x)", flags);
@@ -304,6 +337,7 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
   nfftcu_solver_s *s = new nfftcu_solver_s();
   s->plan = plan;
   s->device = plan->device;   // destroy must not touch the plan: nfft_finalize before solver_finalize is legal (solver.c:373-389)
+  s->K = K;
   s->flags = flags;
   auto fail = [&](int rc) { nfftcu_solver_destroy(s); return rc; };
 #define SOLVER_ALLOC(ptr, bytes)                                                                    \
@@ -322,11 +356,11 @@ int nfftcu_solver_create(nfftcu_solver **out, nfftcu_ctx *plan, unsigned flags) 
   if (flags & PRECOMPUTE_DAMP) SOLVER_ALLOC(s->vec[NFFTCU_SOLVER_W_HAT], vec_bytes(s, NFFTCU_SOLVER_W_HAT));
   SOLVER_ALLOC(s->fhat_in, vec_bytes(s, NFFTCU_SOLVER_F_HAT_ITER));
   SOLVER_ALLOC(s->f_in, vec_bytes(s, NFFTCU_SOLVER_Y));
-  SOLVER_ALLOC(s->sc, 8 * sizeof(double));
-  SOLVER_ALLOC(s->partial, kMaxBlocks * sizeof(double));
+  SOLVER_ALLOC(s->sc, 8 * sizeof(double) * (size_t) K);
+  SOLVER_ALLOC(s->partial, kMaxBlocks * sizeof(double) * (size_t) K);
 #undef SOLVER_ALLOC
-  if (cudaMemset(s->sc, 0, 8 * sizeof(double)) != cudaSuccess ||
-      pool_malloc_host(&s->sc_host, 8 * sizeof(double)) != cudaSuccess ||
+  if (cudaMemset(s->sc, 0, 8 * sizeof(double) * (size_t) K) != cudaSuccess ||
+      pool_malloc_host(&s->sc_host, 8 * sizeof(double) * (size_t) K) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_fhat, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_r, cudaEventDisableTiming) != cudaSuccess) {

@@ -226,3 +226,49 @@ def test_plan_cache_reuses_nodes_and_stays_correct(precision):
     assert rel_l2(eng.trafo(fh), o.trafo(spec["N"], spec["n"], 6, x2, fh)) <= TOL[precision]
     eng.close()
     cabi.lib().nfftcu_pool_trim()
+
+
+# ---- multi-right-hand-side device solver (the batch API's consumer: multi-coil CGNR) ---------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("method", ["CGNR", "CGNE", "LANDWEBER", "STEEPEST_DESCENT"])
+def test_batched_solver_equals_independent_solvers(method, precision):
+    """nfftcu_solver_create_batch with K = 3 right-hand sides against three K = 1 device solvers (each of which is
+    checked against the reference's solver.c in test_device_solver_vs_reference): iterates, residuals and scalars."""
+    spec = dict(d=2, N=[32, 32], n=[64, 64], m=6, M=3000, seed=91)
+    x, _, _ = make_case(spec, precision)
+    rng = np.random.default_rng(7)
+    K, iters = 3, 6
+    cplx = np.complex128 if precision == "double" else np.complex64
+    real = np.float64 if precision == "double" else np.float32
+    y = (rng.random((K, spec["M"])) - 0.5 + 1j * (rng.random((K, spec["M"])) - 0.5)).astype(cplx)
+    w = (0.5 + rng.random(spec["M"])).astype(real)
+    w_hat = (0.5 + rng.random(32 * 32)).astype(real)
+    flags = getattr(cabi, method) | cabi.PRECOMPUTE_WEIGHT | cabi.PRECOMPUTE_DAMP
+    if method == "LANDWEBER":
+        flags |= cabi.NORMS_FOR_LANDWEBER
+    eng = cabi.Engine(spec["N"], spec["n"], 6, spec["M"], precision=precision)
+    eng.set_nodes(x)
+
+    def run(Kr, ys):
+        s = cabi.BatchSolver(eng, flags, Kr)
+        s.upload(cabi.SOLVER_Y, ys)
+        s.upload(cabi.SOLVER_W, w)
+        s.upload(cabi.SOLVER_W_HAT, w_hat)
+        s.upload(cabi.SOLVER_F_HAT_ITER, np.zeros((Kr, 32 * 32), dtype=cplx))
+        s.scal[:, 0] = 1e-3                     # alpha_iter is caller-owned for LANDWEBER
+        sc = [s.before_loop()]
+        for _ in range(iters):
+            s.scal[:, 0] = 1e-3 if method == "LANDWEBER" else s.scal[:, 0]
+            sc.append(s.step())
+        out = (s.download(cabi.SOLVER_F_HAT_ITER), s.download(cabi.SOLVER_R_ITER), np.array(sc))
+        s.close()
+        return out
+
+    fh_b, r_b, sc_b = run(K, y)
+    for k in range(K):
+        fh_1, r_1, sc_1 = run(1, y[k:k + 1])
+        tol = 1e-12 if precision == "double" else 1e-5
+        assert rel_l2(fh_b[k], fh_1[0]) <= tol
+        assert rel_l2(r_b[k], r_1[0]) <= tol
+        assert np.allclose(sc_b[:, k, :], sc_1[:, 0, :], rtol=1e-10 if precision == "double" else 1e-4, atol=0)
+    eng.close()

@@ -132,7 +132,7 @@ def cfg5(coils, cpu_coils, iters=20):
     return out
 
 
-def cfg5_multi_gpu(coils, gpus, iters=20):
+def cfg5_multi_gpu(coils, gpus, iters=20, batched=False):
     """cfg5 distributed plan-per-GPU (SURVEY 8e "Batched / multi-coil": replicas only, no collective): coil c runs on
     GPU c mod gpus, one worker process per GPU (env NFFT_B200_DEVICE), each driving the device-resident solver
     through the unmodified plan-per-coil call sequence of reconstruct_data_2d.c.  Wall clock of the slowest worker,
@@ -145,7 +145,8 @@ def cfg5_multi_gpu(coils, gpus, iters=20):
     for r in range(gpus):
         mine = [c for c in range(coils) if c % gpus == r]
         env = dict(os.environ, NFFT_B200_DEVICE=str(r))
-        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cfg5-worker",
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__),
+                                       "--cfg5-batch-worker" if batched else "--cfg5-worker",
                                        ",".join(map(str, mine)), "--go-file", go, "--iters", str(iters)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     # workers print READY after warm-up; release them together
@@ -167,6 +168,46 @@ def cfg5_multi_gpu(coils, gpus, iters=20):
     return dict(gpus=gpus, coils=coils, iters=iters, seconds=slowest, seconds_per_coil=slowest / coils,
                 coils_per_s=coils / slowest, transforms_per_s=coils * iters * 2 / slowest, parent_wall_seconds=wall,
                 workers=per)
+
+
+def cfg5_batch_worker(coil_ids, go_file, iters):
+    """The same reconstruction with the coils of this GPU as ONE batched solve: one plan, one node set, K = len(coil_ids)
+    right-hand sides in lock-step (nfftcu_solver_create_batch on nfftcu_*_batch_dev).  Timed: plan creation, node set-up,
+    uploads, before_loop + `iters` steps, download of the iterates."""
+    from nfft_b200 import cabi
+    N, n, m, M = [512, 512], [1024, 1024], 6, 512 * 512
+    x = spiral(M, 512)
+    NN = 512 * 512
+    k = np.stack(np.meshgrid(*[np.arange(-v // 2, v // 2) / v for v in N], indexing="ij"), -1)
+    w_hat = np.ascontiguousarray((np.sqrt((k ** 2).sum(-1)) <= 0.5).astype(np.float64).ravel())
+    rng = np.random.default_rng(5)
+    K = len(coil_ids)
+    ys = np.ascontiguousarray(np.stack([rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5) for _ in coil_ids]))
+    dev = int(os.environ.get("NFFT_B200_DEVICE", "0"))
+
+    def solve():
+        eng = cabi.Engine(N, n, m, M, device=dev)
+        eng.set_option(cabi.OPT_PSI_TABLE, 1)
+        eng.set_nodes(x)
+        s = cabi.BatchSolver(eng, cabi.CGNR | cabi.PRECOMPUTE_DAMP, K)
+        s.upload(cabi.SOLVER_Y, ys)
+        s.upload(cabi.SOLVER_W_HAT, w_hat)
+        s.upload(cabi.SOLVER_F_HAT_ITER, np.zeros((K, NN), dtype=np.complex128))
+        s.before_loop()
+        for _ in range(iters):
+            sc = s.step()
+        out = s.download(cabi.SOLVER_F_HAT_ITER)
+        s.close()
+        eng.close()
+        return out, sc
+    solve()            # warm-up: context creation, module load
+    print("READY", flush=True)
+    while not os.path.exists(go_file):
+        time.sleep(0.0005)
+    t0 = time.perf_counter()
+    out, sc = solve()
+    dt = time.perf_counter() - t0
+    print(json.dumps(dict(device=str(dev), coils=K, seconds=dt, last_dot_r=float(sc[-1, 2]))), flush=True)
 
 
 def cfg5_worker(coil_ids, go_file, iters):
@@ -207,6 +248,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1, help="cfg5: distribute the coils plan-per-GPU over this many GPUs")
     ap.add_argument("--cfg5-worker", default=None)
+    ap.add_argument("--cfg5-batch-worker", default=None)
     ap.add_argument("--go-file", default=None)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--configs", default="cfg1,cfg2,cfg4,cfg5")
@@ -214,6 +256,9 @@ def main():
     ap.add_argument("--cpu-coils", type=int, default=1)
     ap.add_argument("--cfg4-nodes", type=int, default=100_000_000)
     args = ap.parse_args()
+    if args.cfg5_batch_worker is not None:
+        cfg5_batch_worker([int(v) for v in args.cfg5_batch_worker.split(",") if v], args.go_file, args.iters)
+        return
     if args.cfg5_worker is not None:
         cfg5_worker([int(v) for v in args.cfg5_worker.split(",") if v], args.go_file, args.iters)
         return
@@ -247,6 +292,10 @@ def main():
     if "cfg5" in want:
         print(json.dumps(dict(config="cfg5: 2-D CGNR 20 iterations x %d coils, 512^2 spiral, reference solver.c on the engine"
                                      % args.coils, **cfg5(args.coils, args.cpu_coils))), flush=True)
+    if "cfg5batch" in want:
+        print(json.dumps(dict(config="cfg5 batched: 2-D CGNR 20 iterations x %d coils over %d GPUs, 512^2 spiral, the coils of "
+                                     "a GPU as ONE batched solve (nfftcu_solver_create_batch), one worker process per GPU"
+                                     % (args.coils, args.gpus), **cfg5_multi_gpu(args.coils, args.gpus, batched=True))), flush=True)
     if "cfg5mg" in want:
         print(json.dumps(dict(config="cfg5 plan-per-GPU: 2-D CGNR 20 iterations x %d coils over %d GPUs, 512^2 spiral, "
                                      "device-resident solver_*_complex, one worker process per GPU, no collective"
