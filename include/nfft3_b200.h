@@ -216,6 +216,16 @@ void mri_inh_3d_finalize(mri_inh_3d_plan *ths);
 #define PRE_ONE_PSI (PRE_LIN_PSI | PRE_FG_PSI | PRE_PSI | PRE_FULL_PSI)
 #endif
 
+/* split-phase extensions (no reference counterpart): begin enqueues copy-in + transform + copy-out on the plan's stream
+ * and returns, wait returns when they are done; two plans overlap their copies with each other's kernels.  Buffers must
+ * be nfft_malloc'ed (page-locked) and untouched until the wait; the resident nodes are used as they are. */
+void nfft_b200_trafo_begin(nfft_plan *ths);
+void nfft_b200_adjoint_begin(nfft_plan *ths);
+void nfft_b200_wait(nfft_plan *ths);
+void nfftf_b200_trafo_begin(nfftf_plan *ths);
+void nfftf_b200_adjoint_begin(nfftf_plan *ths);
+void nfftf_b200_wait(nfftf_plan *ths);
+
 /* util entry points of include/nfft3.h:839-890 that the plan initialisers depend on */
 NFFT_INT nfft_next_power_of_2(const NFFT_INT N);
 NFFT_INT nfftf_next_power_of_2(const NFFT_INT N);

@@ -119,6 +119,14 @@ int nfftcu_adjoint(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);
  * NULL) reports whether the nodes were replaced, i.e. whether index_x has to be fetched again. */
 int nfftcu_trafo_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_hat_host, void *f_host, int *changed);
 int nfftcu_adjoint_refresh(nfftcu_ctx *ctx, const void *x_host, const void *f_host, void *f_hat_host, int *changed);
+/* Split-phase variants (no reference counterpart): *_begin enqueues the H2D copy, the transform and the D2H copy on the
+ * plan's stream and returns at once; nfftcu_end waits for them.  With page-locked host buffers (nfft_malloc) two plans --
+ * e.g. the trafo plan and the adjoint plan of an iteration on independent data -- overlap their copies with each other's
+ * kernels; bench.py reports that as e2e.overlapped.  The resident nodes are used as they are; the host buffers must not
+ * be touched between begin and end. */
+int nfftcu_trafo_begin(nfftcu_ctx *ctx, const void *f_hat_host, void *f_host);
+int nfftcu_adjoint_begin(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);
+int nfftcu_end(nfftcu_ctx *ctx);
 /* nfft_trafo_direct / nfft_adjoint_direct (nfft.c:145-297): exact NDFT */
 int nfftcu_trafo_direct(nfftcu_ctx *ctx, const void *f_hat_host, void *f_host);
 int nfftcu_adjoint_direct(nfftcu_ctx *ctx, const void *f_host, void *f_hat_host);

@@ -25,7 +25,7 @@ SYMBOLS = (
     "nfftcu_last_error", "nfftcu_device_count", "nfftcu_create", "nfftcu_destroy",
     "nfftcu_get_c_phi_inv", "nfftcu_get_window_params", "nfftcu_get_window_scale", "nfftcu_set_nodes", "nfftcu_set_nodes_dev",
     "nfftcu_nodes_version", "nfftcu_get_index_x", "nfftcu_trafo", "nfftcu_adjoint",
-    "nfftcu_trafo_direct", "nfftcu_adjoint_direct", "nfftcu_trafo_dev", "nfftcu_adjoint_dev",
+    "nfftcu_trafo_direct", "nfftcu_adjoint_direct", "nfftcu_trafo_begin", "nfftcu_adjoint_begin", "nfftcu_end", "nfftcu_trafo_dev", "nfftcu_adjoint_dev",
     "nfftcu_trafo_direct_dev", "nfftcu_adjoint_direct_dev", "nfftcu_stage_D", "nfftcu_stage_F",
     "nfftcu_stage_B", "nfftcu_stage_BT", "nfftcu_stage_DT", "nfftcu_grid_ptr", "nfftcu_set_option",
     "nfftcu_set_stream", "nfftcu_get_stream", "nfftcu_sync", "nfftcu_stage_times", "nfftcu_b_kernel_time", "nfftcu_trafo_refresh", "nfftcu_adjoint_refresh",
@@ -68,10 +68,13 @@ def lib() -> C.CDLL:
                      "nfftcu_stage_D", "nfftcu_stage_B", "nfftcu_stage_BT", "nfftcu_stage_DT",
                      "nfftcu_set_stream"):
             getattr(L, name).argtypes = [vp, vp]
-        for name in ("nfftcu_trafo", "nfftcu_adjoint", "nfftcu_trafo_direct", "nfftcu_adjoint_direct",
+        for name in ("nfftcu_trafo", "nfftcu_adjoint", "nfftcu_trafo_direct", "nfftcu_adjoint_direct", "nfftcu_trafo_begin", "nfftcu_adjoint_begin", "nfftcu_end",
                      "nfftcu_trafo_dev", "nfftcu_adjoint_dev", "nfftcu_trafo_direct_dev",
                      "nfftcu_adjoint_direct_dev"):
             getattr(L, name).argtypes = [vp, vp, vp]
+        for name in ("nfftcu_trafo_begin", "nfftcu_adjoint_begin"):
+            getattr(L, name).argtypes = [vp, vp, vp]
+        L.nfftcu_end.argtypes = [vp]
         L.nfftcu_nodes_version.argtypes = [vp]
         L.nfftcu_nodes_version.restype = i64
         L.nfftcu_stage_F.argtypes = [vp, ci]

@@ -813,6 +813,32 @@ int nfftcu_adjoint_refresh(nfftcu_ctx *c, const void *x_host, const void *f_host
   return host_transform_refresh(c, x_host, f_host, f_hat_host, 1, changed);
 }
 
+// Split-phase host-pointer transforms: *_begin enqueues H2D, the transform and D2H on the plan's stream and returns;
+// nfftcu_end waits.  Two plans (or one plan and the caller's own work) can then overlap their copies with each other's
+// kernels -- the synchronous nfft_trafo / nfft_adjoint cannot, the reference API has no such notion.  The host buffers
+// must be page-locked (nfft_malloc'ed) for the copies to be asynchronous and must stay untouched until nfftcu_end;
+// the resident nodes are used as they are (no refresh, like a plan with PRE_PSI).
+static int host_begin(nfftcu_ctx *c, const void *in_host, void *out_host, bool forward) {
+  NFFTCU_TRY(check_ctx(c));
+  NFFTCU_TRY(bind_device(c));
+  NFFTCU_TRY(need_nodes(c));
+  NFFTCU_TRY(ensure_staging(c));
+  const size_t in_bytes = forward ? cbytes(c, c->N_total) : cbytes(c, c->M);
+  const size_t out_bytes = forward ? cbytes(c, c->M) : cbytes(c, c->N_total);
+  void *in_dev = forward ? c->fhat_dev : c->f_dev, *out_dev = forward ? c->f_dev : c->fhat_dev;
+  if (in_bytes) NFFTCU_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  const int timing = c->opt_timing;
+  c->opt_timing = 0;   // the stage timers synchronise
+  const int r = forward ? trafo_dev_impl(c, in_dev, out_dev) : adjoint_dev_impl(c, in_dev, out_dev);
+  c->opt_timing = timing;
+  if (r != NFFTCU_OK) return r;
+  if (out_bytes) NFFTCU_CUDA(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  return NFFTCU_OK;
+}
+int nfftcu_trafo_begin(nfftcu_ctx *c, const void *f_hat_host, void *f_host) { return host_begin(c, f_hat_host, f_host, true); }
+int nfftcu_adjoint_begin(nfftcu_ctx *c, const void *f_host, void *f_hat_host) { return host_begin(c, f_host, f_hat_host, false); }
+int nfftcu_end(nfftcu_ctx *c) { return nfftcu_sync(c); }
+
 int nfftcu_trafo(nfftcu_ctx *c, const void *f_hat_host, void *f_host) {
   return host_transform(c, f_hat_host, f_host, 0);
 }

@@ -410,6 +410,31 @@ void X(adjoint)(X(plan) *ths)
   store_times(ths);
 }
 
+/* ---- split-phase extensions (not part of the reference API; include/nfft3_b200.h) ------------------------------
+ * nfft_b200_trafo_begin / nfft_b200_adjoint_begin enqueue copy-in, transform and copy-out on the plan's stream and
+ * return; nfft_b200_wait returns when they are done.  The nodes must be resident (nfft_precompute_* or an earlier
+ * transform) and unchanged; f / f_hat must be page-locked (nfft_malloc) to overlap, and untouched until the wait. */
+void X(b200_trafo_begin)(X(plan) *ths)
+{
+  if (!ths->f_hat || !ths->f) X(die)("nfft_b200_trafo_begin: f_hat or f is NULL");
+  if (group_of(ths)) X(die)("nfft_b200_trafo_begin: not available on multi-device plans");
+  if (nodes_version(ths) == 0) upload_nodes(ths);
+  check_cu(nfftcu_trafo_begin(ctx_of(ths), ths->f_hat, ths->f));
+}
+
+void X(b200_adjoint_begin)(X(plan) *ths)
+{
+  if (!ths->f_hat || !ths->f) X(die)("nfft_b200_adjoint_begin: f_hat or f is NULL");
+  if (group_of(ths)) X(die)("nfft_b200_adjoint_begin: not available on multi-device plans");
+  if (nodes_version(ths) == 0) upload_nodes(ths);
+  check_cu(nfftcu_adjoint_begin(ctx_of(ths), ths->f, ths->f_hat));
+}
+
+void X(b200_wait)(X(plan) *ths)
+{
+  if (!group_of(ths)) check_cu(nfftcu_end(ctx_of(ths)));
+}
+
 void X(trafo_1d)(X(plan) *ths) { X(trafo)(ths); }
 void X(trafo_2d)(X(plan) *ths) { X(trafo)(ths); }
 void X(trafo_3d)(X(plan) *ths) { X(trafo)(ths); }

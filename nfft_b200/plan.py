@@ -173,6 +173,11 @@ class Plan:
     def trafo_direct(self): self._call("trafo_direct")
     def adjoint_direct(self): self._call("adjoint_direct")
 
+    # split-phase extensions (product library only): begin returns at once, wait blocks until the plan's work is done
+    def trafo_begin(self): self._call("b200_trafo_begin")
+    def adjoint_begin(self): self._call("b200_adjoint_begin")
+    def wait(self): self._call("b200_wait")
+
     def trafo_nd(self):
         self._call(f"trafo_{self.d}d")
 

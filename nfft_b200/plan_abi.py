@@ -135,4 +135,11 @@ def bind_api(lib: C.CDLL, prefix: str):
     f.argtypes = [C.c_void_p]
     f.restype = None
     ns["free"] = f
+    # split-phase extensions of libnfft3_b200.so (absent from a reference build)
+    for fn in ("b200_trafo_begin", "b200_adjoint_begin", "b200_wait"):
+        if hasattr(lib, prefix + fn):
+            f = getattr(lib, prefix + fn)
+            f.argtypes = [pp]
+            f.restype = None
+            ns[fn] = f
     return struct, ns

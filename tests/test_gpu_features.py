@@ -272,3 +272,30 @@ def test_batched_solver_equals_independent_solvers(method, precision):
         assert rel_l2(r_b[k], r_1[0]) <= tol
         assert np.allclose(sc_b[:, k, :], sc_1[:, 0, :], rtol=1e-10 if precision == "double" else 1e-4, atol=0)
     eng.close()
+
+
+# ---- split-phase plan API extension ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_split_phase_transforms_overlap_two_plans(precision):
+    """nfft_b200_trafo_begin / nfft_b200_adjoint_begin / nfft_b200_wait on two plans in flight at once: the same results
+    as the synchronous calls (oracle), repeated with fresh data to exercise buffer reuse."""
+    spec = dict(d=3, N=[32, 32, 32], n=[64, 64, 64], m=6, M=40000, seed=95)
+    flags = BASE | abi.PRE_PSI
+    x, fh, f = make_case(spec, precision)
+    o = common.oracle(precision)
+    p = Plan.init_guru(3, spec["N"], spec["M"], spec["n"], 6, flags, precision=precision)
+    q = Plan.init_guru(3, spec["N"], spec["M"], spec["n"], 6, flags, precision=precision)
+    for pl in (p, q):
+        pl.x[:] = x
+        pl.precompute_one_psi()
+    for rep in range(3):
+        p.f_hat[:] = fh * (rep + 1)
+        q.f[:] = f * (rep + 1)
+        p.trafo_begin()
+        q.adjoint_begin()
+        p.wait()
+        q.wait()
+        assert rel_l2(p.f, (rep + 1) * o.trafo(spec["N"], spec["n"], 6, x, fh)) <= TOL[precision]
+        assert rel_l2(q.f_hat, (rep + 1) * o.adjoint(spec["N"], spec["n"], 6, x, f, True)) <= TOL[precision]
+    p.finalize()
+    q.finalize()
