@@ -187,6 +187,36 @@ class ShardedPlan:
             f_hat_host.copy_(fh_d, non_blocking=True)
         torch.cuda.current_stream(fh_d.device).synchronize()
 
+    def pair_host(self, f_hat_host, f_out_host, f_in_host, f_hat_out_host, device: int = 0, root: int = 0):
+        """One trafo (f_hat_host -> f_out_host) and one adjoint (f_in_host -> f_hat_out_host) on independent data with
+        the copies overlapped with the kernels: the adjoint's samples go up on a side stream while the trafo computes,
+        the trafo's result comes down while the adjoint computes.  Same bytes as trafo_host + adjoint_host."""
+        import torch
+        fh_d, f_d = self._staging(f_hat_host, f_out_host, device)
+        if getattr(self, "_st2", None) is None:
+            self._st2 = (torch.empty_like(f_d), torch.empty_like(fh_d), torch.cuda.Stream(fh_d.device))
+        f2_d, fh2_d, side = self._st2
+        main = torch.cuda.current_stream(fh_d.device)
+        side.wait_stream(main)                       # earlier work on the buffers
+        with torch.cuda.stream(side):
+            f2_d.copy_(f_in_host, non_blocking=True)
+        if self.world == 1 or root is None:
+            fh_d.copy_(f_hat_host, non_blocking=True)
+        else:
+            if self.rank == root:
+                fh_d.copy_(f_hat_host, non_blocking=True)
+            self.dist.broadcast(fh_d, src=root, group=self.group)
+        self.trafo(fh_d, f_d)
+        side.wait_stream(main)                       # trafo done (and the upload above): bring its result down ...
+        with torch.cuda.stream(side):
+            f_out_host.copy_(f_d, non_blocking=True)
+        main.wait_stream(side)                       # ... the adjoint needs the uploaded samples (already there)
+        self.adjoint(f2_d, fh2_d)
+        if root is None or self.rank == root or self.world == 1:
+            f_hat_out_host.copy_(fh2_d, non_blocking=True)
+        main.synchronize()
+        side.synchronize()
+
     def collective_ms(self, f_hat, reps: int = 5) -> float:
         """Device time of D^T + cross-rank reduction alone (on whatever the grids hold), max over ranks."""
         import torch
