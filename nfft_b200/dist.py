@@ -194,12 +194,13 @@ class ShardedPlan:
         import torch
         fh_d, f_d = self._staging(f_hat_host, f_out_host, device)
         if getattr(self, "_st2", None) is None:
-            self._st2 = (torch.empty_like(f_d), torch.empty_like(fh_d), torch.cuda.Stream(fh_d.device))
-        f2_d, fh2_d, side = self._st2
+            self._st2 = (torch.empty_like(f_d), torch.empty_like(fh_d), torch.cuda.Stream(fh_d.device),
+                         torch.cuda.Stream(fh_d.device))
+        f2_d, fh2_d, s_up, s_dn = self._st2
         main = torch.cuda.current_stream(fh_d.device)
-        side.wait_stream(main)                       # earlier work on the buffers
-        with torch.cuda.stream(side):
-            f2_d.copy_(f_in_host, non_blocking=True)
+        s_up.wait_stream(main)                       # earlier work on the staging buffers
+        with torch.cuda.stream(s_up):
+            f2_d.copy_(f_in_host, non_blocking=True)     # overlaps the trafo's kernels
         if self.world == 1 or root is None:
             fh_d.copy_(f_hat_host, non_blocking=True)
         else:
@@ -207,15 +208,15 @@ class ShardedPlan:
                 fh_d.copy_(f_hat_host, non_blocking=True)
             self.dist.broadcast(fh_d, src=root, group=self.group)
         self.trafo(fh_d, f_d)
-        side.wait_stream(main)                       # trafo done (and the upload above): bring its result down ...
-        with torch.cuda.stream(side):
-            f_out_host.copy_(f_d, non_blocking=True)
-        main.wait_stream(side)                       # ... the adjoint needs the uploaded samples (already there)
+        s_dn.wait_stream(main)                       # trafo done: its result comes down on its own stream ...
+        with torch.cuda.stream(s_dn):
+            f_out_host.copy_(f_d, non_blocking=True)     # ... while the adjoint computes
+        main.wait_stream(s_up)                       # the adjoint needs the uploaded samples only
         self.adjoint(f2_d, fh2_d)
         if root is None or self.rank == root or self.world == 1:
             f_hat_out_host.copy_(fh2_d, non_blocking=True)
         main.synchronize()
-        side.synchronize()
+        s_dn.synchronize()
 
     def collective_ms(self, f_hat, reps: int = 5) -> float:
         """Device time of D^T + cross-rank reduction alone (on whatever the grids hold), max over ranks."""
