@@ -225,7 +225,14 @@ int ensure_batch(nfftcu_ctx *c, int K) {
   return NFFTCU_OK;
 }
 
+// the options the node-dependent state (orders, bins, tables, images) was built under
+static unsigned node_opts_signature(const nfftcu_ctx *c) {
+  return (unsigned) (c->opt_b_kernel & 15) | ((unsigned) (c->opt_node_order & 15) << 4) | ((unsigned) (c->opt_psi_table & 1) << 8) |
+         ((unsigned) (c->opt_window_images & 3) << 9) | ((c->flags & (1u << 11)) ? 1u << 11 : 0u);
+}
+
 int nodes_ready(nfftcu_ctx *c) {
+  c->built_sig = node_opts_signature(c);
   if (c->nodes_only) {   // sorter of a multi-GPU group: the reference order is all that is needed
     NFFTCU_TRY(sort_nodes(c));
     c->ref_sorted = true;
@@ -612,6 +619,11 @@ int nfftcu_set_nodes(nfftcu_ctx *c, const void *x_host) {
         c->parked_nodes = false;
         c->have_nodes = true;
         c->nodes_version++;
+      }
+      // ... unless that state was built under other kernel / order options than the ones in force now
+      if (c->built_sig != node_opts_signature(c)) {
+        NFFTCU_TRY(nodes_ready(c));
+        NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
       }
       return NFFTCU_OK;
     }

@@ -114,6 +114,7 @@ struct nfftcu_ctx_s {
   bool psi_table_valid = false;     // table was built for the current nodes (nodes_ready clears it)
   uint64_t x_fp = 0;                // fingerprint of the HOST array the resident nodes were uploaded from
   bool x_fp_valid = false;
+  unsigned built_sig = 0;           // node_opts_signature at the time the node-dependent state was built
   bool parked_nodes = false;        // revived from the plan cache: node state of the previous owner, not yet adopted
   // tile-binned order for the 3-D pencil-sweep kernels (tile3d.cu)
   bool tile_ready = false;

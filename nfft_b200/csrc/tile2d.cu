@@ -117,18 +117,46 @@ __global__ void tile2_gather_f_kernel(const C2 *__restrict__ f, const uint32_t *
 // | node origin (r0, c0) relative to the footprint
 struct NodeOrg { short r0, c0; };
 
-// window values of the chunk's nodes: thread per (node, dim, tap)
+// Node data of a round (coordinates, and the samples for spreading), staged in shared memory ONE ROUND AHEAD: the
+// global loads of round r + 1 are issued before the node loop of round r and stored after it, so that the window
+// evaluation never waits for L2 (the per-value loads it replaces were the top stall of both kernels:
+// profiles/r2_full_new_kernels.md, 30 % of the samples on the first use of x / f).
+template <typename TS>
+struct NodeStage {
+  TS x[kChunkNodes * 2];
+  typename Cplx<TS>::type f[kChunkNodes];
+};
+// thread t carries coordinate t (t < 2 cnt) and sample t (t < cnt) of the next round in registers
 template <typename TS, bool SPREAD>
-__device__ __forceinline__ void chunk_windows(const TS *__restrict__ xt, const typename Cplx<TS>::type *__restrict__ ft,
-                                              const double *__restrict__ poly, const Tile2Params &P, int k0, int cnt,
-                                              int ta, int tb, double *psi0, double *psi1, NodeOrg *org, double *coef) {
-  if (P.use_poly) {   // the polynomial coefficients of both dimensions: 2 (deg+1) W doubles, read (deg+1) times per value
-    for (int i = threadIdx.x; i < 2 * (kKbPolyDeg + 1) * P.W; i += blockDim.x) coef[i] = poly[i];
-    __syncthreads();
+__device__ __forceinline__ void node_load(const TS *__restrict__ xt, const typename Cplx<TS>::type *__restrict__ ft,
+                                          int k0, int cnt, TS &rx, TS &rfx, TS &rfy) {
+  const int t = threadIdx.x;
+  rx = (t < 2 * cnt) ? xt[2 * (size_t) k0 + t] : (TS) 0;
+  rfx = rfy = (TS) 0;
+  if (SPREAD && t < cnt) {
+    const typename Cplx<TS>::type v = ft[(size_t) k0 + t];
+    rfx = v.x;
+    rfy = v.y;
   }
+}
+template <typename TS, bool SPREAD>
+__device__ __forceinline__ void node_store(NodeStage<TS> &st, int cnt, TS rx, TS rfx, TS rfy) {
+  const int t = threadIdx.x;
+  if (t < 2 * cnt) st.x[t] = rx;
+  if (SPREAD && t < cnt) {
+    st.f[t].x = rfx;
+    st.f[t].y = rfy;
+  }
+}
+
+// window values of the chunk's nodes: thread per (node, dim, tap); node data from the staged copy
+template <typename TS, bool SPREAD>
+__device__ __forceinline__ void chunk_windows(const NodeStage<TS> &ns, const Tile2Params &P, int cnt,
+                                              int ta, int tb, double *psi0, double *psi1, NodeOrg *org,
+                                              const double *coef) {
   for (int i = threadIdx.x; i < cnt * 2 * kMaxW2; i += blockDim.x) {
     const int l = i % kMaxW2, t = (i / kMaxW2) & 1, j = i / (2 * kMaxW2);
-    const TS x = xt[2 * (size_t) (k0 + j) + t];
+    const TS x = ns.x[2 * j + t];
     const int n = t == 0 ? P.n0 : P.n1;
     const long long c = cell_of(x, (long long) n);
     double v = 0.0;
@@ -146,7 +174,7 @@ __device__ __forceinline__ void chunk_windows(const TS *__restrict__ xt, const t
     if (t == 0) psi0[j * kMaxW2 + l] = v;
     else if (!SPREAD) psi1[j * kMaxW2 + l] = v;
     else {
-      const typename Cplx<TS>::type fv = ft[k0 + j];
+      const typename Cplx<TS>::type fv = ns.f[j];
       psi1[2 * (j * kMaxW2 + l)] = v * (double) fv.x;
       psi1[2 * (j * kMaxW2 + l) + 1] = v * (double) fv.y;
     }
@@ -172,9 +200,14 @@ interp_tile2_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__r
   double *psi1 = psi0 + kChunkNodes * kMaxW2;
   NodeOrg *org = reinterpret_cast<NodeOrg *>(psi1 + kChunkNodes * kMaxW2);
   double *coef = reinterpret_cast<double *>(org + kChunkNodes);
+  NodeStage<TS> &ns = *reinterpret_cast<NodeStage<TS> *>(coef + 2 * (kKbPolyDeg + 1) * kMaxW2);
   const uint4 ch = chunks[blockIdx.x];
   const int ta = (int) ch.x / P.NT1, tb = (int) ch.x - ta * P.NT1;
   const int kbeg = (int) ch.y, kend = (int) ch.z;
+  TS nx, nfx, nfy;   // next round's node data of this thread
+  node_load<TS, false>(xt, nullptr, kbeg, min(kChunkNodes, kend - kbeg), nx, nfx, nfy);
+  if (P.use_poly)   // polynomial coefficients of both dimensions, once per CTA
+    for (int i = threadIdx.x; i < 2 * (kKbPolyDeg + 1) * P.W; i += blockDim.x) coef[i] = poly[i];
 
   for (int i = threadIdx.x; i < P.F * P.F; i += blockDim.x) {
     const int r = i / P.F, cc = i - r * P.F;
@@ -184,7 +217,11 @@ interp_tile2_kernel(const typename Cplx<TS>::type *__restrict__ G, const TS *__r
   const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
   for (int k0 = kbeg; k0 < kend; k0 += kChunkNodes) {
     const int cnt = min(kChunkNodes, kend - k0);
-    chunk_windows<TS, false>(xt, nullptr, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
+    node_store<TS, false>(ns, cnt, nx, nfx, nfy);
+    __syncthreads();   // staged nodes (and, in the first round, the footprint and the coefficients) are visible
+    if (k0 + kChunkNodes < kend)   // next round's nodes: in flight during this round
+      node_load<TS, false>(xt, nullptr, k0 + kChunkNodes, min(kChunkNodes, kend - k0 - kChunkNodes), nx, nfx, nfy);
+    chunk_windows<TS, false>(ns, P, cnt, ta, tb, psi0, psi1, org, coef);
     __syncthreads();
     for (int j0 = 0; j0 < cnt; j0 += kThreads2 / 16) {   // warp-uniform trip count: the shuffles below need all 32 lanes
       const int j = j0 + hw;
@@ -237,9 +274,14 @@ spread_tile2_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restric
   double *psi1 = psi0 + kChunkNodes * kMaxW2;                       // (psi1 * f) complex
   NodeOrg *org = reinterpret_cast<NodeOrg *>(psi1 + 2 * kChunkNodes * kMaxW2);
   double *coef = reinterpret_cast<double *>(org + kChunkNodes);
+  NodeStage<TS> &ns = *reinterpret_cast<NodeStage<TS> *>(coef + 2 * (kKbPolyDeg + 1) * kMaxW2);
   const uint4 ch = chunks[blockIdx.x];
   const int ta = (int) ch.x / P.NT1, tb = (int) ch.x - ta * P.NT1;
   const int kbeg = (int) ch.y, kend = (int) ch.z;
+  TS nx, nfx, nfy;   // next round's node data of this thread
+  node_load<TS, true>(xt, ft, kbeg, min(kChunkNodes, kend - kbeg), nx, nfx, nfy);
+  if (P.use_poly)
+    for (int i = threadIdx.x; i < 2 * (kKbPolyDeg + 1) * P.W; i += blockDim.x) coef[i] = poly[i];
 
   for (int i = threadIdx.x; i < P.F * P.pitch; i += blockDim.x) tile[i] = make_double2(0.0, 0.0);
   // thread (h, l) owns the footprint cells with row = h and column = l (mod 16): a node's <= 16 consecutive rows and
@@ -250,7 +292,11 @@ spread_tile2_kernel(typename Cplx<TS>::type *__restrict__ G, const TS *__restric
   const double2 *pf = reinterpret_cast<const double2 *>(psi1);
   for (int k0 = kbeg; k0 < kend; k0 += kChunkNodes) {
     const int cnt = min(kChunkNodes, kend - k0);
-    chunk_windows<TS, true>(xt, ft, poly, P, k0, cnt, ta, tb, psi0, psi1, org, coef);
+    node_store<TS, true>(ns, cnt, nx, nfx, nfy);
+    __syncthreads();
+    if (k0 + kChunkNodes < kend)
+      node_load<TS, true>(xt, ft, k0 + kChunkNodes, min(kChunkNodes, kend - k0 - kChunkNodes), nx, nfx, nfy);
+    chunk_windows<TS, true>(ns, P, cnt, ta, tb, psi0, psi1, org, coef);
     __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < cnt; j++) {
@@ -303,7 +349,8 @@ Tile2Params make_params2(const nfftcu_ctx *c) {
 
 size_t smem2(const Tile2Params &P, bool spread) {
   return sizeof(double2) * (size_t) P.F * P.pitch + sizeof(double) * kChunkNodes * kMaxW2 * (spread ? 3 : 2) +
-         sizeof(NodeOrg) * kChunkNodes + sizeof(double) * 2 * (kKbPolyDeg + 1) * kMaxW2;
+         sizeof(NodeOrg) * kChunkNodes + sizeof(double) * 2 * (kKbPolyDeg + 1) * kMaxW2 +
+         sizeof(double) * 2 * kChunkNodes + sizeof(double2) * kChunkNodes + 16;   // NodeStage (sized for double)
 }
 
 template <typename TS>
