@@ -186,7 +186,8 @@ int adjoint_dev_impl(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev, bool pee
   if (c->direct_only) return ndft_adjoint(c, f_dev, f_hat_dev);
   StageTimer tm(c);
   tm.mark(0);
-  NFFTCU_TRY(stage_BT(c, f_dev));
+  const bool pruned = c->opt_fft_prune != 0 && !c->fft_no_prune;
+  NFFTCU_TRY(stage_BT(c, f_dev, pruned));
   tm.mark(1);
   NFFTCU_TRY(stage_F(c, +1, c->opt_fft_prune != 0 && !c->fft_no_prune));
   tm.mark(2);
@@ -225,10 +226,63 @@ int ensure_batch(nfftcu_ctx *c, int K) {
   return NFFTCU_OK;
 }
 
+// min / max over the nodes of u_0 = (floor(n_0 x_0) - m) mod n_0, the first plane a node's taps touch
+template <typename T>
+__global__ void slab_minmax_kernel(const T *__restrict__ x, long long M, int d, long long n0, long long m, int *mm) {
+  int lo = 0x7fffffff, hi = -1;
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x; j < M; j += stride) {
+    long long u = (cell_of(x[j * d], n0) - m) % n0;
+    if (u < 0) u += n0;
+    lo = min(lo, (int) u);
+    hi = max(hi, (int) u);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+
+// Slab mode: when the nodes of the plan occupy a slab of the first axis -- a rank of a node-sharded multi-GPU run holds
+// 1/P of the globally sorted nodes -- only the planes [u_min, u_max + 2m + 2) of the grid are ever touched by B / B^T.
+// The pruned F passes and the B^T memset then skip the rest (fft.cu run_axis_slab).  Off when the window is wider than
+// 3/4 of the axis (single-GPU runs), for plans with a split FFT axis and with NFFTCU_OPT_SLAB_FFT = 1.
+static int slab_detect(nfftcu_ctx *c) {
+  c->slab_on = false;
+  if (c->direct_only || c->nodes_only || c->opt_slab == 1 || c->d < 2 || c->M == 0 || c->fft_no_prune ||
+      c->n[0] > 0x3fffffff)
+    return NFFTCU_OK;
+  int *mm = nullptr;
+  NFFTCU_CUDA(pool_malloc((void **) &mm, 2 * sizeof(int)));
+  const int init[2] = {0x7fffffff, -1};
+  NFFTCU_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  long long blocks = (c->M + 255) / 256;
+  if (blocks > (long long) c->sm_count * 8) blocks = (long long) c->sm_count * 8;
+  if (c->prec == NFFTCU_DOUBLE)
+    slab_minmax_kernel<double><<<(unsigned) blocks, 256, 0, c->stream>>>((const double *) c->x_dev, c->M, c->d, c->n[0], c->m, mm);
+  else
+    slab_minmax_kernel<float><<<(unsigned) blocks, 256, 0, c->stream>>>((const float *) c->x_dev, c->M, c->d, c->n[0], c->m, mm);
+  c->launches++;
+  int h[2] = {0, 0};
+  NFFTCU_CUDA(cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+  pool_free(mm);
+  if (h[1] < h[0]) return NFFTCU_OK;
+  const long long wc = (long long) h[1] - h[0] + 2 * c->m + 2;
+  if (4 * wc <= 3 * c->n[0]) {
+    c->slab_on = true;
+    c->slab_w0 = h[0];
+    c->slab_wc = wc;
+  }
+  return NFFTCU_OK;
+}
+
 // the options the node-dependent state (orders, bins, tables, images) was built under
 static unsigned node_opts_signature(const nfftcu_ctx *c) {
   return (unsigned) (c->opt_b_kernel & 15) | ((unsigned) (c->opt_node_order & 15) << 4) | ((unsigned) (c->opt_psi_table & 1) << 8) |
-         ((unsigned) (c->opt_window_images & 3) << 9) | ((c->flags & (1u << 11)) ? 1u << 11 : 0u);
+         ((unsigned) (c->opt_window_images & 3) << 9) | ((c->flags & (1u << 11)) ? 1u << 11 : 0u) |
+         ((unsigned) (c->opt_slab & 1) << 12);
 }
 
 int nodes_ready(nfftcu_ctx *c) {
@@ -260,6 +314,7 @@ int nodes_ready(nfftcu_ctx *c) {
     else if (use_tile2) NFFTCU_TRY(tile2d_bin_nodes(c));
     else if (c->opt_psi_table) NFFTCU_TRY(build_psi_table(c));
   }
+  NFFTCU_TRY(slab_detect(c));
   c->have_nodes = true;
   c->nodes_version++;
   return NFFTCU_OK;
@@ -398,6 +453,7 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
         c->opt_psi_table = 0;
         c->opt_b_flush = 0;
         c->opt_fft_prune = 1;
+        c->opt_slab = 0;
         c->cur_batch = 1;
         // to its new owner the plan has no nodes yet; the parked ones are adopted by the first nfftcu_set_nodes
         // whose host array has the same fingerprint
@@ -1025,6 +1081,7 @@ int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
     case NFFTCU_OPT_FFT_PRUNE: c->opt_fft_prune = (int) value; break;
     case NFFTCU_OPT_FFT_KERNEL: c->opt_fft_kernel = (int) value; break;
     case NFFTCU_OPT_WINDOW_IMAGES: c->opt_window_images = (int) value; break;
+    case NFFTCU_OPT_SLAB_FFT: c->opt_slab = (int) value; break;
     default:
       set_error("nfftcu_set_option: unknown option %d", option);
       return NFFTCU_EINVAL;

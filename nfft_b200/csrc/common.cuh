@@ -98,6 +98,11 @@ struct nfftcu_ctx_s {
   int cur_batch = 1;                          // right-hand sides of the transform in flight: every stage reads it
   void *grid2 = nullptr;                      // second buffer, only for plans with a split (four-step) FFT axis
   bool fft_no_prune = false;                  // a split axis runs unpruned passes
+  // slab mode (nodes_ready -> slab_detect): all taps of the resident nodes lie in the planes [slab_w0, slab_w0 + slab_wc)
+  // (mod n_0) of the first axis; the pruned F passes and the B^T memset then leave every other plane alone (fft.cu)
+  bool slab_on = false;
+  long long slab_w0 = 0, slab_wc = 0;
+  int opt_slab = 0;                           // NFFTCU_OPT_SLAB_FFT: 0 auto | 1 off
   nfftcu::FftAxis fft[NFFTCU_MAX_D];
 
   // nodes
@@ -207,7 +212,7 @@ int fft_plan_axes(nfftcu_ctx *c);                                   // fft.cu
 void fft_free_axes(nfftcu_ctx *c);                                  // fft.cu
 int stage_F(nfftcu_ctx *c, int sign, bool pruned = false);          // fft.cu
 int stage_B(nfftcu_ctx *c, void *f_dev);                            // interp.cu
-int stage_BT(nfftcu_ctx *c, const void *f_dev);                     // spread.cu
+int stage_BT(nfftcu_ctx *c, const void *f_dev, bool slab_ok = false);   // spread.cu; slab_ok: the caller runs the pruned F behind it
 int build_psi_table(nfftcu_ctx *c);                                 // interp.cu
 int ndft_trafo(nfftcu_ctx *c, const void *f_hat_dev, void *f_dev);  // ndft.cu
 int ndft_adjoint(nfftcu_ctx *c, const void *f_dev, void *f_hat_dev);// ndft.cu

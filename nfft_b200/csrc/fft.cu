@@ -49,7 +49,8 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 struct LineGeom {
   long long len;      // transform length L
   long long inner;    // element stride of the axis (product of faster dims)
-  long long lines;    // number of lines = total / len
+  long long icount;   // lines per outer index: inner, or the number of band lines when the inner axes are pruned
+  long long lines;    // number of lines visited = outer count * icount
   int bundle;         // lines per CTA
   long long bundles_inner;  // ceil(inner / bundle) when inner > 1
   int pitch;          // shared-memory pitch of one line (complex elements)
@@ -60,6 +61,17 @@ struct LineGeom {
   long long olow[NFFTCU_MAX_D];     // ... of which the first olow[s] map to l = c, the rest to l = c + n_s - N_s
   long long on[NFFTCU_MAX_D];       // ... and full lengths n_s
   long long elow, ehigh;            // band of this axis: e < elow || e >= ehigh
+  // slab mode (multi-GPU node slabs, see run_axis_slab): a plane window [w0, w0 + wc) mod n_0 of the first axis.
+  //   ooff[s]: offset added (mod on[s]) to the mapped outer coordinate -- the window start when axis s is the first axis
+  //   wload / wstore: on the transform axis itself, elements outside the window are zero (not read) / not needed
+  //   iprune: the axes BEHIND this one are still band-limited: only the lines whose inner coordinates lie in the band
+  //           are visited (compact inner index -> element offset through iN / ilow / in, last inner axis fastest)
+  long long ooff[NFFTCU_MAX_D];
+  int wload, wstore;
+  long long w0, wc;
+  int iprune, niax;
+  long long iN[NFFTCU_MAX_D], ilow[NFFTCU_MAX_D], in_[NFFTCU_MAX_D];
+  long long ialign;   // iprune: a bundle must divide this (both band halves of the last inner axis), host side only
   // four-step split of a long axis (see the header).  twist: this pass is the column pass, element e (= k1) of
   // the line with inner index i is multiplied by W_Ltot^((i / tw_I) * e) = twA[q >> tw_shift] * twB[q & mask]
   // at the store.  tstore: this pass is the row pass over [o][k1][e = k2][i], stored as [o][k2][k1][i].
@@ -82,10 +94,42 @@ __device__ __forceinline__ long long map_outer(const LineGeom &g, long long oc) 
   for (int s = g.nouter - 1; s >= 0; s--) {
     const long long dgt = oc % g.oN[s];
     oc /= g.oN[s];
-    o += (dgt < g.olow[s] ? dgt : dgt + (g.on[s] - g.oN[s])) * mul;
+    long long dr = (dgt < g.olow[s] ? dgt : dgt + (g.on[s] - g.oN[s])) + g.ooff[s];
+    if (dr >= g.on[s]) dr -= g.on[s];
+    o += dr * mul;
     mul *= g.on[s];
   }
   return o;
+}
+
+// compact index over the band lines of the inner axes -> element offset (stride 1 on the last axis)
+__device__ __forceinline__ long long map_inner(const LineGeom &g, long long ic) {
+  if (!g.iprune) return ic;
+  long long i = 0, mul = 1;
+  for (int s = g.niax - 1; s >= 0; s--) {
+    const long long dgt = ic % g.iN[s];
+    ic /= g.iN[s];
+    i += (dgt < g.ilow[s] ? dgt : dgt + (g.in_[s] - g.iN[s])) * mul;
+    mul *= g.in_[s];
+  }
+  return i;
+}
+
+__device__ __forceinline__ bool in_window(const LineGeom &g, int e) {
+  long long ee = (long long) e - g.w0;
+  if (ee < 0) ee += g.len;
+  return ee < g.wc;
+}
+// element e of a line: does it have to be read (else it is zero) / written (else nobody reads it)?
+__device__ __forceinline__ bool keep_load(const LineGeom &g, int e) {
+  if (g.prune == 1 && !(e < g.elow || e >= g.ehigh)) return false;
+  if (g.wload && !in_window(g, e)) return false;
+  return true;
+}
+__device__ __forceinline__ bool keep_store(const LineGeom &g, int e) {
+  if (g.prune == 2 && !(e < g.elow || e >= g.ehigh)) return false;
+  if (g.wstore && !in_window(g, e)) return false;
+  return true;
 }
 
 // global <-> shared staging shared by both kernels.  Line c of bundle b:
@@ -106,7 +150,6 @@ template <typename C, bool STORE>
 __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict__ sm,
                                             const LineGeom &g, long long b, int sign = 0) {
   const int L = (int) g.len;
-  const bool band_only = STORE ? g.prune == 2 : g.prune == 1;
   __shared__ long long line_base[64];
   if (STORE && g.tstore) {
     // row pass of a split axis: line (oc = o * L1 + k1, i), element e = k2 -> [o][k2][k1][i]; the bundle runs
@@ -119,7 +162,7 @@ __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict_
     } else {
       oc = b / g.bundles_inner;
       i0 = (b - oc * g.bundles_inner) * g.bundle;
-      cnt = (int) min((long long) g.bundle, g.inner - i0);
+      cnt = (int) min((long long) g.bundle, g.icount - i0);
     }
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int e = i / cnt, cl = i - e * cnt;
@@ -137,18 +180,18 @@ __device__ __forceinline__ void stage_lines(C *__restrict__ data, C *__restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int cl = i / L, e = i - cl * L;
-      const bool in_band = !band_only || e < g.elow || e >= g.ehigh;
+      const bool in_band = STORE ? keep_store(g, e) : keep_load(g, e);
       if (STORE) { if (in_band) data[line_base[cl] + e] = sm[cl * g.pitch + e]; }
       else sm[cl * g.pitch + e] = in_band ? data[line_base[cl] + e] : C{0, 0};
     }
   } else {
     const long long oc = b / g.bundles_inner;
     const long long i0 = (b - oc * g.bundles_inner) * g.bundle;
-    const int cnt = (int) min((long long) g.bundle, g.inner - i0);
-    C *base = data + map_outer(g, oc) * g.len * g.inner + i0;
+    const int cnt = (int) min((long long) g.bundle, g.icount - i0);
+    C *base = data + map_outer(g, oc) * g.len * g.inner + map_inner(g, i0);   // a bundle never straddles a band gap
     for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
       const int e = i / cnt, cl = i - e * cnt;
-      const bool in_band = !band_only || e < g.elow || e >= g.ehigh;
+      const bool in_band = STORE ? keep_store(g, e) : keep_load(g, e);
       if (STORE) {
         C v = sm[cl * g.pitch + e];
         if (g.twist && e) v = cmul(v, twist_factor<C>(g, (i0 + cl) / g.tw_I, e, sign));
@@ -163,7 +206,7 @@ template <typename C>
 __device__ __forceinline__ int bundle_count(const LineGeom &g, long long b) {
   if (g.inner == 1) return (int) min((long long) g.bundle, g.lines - b * g.bundle);
   const long long o = b / g.bundles_inner;
-  return (int) min((long long) g.bundle, g.inner - (b - o * g.bundles_inner) * g.bundle);
+  return (int) min((long long) g.bundle, g.icount - (b - o * g.bundles_inner) * g.bundle);
 }
 
 // ---- power-of-two lengths: Stockham autosort in shared memory -----------------------------------
@@ -387,7 +430,7 @@ fft_reg_kernel(typename Cplx<T>::type *__restrict__ data, const typename Cplx<T>
     if (g.inner == 1) base += map_outer(g, b * g.bundle + cl) * L;
     else {
       const long long oc = b / g.bundles_inner;
-      base += map_outer(g, oc) * L * g.inner + (b - oc * g.bundles_inner) * g.bundle + cl;
+      base += map_outer(g, oc) * L * g.inner + map_inner(g, (b - oc * g.bundles_inner) * g.bundle) + cl;
       stride = g.inner;
     }
   }
@@ -395,8 +438,7 @@ fft_reg_kernel(typename Cplx<T>::type *__restrict__ data, const typename Cplx<T>
 #pragma unroll
   for (int e = 0; e < 16; e++) {
     const int i = t + TPL * e;
-    const bool in_band = g.prune != 1 || i < g.elow || i >= g.ehigh;
-    v[e] = (active && in_band) ? base[(long long) i * stride] : C{0, 0};
+    v[e] = (active && keep_load(g, i)) ? base[(long long) i * stride] : C{0, 0};
   }
   reg_step<T, SIGN, L, R1, 1, false>(v, t, tw, row);
   __syncthreads();
@@ -416,7 +458,7 @@ fft_reg_kernel(typename Cplx<T>::type *__restrict__ data, const typename Cplx<T>
 #pragma unroll
     for (int e = 0; e < 16; e++) {
       const int i = t + TPL * e;
-      if (g.prune != 2 || i < g.elow || i >= g.ehigh) base[(long long) i * stride] = v[e];
+      if (keep_store(g, i)) base[(long long) i * stride] = v[e];
     }
   }
 }
@@ -735,14 +777,16 @@ int launch_reg(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *dat
   const int seg = (int) (128 / sizeof(C));                 // lines per 128-byte segment of a strided axis
   if (g.inner > 1 && bundle > seg) bundle = seg;
   if (g.inner == 1 && bundle > 8) bundle = 8;
-  if (g.inner > 1 && (long long) bundle > g.inner) bundle = (int) g.inner;
+  if (g.icount == 0) g.icount = g.inner;
+  if (g.inner > 1 && (long long) bundle > g.icount) bundle = (int) g.icount;
   if (bundle < 1) bundle = 1;
+  while (g.iprune && bundle > 1 && g.ialign % bundle) bundle--;   // bundles must not straddle a band gap
   g.len = L;
   g.bundle = bundle;
-  g.bundles_inner = g.inner == 1 ? 1 : (g.inner + bundle - 1) / bundle;
+  g.bundles_inner = g.inner == 1 ? 1 : (g.icount + bundle - 1) / bundle;
   g.pitch = L + L / 16;
   while (g.pitch % 8 != 1) g.pitch++;                      // odd multiple of 16 bytes (fp64) between rows
-  const long long nb = g.inner == 1 ? (g.lines + bundle - 1) / bundle : (g.lines / g.inner) * g.bundles_inner;
+  const long long nb = g.inner == 1 ? (g.lines + bundle - 1) / bundle : (g.lines / g.icount) * g.bundles_inner;
   if (nb > 0x7fffffffll) { set_error("FFT: too many line bundles (%lld)", nb); return NFFTCU_EINVAL; }
   const size_t smem = sizeof(C) * (size_t) g.pitch * bundle;
   const unsigned threads = (unsigned) (bundle * TPL);
@@ -797,11 +841,13 @@ int run_pass(nfftcu_ctx *c, const FftLine &ln, LineGeom g, int sign, void *src, 
     return NFFTCU_EINVAL;
   }
   g.bundle = pref < fit ? pref : fit;
-  if (g.inner > 1 && (long long) g.bundle > g.inner) g.bundle = (int) g.inner;
-  g.bundles_inner = g.inner == 1 ? 1 : (g.inner + g.bundle - 1) / g.bundle;
+  if (g.icount == 0) g.icount = g.inner;
+  if (g.inner > 1 && (long long) g.bundle > g.icount) g.bundle = (int) g.icount;
   if (g.bundle > 64) g.bundle = 64;   // line_base[] of stage_lines
+  while (g.iprune && g.bundle > 1 && g.ialign % g.bundle) g.bundle--;   // bundles must not straddle a band gap
+  g.bundles_inner = g.inner == 1 ? 1 : (g.icount + g.bundle - 1) / g.bundle;
   const long long nb = g.inner == 1 ? (g.lines + g.bundle - 1) / g.bundle
-                                    : (g.lines / g.inner) * g.bundles_inner;
+                                    : (g.lines / g.icount) * g.bundles_inner;
   if (nb > 0x7fffffffll) {
     set_error("FFT: too many line bundles (%lld)", nb);
     return NFFTCU_EINVAL;
@@ -896,6 +942,67 @@ int run_axis(nfftcu_ctx *c, int t, int sign, bool pruned) {
   return run_pass<T>(c, ax.whole, g, sign, c->grid, c->grid);
 }
 
+// ---- slab mode: the F step of a GPU that holds a node SLAB (multi-GPU node sharding) ------------------------------
+// The nodes of the plan touch only the planes [w0, w0 + wc) (mod n_0) of the first axis (slab_detect in api.cu).
+// Forward (after D, before B) only those planes of the result are read, backward (after B^T, before D^T) only
+// those planes of the input are non-zero.  The passes therefore run FIRST AXIS FIRST in the forward direction:
+//   axis 0: the N_1 x N_2 band lines (inner axes still band-limited: iprune), band loads, window stores;
+//   axis 1: window planes x N_2 band lines, band loads;      axis 2: window planes x n_1 lines, band loads;
+// and in the opposite order with loads and stores exchanged in the backward direction.  At sigma = 2 with a window
+// of 78 of 512 planes (cfg4 on 8 GPUs) this visits 27 % of the lines of the full pruned transform.
+template <typename T>
+int run_axis_slab(nfftcu_ctx *c, int t, int sign) {
+  const FftAxis &ax = c->fft[t];
+  LineGeom g;
+  memset(&g, 0, sizeof(g));
+  const long long K = c->cur_batch;
+  long long inner = 1;
+  for (int t2 = t + 1; t2 < c->d; t2++) inner *= c->n[t2];
+  g.inner = inner;
+  g.prune = sign < 0 ? 1 : 2;               // band loads (forward) / band stores (backward) on the transform axis
+  g.elow = c->N[t] - c->N[t] / 2;
+  g.ehigh = c->n[t] - c->N[t] / 2;
+  long long outer = 1;
+  int o0 = 0;
+  if (K > 1) { g.oN[0] = g.olow[0] = g.on[0] = K; outer = K; o0 = 1; }
+  if (t == 0) {
+    // window on the transform axis itself; the inner axes are band-limited
+    if (sign < 0) g.wstore = 1; else g.wload = 1;
+    g.w0 = c->slab_w0;
+    g.wc = c->slab_wc;
+  } else {
+    // the first axis is an outer axis restricted to the window planes
+    g.oN[o0] = g.olow[o0] = c->slab_wc;
+    g.on[o0] = c->n[0];
+    g.ooff[o0] = c->slab_w0;
+    outer *= c->slab_wc;
+    for (int s2 = 1; s2 < t; s2++) {        // axes between the first and this one: already / still in grid space
+      g.oN[o0 + s2] = g.olow[o0 + s2] = g.on[o0 + s2] = c->n[s2];
+      outer *= c->n[s2];
+    }
+  }
+  g.nouter = t + o0;
+  g.icount = inner;
+  if (t + 1 < c->d) {                       // axes behind this one are band-limited: visit the band lines only
+    g.iprune = 1;
+    g.niax = c->d - 1 - t;
+    long long ic = 1;
+    for (int s2 = t + 1; s2 < c->d; s2++) {
+      g.iN[s2 - t - 1] = c->N[s2];
+      g.ilow[s2 - t - 1] = c->N[s2] - c->N[s2] / 2;
+      g.in_[s2 - t - 1] = c->n[s2];
+      ic *= c->N[s2];
+    }
+    g.icount = ic;
+    const long long lo = c->N[c->d - 1] - c->N[c->d - 1] / 2, hi = c->N[c->d - 1] / 2;
+    long long a = lo, b2 = hi;               // gcd
+    while (b2) { const long long r = a % b2; a = b2; b2 = r; }
+    g.ialign = a;
+  }
+  g.lines = outer * g.icount;
+  return run_pass<T>(c, ax.whole, g, sign, c->grid, c->grid);
+}
+
 }  // namespace
 
 int fft_plan_axes(nfftcu_ctx *c) {
@@ -951,6 +1058,15 @@ void fft_free_axes(nfftcu_ctx *c) {
 // sparse D; adjoint: only the band of the result is read by D^T)
 int stage_F(nfftcu_ctx *c, int sign, bool pruned) {
   if (c->fft_no_prune) pruned = false;
+  if (pruned && c->slab_on && c->d >= 2) {
+    // forward: first axis first; backward: last axis first
+    for (int i = 0; i < c->d; i++) {
+      const int t = sign < 0 ? i : c->d - 1 - i;
+      if (c->prec == NFFTCU_DOUBLE) NFFTCU_TRY(run_axis_slab<double>(c, t, sign));
+      else NFFTCU_TRY(run_axis_slab<float>(c, t, sign));
+    }
+    return NFFTCU_OK;
+  }
   // forward (and every unpruned transform): last axis first; pruned backward: first axis first
   const bool last_first = !(pruned && sign > 0);
   for (int i = 0; i < c->d; i++) {

@@ -132,7 +132,7 @@ int run_generic(nfftcu_ctx *c, const void *f_dev) {
 
 }  // namespace
 
-int stage_BT(nfftcu_ctx *c, const void *f_dev) {
+int stage_BT(nfftcu_ctx *c, const void *f_dev, bool slab_ok) {
   if (c->cur_batch > 1 && !(c->tile2_ready && c->opt_b_kernel != 1)) {
     // kernel families without a batch dimension: one right-hand side per launch, grid pointer moved along the batch
     const int K = c->cur_batch;
@@ -142,13 +142,22 @@ int stage_BT(nfftcu_ctx *c, const void *f_dev) {
     c->cur_batch = 1;
     for (int k = 0; k < K && r == NFFTCU_OK; k++) {
       c->grid = g0 + C * (size_t) c->n_total * k;
-      r = stage_BT(c, (const char *) f_dev + C * (size_t) c->M * k);
+      r = stage_BT(c, (const char *) f_dev + C * (size_t) c->M * k, slab_ok);
     }
     c->grid = g0;
     c->cur_batch = K;
     return r;
   }
-  NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, 2 * real_size(c) * (size_t) c->n_total * (size_t) c->cur_batch, c->stream));
+  if (slab_ok && c->slab_on && c->cur_batch == 1) {
+    // slab mode: the pruned backward F reads the window planes only (fft.cu), so only they are cleared
+    const size_t plane = 2 * real_size(c) * (size_t) (c->n_total / c->n[0]);
+    const long long w0 = c->slab_w0, wc = c->slab_wc, n0 = c->n[0];
+    const long long first = w0 + wc <= n0 ? wc : n0 - w0;
+    NFFTCU_CUDA(cudaMemsetAsync((char *) c->grid + plane * (size_t) w0, 0, plane * (size_t) first, c->stream));
+    if (first < wc) NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, plane * (size_t) (wc - first), c->stream));
+  } else {
+    NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, 2 * real_size(c) * (size_t) c->n_total * (size_t) c->cur_batch, c->stream));
+  }
   if (c->M == 0) return NFFTCU_OK;
   if (c->mma_ready) return mma3d_spread(c, f_dev);
   if (c->tile2_ready && c->opt_b_kernel != 1) return tile2d_spread(c, f_dev);
