@@ -213,6 +213,7 @@ int ensure_batch(nfftcu_ctx *c, int K) {
   NFFTCU_CUDA(pool_malloc(&g, gb));
   pool_free(c->grid);
   c->grid = g;
+  NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, gb, c->stream));   // see nfftcu_create
   if (c->grid2) {
     void *g2 = nullptr;
     NFFTCU_CUDA(pool_malloc(&g2, gb));
@@ -565,6 +566,9 @@ int nfftcu::create_ctx(nfftcu_ctx **out, int precision, int d, const int64_t *N,
   }
   if (!c->direct_only && !nodes_only) {
     NFFTCU_CUDA(pool_malloc(&c->grid, cbytes(c, c->n_total)));
+    // never leave pool garbage in the grid: the slab mode of the F step writes only the planes the nodes touch, and the
+    // tiled B kernels read their whole footprint (zero weights times a NaN bit pattern would still be NaN)
+    NFFTCU_CUDA(cudaMemsetAsync(c->grid, 0, cbytes(c, c->n_total), c->stream));
     NFFTCU_TRY(fft_plan_axes(c));
     if (tile3d_supported(c) || tile2d_supported(c)) NFFTCU_TRY(build_kb_poly(c));
   }

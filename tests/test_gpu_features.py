@@ -305,6 +305,8 @@ def test_split_phase_transforms_overlap_two_plans(precision):
 SLAB_CASES = {
     "3d_reg": dict(d=3, N=[64, 64, 64], n=[128, 128, 128], m=6, M=30000, lo=-0.30, hi=-0.12),
     "3d_wrap": dict(d=3, N=[64, 32, 32], n=[128, 64, 64], m=6, M=20000, lo=0.40, hi=0.4999),
+    # taps wrap around the first axis: u_0 = floor(n x) - m mod n lies in [118, 127], the window is [118, 141) mod 128
+    "3d_tapwrap": dict(d=3, N=[64, 32, 32], n=[128, 64, 64], m=6, M=20000, lo=-0.03, hi=0.045),
     "3d_low_edge": dict(d=3, N=[32, 32, 32], n=[64, 64, 64], m=4, M=10000, lo=-0.5, hi=-0.35),
     "3d_nonpow2": dict(d=3, N=[24, 20, 18], n=[48, 40, 36], m=4, M=6000, lo=0.05, hi=0.2),
     "3d_pencil_m8": dict(d=3, N=[32, 16, 16], n=[80, 40, 40], m=8, M=3000, lo=-0.1, hi=0.1),
@@ -318,7 +320,7 @@ SLAB_CASES = {
 def test_slab_mode_fft_vs_oracle(case, precision):
     """Nodes confined to a slab of the first axis (what a rank of a node-sharded run holds): the pruned F passes visit
     only the slab's planes (fft.cu run_axis_slab) -- trafo and adjoint against the oracle on the FULL grid, and
-    bit-identical to the same plan with the slab mode switched off; also as a batched transform."""
+    equal to rounding to the same plan with the slab mode switched off; also as a batched transform."""
     spec = SLAB_CASES[case]
     if precision == "float" and spec["m"] > 6:
         pytest.skip("the fp32 checker overflows for m = 8 in 3-D")
@@ -349,7 +351,8 @@ def test_slab_mode_fft_vs_oracle(case, precision):
         assert rel_l2(fb[1], 2 * want_f) <= TOL[precision] and rel_l2(fb[2], -want_f) <= TOL[precision]
         assert rel_l2(fhb[1], 3 * want_fh) <= TOL[precision]
         outs.append((got_f, got_fh))
-    # same arithmetic per line, fewer lines: the slab mode must not change a single bit
-    assert np.array_equal(outs[0][0], outs[1][0])
-    if precision == "double" or True:
-        assert rel_l2(outs[0][1], outs[1][1]) <= (1e-15 if precision == "double" else 1e-6)
+    # the slab mode visits fewer lines AND runs the axes in the opposite order (first axis first in the forward
+    # direction), so the two results agree to rounding, not bit for bit
+    tol = 1e-14 if precision == "double" else 2e-6
+    assert rel_l2(outs[0][0], outs[1][0]) <= tol
+    assert rel_l2(outs[0][1], outs[1][1]) <= tol
