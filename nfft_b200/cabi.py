@@ -19,6 +19,7 @@ DOUBLE, FLOAT = 0, 1
 PEER_HANDLE_BYTES = 192
 OPT_TIMING, OPT_PSI_TABLE, OPT_B_KERNEL, OPT_NODE_ORDER, OPT_B_FLUSH, OPT_FFT_PRUNE, OPT_FFT_KERNEL, OPT_WINDOW_IMAGES = 1, 2, 3, 4, 5, 6, 7, 8
 OPT_SLAB_FFT = 9
+OPT_TC5 = 10
 FLAG_GAUSSIAN = 1 << 30
 
 # every symbol include/nfftcu.h declares (tests/test_abi.py checks the .so exports all of them)

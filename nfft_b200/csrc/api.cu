@@ -283,7 +283,7 @@ static int slab_detect(nfftcu_ctx *c) {
 static unsigned node_opts_signature(const nfftcu_ctx *c) {
   return (unsigned) (c->opt_b_kernel & 15) | ((unsigned) (c->opt_node_order & 15) << 4) | ((unsigned) (c->opt_psi_table & 1) << 8) |
          ((unsigned) (c->opt_window_images & 3) << 9) | ((c->flags & (1u << 11)) ? 1u << 11 : 0u) |
-         ((unsigned) (c->opt_slab & 1) << 12);
+         ((unsigned) (c->opt_slab & 1) << 12) | ((unsigned) (c->opt_tc5 & 3) << 13);
 }
 
 int nodes_ready(nfftcu_ctx *c) {
@@ -427,7 +427,7 @@ bool same_plan(const nfftcu_ctx *c, int precision, int d, const int64_t *N, cons
 }
 size_t plan_device_bytes(const nfftcu_ctx *c) {   // rough: what parking this plan keeps allocated
   const size_t r = real_size(c);
-  return 2 * r * (size_t) c->n_total * (size_t) c->batch_cap * (c->grid2 ? 2 : 1) + c->mma_images_bytes +
+  return 2 * r * (size_t) c->n_total * (size_t) c->batch_cap * (c->grid2 ? 2 : 1) + c->mma_images_bytes + c->tc5_images_bytes +
          (size_t) c->M * (size_t) (r * c->d * 4 + 48);
 }
 }  // namespace
@@ -612,7 +612,8 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) pool_free(c->c_dev[t]);
-  void *bufs[] = {c->mma_images, c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
+  void *bufs[] = {c->tc5_images, c->tc5_batches, (void *) c->tc5_batch_start, (void *) c->tc5_counts, (void *) c->tc5_chunk_start, c->tc5_chunks,
+                  c->mma_images, c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)
     if (p) pool_free(p);
@@ -1086,6 +1087,7 @@ int nfftcu_set_option(nfftcu_ctx *c, int option, int64_t value) {
     case NFFTCU_OPT_FFT_KERNEL: c->opt_fft_kernel = (int) value; break;
     case NFFTCU_OPT_WINDOW_IMAGES: c->opt_window_images = (int) value; break;
     case NFFTCU_OPT_SLAB_FFT: c->opt_slab = (int) value; break;
+    case NFFTCU_OPT_TC5: c->opt_tc5 = (int) value; break;
     default:
       set_error("nfftcu_set_option: unknown option %d", option);
       return NFFTCU_EINVAL;

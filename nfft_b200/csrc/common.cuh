@@ -137,6 +137,15 @@ struct nfftcu_ctx_s {
   bool mma_images_ready = false;
   bool mma_images_tf32 = false;     // images hold packed fp32 / TF32 pairs (fp32 plans on the TF32 kernels)
   int opt_window_images = 0;        // 0 auto | 1 off | 2 on regardless of the memory budget
+  // fp32 plans on the tcgen05 / TMEM kernels (tc5.cu): own batch table (<= 16 nodes, 8-aligned window base), chunks, images
+  bool tc5_ready = false;
+  void *tc5_batches = nullptr;      // uint2 per batch: first node, base | nb << 24
+  uint32_t *tc5_batch_start = nullptr, *tc5_counts = nullptr, *tc5_chunk_start = nullptr;
+  void *tc5_chunks = nullptr;       // uint4 per chunk: tile, first batch, end batch
+  void *tc5_images = nullptr;       // 5 KB per batch: psi2 as the (hi, lo) B operand, psi0 / psi1 placed in the footprint
+  size_t tc5_images_bytes = 0;
+  long long tc5_units = 0, tc5_batch_cap = 0, tc5_chunk_cap = 0, tc5_nchunks = 0, tc5_nbatches = 0;
+  int opt_tc5 = 0;                  // NFFTCU_OPT_TC5: 0 auto (fp32, d = 3, m <= 6) | 1 off | 2 on
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

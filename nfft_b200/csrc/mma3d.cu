@@ -54,6 +54,7 @@
 // Spreading has an optional flush through shared memory and TMA bulk reductions (cp.reduce.async.bulk .add.f64,
 // FLUSH = 1, NFFTCU_OPT_B_FLUSH = 2); plain RED.ADD from the accumulator registers measured faster and is the default.
 #include "common.cuh"
+#include "mma3d.cuh"
 
 namespace nfftcu {
 
@@ -67,17 +68,6 @@ namespace {
 constexpr int kNB = 8;        // nodes per batch
 constexpr int kF = 16;        // footprint rows per axis, window slots
 constexpr unsigned kFull = 0xffffffffu;
-
-struct MmaParams {
-  int n0, n1, n2;
-  int T;            // tile edge: 17 - W
-  int NT0, NT1;
-  int zseg;         // work units per tile along z
-  const double *img;   // window images (kImgDoubles per batch) or null
-  long long M;
-  int m;
-  int deg;          // Horner length (fitted polynomial degree)
-};
 
 __device__ __forceinline__ int wrapi(int v, int n) {
   if (v < 0) v += n;
@@ -1162,7 +1152,11 @@ mma_images_kernel(const TS *__restrict__ xt, const uint4 *__restrict__ chunks, c
                                           img + (size_t) b0 * kImgDoubles);
 }
 
-MmaParams make_params(const nfftcu_ctx *c) {
+MmaParams make_params(const nfftcu_ctx *c) { return mma3d_params(c); }
+
+}  // namespace
+
+MmaParams mma3d_params(const nfftcu_ctx *c) {
   MmaParams P;
   P.n0 = (int) c->n[0];
   P.n1 = (int) c->n[1];
@@ -1184,6 +1178,8 @@ MmaParams make_params(const nfftcu_ctx *c) {
   P.M = c->M;
   return P;
 }
+
+namespace {
 
 template <int W, int FLUSH>
 size_t spread_smem() {
@@ -1430,6 +1426,9 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
       }
     }
   }
+  // fp32 plans: the tcgen05 kernels take over when their tables and images could be built (tc5.cu)
+  c->tc5_ready = false;
+  if (tc5_selected(c)) NFFTCU_TRY(tc5_build(c, P));
   c->mma_ready = true;
   return NFFTCU_OK;
 }
@@ -1445,6 +1444,7 @@ extern "C" int nfftcu_debug_clocks(unsigned long long *out) {
 #endif
 
 int mma3d_interp(nfftcu_ctx *c, void *f_dev) {
+  if (c->tc5_ready) return tc5_interp(c, f_dev);
   return c->prec == NFFTCU_DOUBLE ? dispatch<double>(c, nullptr, f_dev, false) : dispatch<float>(c, nullptr, f_dev, false);
 }
 
