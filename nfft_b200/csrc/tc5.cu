@@ -35,25 +35,36 @@
 // Hand-offs are mbarriers only: op_full / op_empty (image ring), a_ready (window covers the batch), acc_full (commit:
 // T is complete) / acc_empty (T was read).  The refill warps run up to three batches ahead; a slot is only overwritten
 // once every batch that still reads its old cell has committed (bases at least 16 cells behind).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mma3d.cuh"
 
 namespace nfftcu {
 
+// timing probes (NFFT_B200_TC5_DBG & 8): cycle totals per role, summed over the CTAs; read with nfftcu_tc5_debug
+__device__ unsigned long long g_t5dbg[32];
+
 namespace {
 
 constexpr int kN = 16;           // nodes per batch = N of the MMA
-constexpr int kRing = 32;        // z-slots of the window ring
+constexpr int kRing = 40;        // z-slots of the window ring: the 24 a batch reads + 16 the refill may already replace
 constexpr int kSpan = 24;        // slots one batch contracts: 3 k-steps of 8
-constexpr int kOpStages = 6;     // operand-image ring
-constexpr int kAcc = 4;          // accumulator stages (4 row blocks x 16 columns each)
-constexpr int kImgBytes = 5120;  // psi2 hi 1536 | psi2 lo 1536 | psi0 1024 | psi1 1024
-constexpr int kOffLo = 1536, kOffP0 = 3072, kOffP1 = 4096;
+constexpr int kOpStages = 16;    // operand-image ring: 80 KB in flight per SM (the images stream from HBM, ~2 us away)
+constexpr int kAcc = 3;          // accumulator stages (4 row blocks x 16 columns each)
+constexpr int kEpi = 2;          // epilogue warpgroups; group g takes the batches with index = g (mod kEpi)
+constexpr int kMmaWarps = 1;     // MMA-issuing warps (warp m would take the batches with index = m mod kMmaWarps; two warps
+                                 // measured no faster: the tensor pipe, the epilogue and the refill share tensor memory)
+constexpr int kThreadsI = 32 * (4 * kEpi + 4 + kMmaWarps + 1);
+constexpr int kImgBytes = 5248;  // psi2 hi 1536 | psi2 lo 1536 | psi0 1024 | psi1 1024 | output index of the 16 nodes 64 | batch entry 8 | pad
+constexpr int kOffLo = 1536, kOffP0 = 3072, kOffP1 = 4096, kOffPerm = 5120, kOffEntry = 5184;
+constexpr int kDone = 8;         // commit barriers in flight (acc_full ring)
+constexpr int kSlides = 8;       // window hand-offs in flight (the hazards keep the refill warps within 2 slides of the MMAs)
 constexpr int kBChunk = 256, kBGroup = 128;   // B operand: (slot/4)*256 + (node/8)*128 + (node%8)*16 + (slot%4)*4
-constexpr int kColA = 256;       // TMEM: D stage s at 64 s + 16 b, A ring of row block b at 256 + 64 b (+32: lo) + slot
+constexpr int kColA = 64 * kAcc;  // TMEM: D stage s at 64 s + 16 b, A ring of row block b at kColA + 2 kRing b (+ kRing: lo) + slot
+static_assert(kColA + 8 * kRing <= 512, "tensor memory has 512 columns");
 constexpr int kChunkBatches = 256;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kOneCtaSmem = 120 * 1024;   // dynamic shared memory requested only to make the kernel one CTA per SM
 
 __device__ __forceinline__ int b_off(int n, int s) { return (s >> 2) * kBChunk + (n >> 3) * kBGroup + (n & 7) * 16 + (s & 3) * 4; }
 // psi0 / psi1 rows of 16 floats; the four 16-byte chunks of row l are rotated by l >> 1 so that the eight rows a quarter
@@ -77,16 +88,32 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Every hand-off of this kernel sits on a batch's critical path, so the waits poll (try_wait without a suspend-time
+// hint returns within tens of cycles; the hinted form parks the warp and wakes it late).  NFFT_B200_TC5_WAIT=1 selects
+// the hinted form for comparison.
+template <bool HINT = false>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+  if (HINT) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -221,8 +248,8 @@ struct WinParams {
 
 // one warp per batch; the image buffer was cleared before, only the taps are written
 __global__ void __launch_bounds__(128)
-t5_images_kernel(const float *__restrict__ xt, const uint4 *__restrict__ chunks, const uint2 *__restrict__ table,
-                 unsigned char *__restrict__ img, MmaParams P, WinParams Wp) {
+t5_images_kernel(const float *__restrict__ xt, const uint32_t *__restrict__ perm, const uint4 *__restrict__ chunks,
+                 const uint2 *__restrict__ table, unsigned char *__restrict__ img, MmaParams P, WinParams Wp) {
   const uint4 chunk = chunks[blockIdx.x];
   const int tile = (int) chunk.x;
   const int a = tile / P.NT1, bt = tile - a * P.NT1;
@@ -232,6 +259,8 @@ t5_images_kernel(const float *__restrict__ xt, const uint4 *__restrict__ chunks,
     const uint2 e = table[b];
     const int base = t5_base(e), nb = t5_nb(e);
     unsigned char *im = img + (size_t) b * kImgBytes;
+    if (lane < 16) reinterpret_cast<uint32_t *>(im + kOffPerm)[lane] = lane < nb ? perm[e.x + lane] : 0u;
+    if (lane == 16) *reinterpret_cast<uint2 *>(im + kOffEntry) = e;
     for (int i = lane; i < nb * 3 * W; i += 32) {
       const int n = i / (3 * W), r = i - n * 3 * W, t = r / W, l = r - t * W;
       const float x = xt[3 * (size_t) (e.x + n) + t];
@@ -256,26 +285,31 @@ t5_images_kernel(const float *__restrict__ xt, const uint4 *__restrict__ chunks,
 // ---- interpolation --------------------------------------------------------------------------------------------
 struct __align__(128) SmemI {
   unsigned char ops[kOpStages][kImgBytes];
-  float red[kAcc][4][32];
+  float red[kEpi][2][4][32];
+  int done_upto[kMmaWarps];        // stream m: every batch = m (mod 2) up to done_upto[m] has committed (written by the epilogue
+                                   // warps, polled by the refill warps)
   uint64_t op_full[kOpStages], op_empty[kOpStages];
-  uint64_t acc_full[kAcc], acc_empty[kAcc];
-  uint64_t a_ready[4];
+  uint64_t acc_full[kDone];        // commit of batch j arrives on acc_full[j % kDone] (the accumulator stage is j % kAcc)
+  uint64_t acc_empty[kAcc];
+  uint64_t a_ready[kSlides];       // one phase per slide of 8 cells
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(320, 1)
-tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ perm, float *__restrict__ f,
-                  const uint4 *__restrict__ chunks, int nchunks, const uint2 *__restrict__ table,
-                  const unsigned char *__restrict__ img, MmaParams P) {
-  __shared__ SmemI S;
+__global__ void __launch_bounds__(kThreadsI, 1)
+tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uint4 *__restrict__ chunks, int nchunks,
+                  const uint2 *__restrict__ table, const unsigned char *__restrict__ img, MmaParams P, int dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemI &S = *reinterpret_cast<SmemI *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < kOpStages; i++) { mbar_init(&S.op_full[i], 1); mbar_init(&S.op_empty[i], 4); }
-    for (int i = 0; i < kAcc; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 4); }
-    for (int i = 0; i < 4; i++) mbar_init(&S.a_ready[i], 4);
+    for (int i = 0; i < kDone; i++) mbar_init(&S.acc_full[i], 1);
+    for (int i = 0; i < kSlides; i++) mbar_init(&S.a_ready[i], 4);
+    for (int i = 0; i < kMmaWarps; i++) S.done_upto[i] = -1;
+    for (int i = 0; i < kAcc; i++) mbar_init(&S.acc_empty[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 4 * kEpi + 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -284,11 +318,17 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
   tc_fence_after();
   const uint32_t tb = S.tmem_base;
   const int n2 = P.n2;
+  unsigned long long tdbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CLK() ((dbg & 8) ? clock64() : 0ll)
+  const long long t_begin = CLK();
+  // every role walks the same sequence of batches: chunks blockIdx.x, + gridDim.x, ...; jg counts them.  The batch entry
+  // (first node, base, count) and the output indices of its nodes travel inside the operand image, so no role has a
+  // dependent global load in its loop.
 
-  if (warp < 4) {
-    // ===== epilogue: lane quarter q = warp, row r = 32 q + lane of every row block; block b = 2 c + h holds component
-    // c (re / im) of pencil p = 128 h + r, i.e. l0 = 8 h + 2 q + (lane >> 4), l1 = lane & 15
-    const int q = warp;
+  if (warp < 4 * kEpi) {
+    // ===== epilogue: lane quarter q, row r = 32 q + lane of every row block; block b = 2 c + h holds component c (re / im)
+    // of pencil p = 128 h + r, i.e. l0 = 8 h + 2 q + (lane >> 4), l1 = lane & 15
+    const int q = warp & 3, grp = warp >> 2;
     const uint32_t lane_base = (uint32_t) (q * 32) << 16;
     const int l1 = lane & 15, l0a = 2 * q + (lane >> 4);
     long long jg = 0;
@@ -296,35 +336,42 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
       const uint4 chunk = chunks[ch];
       const int nbat = (int) (chunk.z - chunk.y);
       for (int j = 0; j < nbat; j++, jg++) {
-        const int st = (int) (jg % kOpStages), s = (int) (jg & 3);
-        const uint2 e = table[chunk.y + j];
-        mbar_wait(&S.acc_full[s], (int) ((jg >> 2) & 1));
+        const int st = (int) (jg % kOpStages), s = (int) (jg % kAcc);
+        if ((int) (jg % kEpi) != grp) continue;   // the other group's batch
+        const long long c0 = CLK();
+        mbar_wait(&S.acc_full[jg % kDone], (int) ((jg / kDone) & 1));
+        const long long c1 = CLK();
+        if (q == 0 && lane == 0) atomicMax(&S.done_upto[jg % kMmaWarps], (int) jg);   // a warp's commits complete in order
         tc_fence_after();
         float v[4][16];
 #pragma unroll
         for (int b = 0; b < 4; b++) tmem_ld16(tb + lane_base + 64 * s + 16 * b, v[b]);
         mbar_wait(&S.op_full[st], (int) ((jg / kOpStages) & 1));   // long complete: makes the TMA writes visible here
         const unsigned char *op = S.ops[st];
-        float acc[32];   // [c][n]
+        const int nb = t5_nb(*reinterpret_cast<const uint2 *>(op + kOffEntry));
+        const uint32_t pj = reinterpret_cast<const uint32_t *>(op + kOffPerm)[lane & 15];
+        float w[2][16];   // row weights (psi0[l0a] psi1[l1], psi0[l0a + 8] psi1[l1]) of the 16 nodes
 #pragma unroll
         for (int cq = 0; cq < 4; cq++) {
           const float4 p1 = *reinterpret_cast<const float4 *>(op + kOffP1 + l1 * 64 + (((cq + (l1 >> 1)) & 3) << 4));
           const float4 pa = *reinterpret_cast<const float4 *>(op + kOffP0 + l0a * 64 + (((cq + (l0a >> 1)) & 3) << 4));
           const float4 pb = *reinterpret_cast<const float4 *>(op + kOffP0 + (l0a + 8) * 64 + (((cq + ((l0a + 8) >> 1)) & 3) << 4));
-          const float w1[4] = {p1.x, p1.y, p1.z, p1.w}, wa[4] = {pa.x, pa.y, pa.z, pa.w}, wb[4] = {pb.x, pb.y, pb.z, pb.w};
-          if (cq == 0) tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int n = 4 * cq + i;
-            const float ka = wa[i] * w1[i], kb = wb[i] * w1[i];
-            acc[n] = fmaf(kb, v[1][n], ka * v[0][n]);
-            acc[16 + n] = fmaf(kb, v[3][n], ka * v[2][n]);
-          }
+          w[0][4 * cq] = pa.x * p1.x; w[0][4 * cq + 1] = pa.y * p1.y; w[0][4 * cq + 2] = pa.z * p1.z; w[0][4 * cq + 3] = pa.w * p1.w;
+          w[1][4 * cq] = pb.x * p1.x; w[1][4 * cq + 1] = pb.y * p1.y; w[1][4 * cq + 2] = pb.z * p1.z; w[1][4 * cq + 3] = pb.w * p1.w;
         }
-        // T was read, the operand stage was read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.op_empty[st]);   // the image stage was read
+        tmem_ld_wait();
+        const long long c2 = CLK();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&S.acc_empty[s]); mbar_arrive(&S.op_empty[st]); }
+        if (lane == 0) mbar_arrive(&S.acc_empty[s]);   // T was read
+        float acc[32];   // [c][n]
+#pragma unroll
+        for (int n = 0; n < 16; n++) {
+          acc[n] = fmaf(w[1][n], v[1][n], w[0][n] * v[0][n]);
+          acc[16 + n] = fmaf(w[1][n], v[3][n], w[0][n] * v[2][n]);
+        }
         // butterfly: after the five steps lane L holds the warp's sum of value index L = 16 c + n
 #pragma unroll
         for (int half = 16; half >= 1; half >>= 1) {
@@ -336,21 +383,30 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
             acc[i] = keep + __shfl_xor_sync(kFull, send, half);
           }
         }
-        S.red[s][q][lane] = acc[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q == (int) (jg & 3)) {
-          const float sum = (S.red[s][0][lane] + S.red[s][1][lane]) + (S.red[s][2][lane] + S.red[s][3][lane]);
+        const long long c3 = CLK();
+        if ((dbg & 8) && warp == 0 && lane == 0) { tdbg[0] += c1 - c0; tdbg[1] += c2 - c1; tdbg[2] += c3 - c2; tdbg[3]++; }
+        if (dbg & 1) continue;   // timing experiments only (NFFT_B200_TC5_DBG)
+        float (*red)[32] = S.red[grp][(jg / kEpi) & 1];
+        red[q][lane] = acc[0];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        if (q == (int) ((jg / kEpi) & 3)) {
+          const float sum = (red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane]);
           const int n = lane & 15, c = lane >> 4;
-          if (n < t5_nb(e)) f[2 * (size_t) perm[e.x + n] + c] = sum;
+          if (n < nb) f[2 * (size_t) pj + c] = sum;
         }
+        if ((dbg & 8) && warp == 0 && lane == 0) tdbg[4] += clock64() - c3;
       }
     }
-  } else if (warp < 8) {
-    // ===== window refill: thread (q, lane) owns row r = 32 q + lane of the four row blocks = pencils r and 128 + r
-    const int q = warp - 4;
+    if ((dbg & 8) && warp == 0 && lane == 0) { for (int i = 0; i < 5; i++) atomicAdd(&g_t5dbg[i], tdbg[i]); atomicAdd(&g_t5dbg[5], (unsigned long long) (clock64() - t_begin)); }
+  } else if (warp < 4 * kEpi + 4) {
+    // ===== window refill: thread (q, lane) owns row r = 32 q + lane of the four row blocks = pencils r and 128 + r.
+    // The warps act per SLIDE (8 new cells), not per batch: they walk the batch table (32 entries per coalesced load) to
+    // find the slides the batches need, and hand each slide to the MMA warp through a_ready[slide % kSlides].
+    const int q = warp & 3;
     const uint32_t lane_base = (uint32_t) (q * 32) << 16;
     const int r = 32 * q + lane;
-    long long jg = 0;
+    long long jg0 = 0;     // index of the chunk's first batch in the CTA's batch sequence
+    long long sg = 0;      // slides handed over so far
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
       const uint4 chunk = chunks[ch];
       const int nbat = (int) (chunk.z - chunk.y);
@@ -362,88 +418,132 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
         const int p = 128 * h + r;
         rowoff[h] = (unsigned) ((wrapi(P.T * a + (p >> 4), P.n0) * (long long) P.n1 + wrapi(P.T * bt + (p & 15), P.n1)) * n2);
       }
-      int whi = 0, base1 = 0, base2 = 0;   // cells [.., whi) are loaded; bases of the two previous batches
-      for (int j = 0; j < nbat; j++, jg++) {
-        const int base = t5_base(table[chunk.y + j]);
-        if (j == 0) {
-          if (jg > 0) mbar_wait(&S.acc_full[(jg - 1) & 3], (int) (((jg - 1) >> 2) & 1));   // every earlier batch has committed
-          whi = base;
-        } else {
-          if (jg >= 3) mbar_wait(&S.acc_full[(jg - 3) & 3], (int) (((jg - 3) >> 2) & 1));   // at most three batches ahead
-          // cells below base - 8 are overwritten: every batch that still reads them must have committed
-          if (base1 < base - 8) mbar_wait(&S.acc_full[(jg - 1) & 3], (int) (((jg - 1) >> 2) & 1));
-          else if (j >= 2 && base2 < base - 8) mbar_wait(&S.acc_full[(jg - 2) & 3], (int) (((jg - 2) >> 2) & 1));
-          if (whi < base) whi = base;
-        }
-        base2 = base1;
-        base1 = base;
-        bool stored = false;
+      // two cursors into the chunk's batch table, each with 32 bases cached in the lanes
+      int nj0 = 0, nbase = lane < nbat ? t5_base(table[chunk.y + lane]) : 0x3fffffff;   // needs: batches [nj0, nj0 + 32)
+      int hj0 = 0, hbase = nbase;                                                         // hazards
+      int hz = 0;            // batches [0, hz) of the chunk are known to have committed
+      int whi = 0;           // cells [.., whi) of the chunk's sweep are in the ring
+      // the next 8 cells [pz, pz + 8) of the thread's two pencils, loaded from L2 ahead of their use (the loads do not
+      // touch tensor memory, so they need not wait for a hazard)
+      float4 pre[2][4];
+      int pz = -1;
+      auto prefetch = [&](int z0) {
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            int z = z0 + 2 * i;
+            if (z >= n2) z %= n2;
+            pre[h][i] = *reinterpret_cast<const float4 *>(G + rowoff[h] + z);   // cells z, z + 1 (z even, n2 even)
+          }
+        pz = z0;
+      };
+      for (int j = 0; j < nbat; j++) {
+        if (j >= nj0 + 32) { nj0 += 32; nbase = nj0 + lane < nbat ? t5_base(table[chunk.y + nj0 + lane]) : 0x3fffffff; }
+        const int base = __shfl_sync(kFull, nbase, j - nj0);
+        if (j == 0) { whi = base; prefetch(base); }
+        if (whi < base) whi = base;
         for (; whi < base + kSpan; whi += 8) {
-          const int slot = whi & (kRing - 1);
+          // cells below whi + 8 - kRing are replaced: every batch whose base lies below that may still read them and
+          // must have committed; so must every batch of the earlier chunks (another tile)
+          const int dead = whi + 8 - kRing;
+          for (;;) {
+            if (hz >= hj0 + 32) { hj0 += 32; hbase = hj0 + lane < nbat ? t5_base(table[chunk.y + hj0 + lane]) : 0x3fffffff; }
+            if (hz >= j || __shfl_sync(kFull, hbase, hz - hj0) >= dead) break;
+            hz++;
+          }
+          const long long need = jg0 + hz - 1;   // last batch that must have committed (-1: none)
+          const long long c0 = CLK();
+          if (need >= 0 && !((dbg & 16) && j > 0)) {
+            // batch `need` and everything before it: the newest batch of either MMA stream
+            const volatile int *du0 = &S.done_upto[need % kMmaWarps], *du1 = &S.done_upto[(need + 1) % kMmaWarps];
+            while ((long long) *du0 < need) { }
+            while ((long long) *du1 < need - 1) { }
+          }
+          tc_fence_after();
+          const long long c1 = CLK();
+          if (pz != whi) prefetch(whi);
+          const int slot = whi % kRing;
 #pragma unroll
           for (int h = 0; h < 2; h++) {
+            if (dbg & 2) break;
             float re[8], im[8];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-              int z = whi + 2 * i;
-              if (z >= n2) z %= n2;
-              const float4 g = *reinterpret_cast<const float4 *>(G + rowoff[h] + z);   // cells z, z + 1 (z even, n2 even)
+              const float4 g = pre[h][i];
               re[2 * i] = g.x; im[2 * i] = g.y; re[2 * i + 1] = g.z; im[2 * i + 1] = g.w;
             }
             float hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) { hi[i] = tf32_rna(re[i]); lo[i] = re[i] - hi[i]; }
-            tmem_st8(tb + lane_base + kColA + 64 * h + slot, hi);
-            tmem_st8(tb + lane_base + kColA + 64 * h + 32 + slot, lo);
+            tmem_st8(tb + lane_base + kColA + 2 * kRing * h + slot, hi);
+            tmem_st8(tb + lane_base + kColA + 2 * kRing * h + kRing + slot, lo);
 #pragma unroll
             for (int i = 0; i < 8; i++) { hi[i] = tf32_rna(im[i]); lo[i] = im[i] - hi[i]; }
-            tmem_st8(tb + lane_base + kColA + 64 * (2 + h) + slot, hi);
-            tmem_st8(tb + lane_base + kColA + 64 * (2 + h) + 32 + slot, lo);
+            tmem_st8(tb + lane_base + kColA + 2 * kRing * (2 + h) + slot, hi);
+            tmem_st8(tb + lane_base + kColA + 2 * kRing * (2 + h) + kRing + slot, lo);
           }
-          stored = true;
+          const long long c2 = CLK();
+          prefetch(whi + 8);   // needed by this batch (initial fill) or by one of the next
+          tmem_st_wait();
+          const long long c3 = CLK();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.a_ready[sg % kSlides]);
+          sg++;
+          if ((dbg & 8) && q == 0 && lane == 0) { tdbg[0] += c1 - c0; tdbg[1] += c2 - c1; tdbg[2] += c3 - c2; tdbg[3]++; }
         }
-        if (stored) tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.a_ready[jg & 3]);
       }
+      jg0 += nbat;
     }
-  } else if (warp == 8) {
-    // ===== MMA issue: the whole warp runs the loop (uniform operands), one elected lane issues
+    if ((dbg & 8) && q == 0 && lane == 0) { for (int i = 0; i < 4; i++) atomicAdd(&g_t5dbg[8 + i], tdbg[i]); }
+  } else if (warp < 4 * kEpi + 4 + kMmaWarps) {
+    // ===== MMA issue: the whole warp runs the loop (uniform operands), one elected lane issues; warp mw takes every second batch
     constexpr uint32_t idesc = make_idesc(128, kN);
-    long long jg = 0;
+    const int mw = warp - (4 * kEpi + 4);
+    long long jg = 0, sg = 0, sw = 0;   // batches walked, slides needed so far, slides this warp has waited for
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
       const uint4 chunk = chunks[ch];
       const int nbat = (int) (chunk.z - chunk.y);
-      uint2 e_next = nbat > 0 ? table[chunk.y] : make_uint2(0, 0);
+      int whi = 0;
       for (int j = 0; j < nbat; j++, jg++) {
-        const int st = (int) (jg % kOpStages), s = (int) (jg & 3);
-        const int base = t5_base(e_next);
-        if (j + 1 < nbat) e_next = table[chunk.y + j + 1];
+        const int st = (int) (jg % kOpStages), s = (int) (jg % kAcc);
+        const long long c0 = CLK();
         mbar_wait(&S.op_full[st], (int) ((jg / kOpStages) & 1));
-        mbar_wait(&S.acc_empty[s], (int) (((jg >> 2) & 1) ^ 1));
-        mbar_wait(&S.a_ready[jg & 3], (int) ((jg >> 2) & 1));
+        const long long c1 = CLK();
+        const int base = t5_base(*reinterpret_cast<const uint2 *>(S.ops[st] + kOffEntry));
+        // the slides the batches need, in the order the refill warps produce them (same rule as theirs)
+        if (j == 0 || whi < base) whi = base;
+        for (; whi < base + kSpan; whi += 8) sg++;
+        if ((int) (jg % kMmaWarps) != mw) continue;   // the other warp's batch
+        mbar_wait(&S.acc_empty[s], (int) (((jg / kAcc) & 1) ^ 1));
+        const long long c2 = CLK();
+        for (; sw < sg; sw++) mbar_wait(&S.a_ready[sw % kSlides], (int) ((sw / kSlides) & 1));
+        const long long c3 = CLK();
         tc_fence_after();
         if (elect_one()) {
           const uint32_t bsm = smem_u32(S.ops[st]);
 #pragma unroll
           for (int i = 0; i < 3; i++) {
-            const uint32_t kb = (uint32_t) (base + 8 * i) & (kRing - 1);
+            if ((dbg & 4) && i > 0) break;
+            const uint32_t kb = (uint32_t) ((base + 8 * i) % kRing);
             const uint64_t bh = make_desc(bsm + 2 * i * kBChunk, kBChunk, kBGroup);
             const uint64_t bl = make_desc(bsm + kOffLo + 2 * i * kBChunk, kBChunk, kBGroup);
 #pragma unroll
             for (int term = 0; term < 3; term++)
 #pragma unroll
               for (int b = 0; b < 4; b++) {
-                const uint32_t a_hi = tb + kColA + 64 * b + kb;
-                mma_ts(tb + 64 * s + 16 * b, term == 0 ? a_hi + 32 : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
+                const uint32_t a_hi = tb + kColA + 2 * kRing * b + kb;
+                mma_ts(tb + 64 * s + 16 * b, term == 0 ? a_hi + kRing : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
               }
           }
-          mma_commit(&S.acc_full[s]);
+          mma_commit(&S.acc_full[jg % kDone]);
         }
         __syncwarp();
+        if ((dbg & 8) && lane == 0) { tdbg[0] += c1 - c0; tdbg[1] += c2 - c1; tdbg[2] += c3 - c2; tdbg[3] += clock64() - c3; tdbg[4]++; }
       }
     }
+    if ((dbg & 8) && lane == 0 && mw == 0) { for (int i = 0; i < 5; i++) atomicAdd(&g_t5dbg[16 + i], tdbg[i]); }
   } else {
     // ===== feeder: one lane streams the operand images into the ring
     long long jg = 0;
@@ -452,7 +552,9 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
       const int nbat = (int) (chunk.z - chunk.y);
       for (int j = 0; j < nbat; j++, jg++) {
         const int st = (int) (jg % kOpStages);
+        const long long c0 = CLK();
         mbar_wait(&S.op_empty[st], (int) (((jg / kOpStages) & 1) ^ 1));
+        if ((dbg & 8) && lane == 0) tdbg[0] += clock64() - c0;
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.op_full[st])), "r"(kImgBytes) : "memory");
@@ -463,10 +565,11 @@ tc5_interp_kernel(const float2 *__restrict__ G, const uint32_t *__restrict__ per
         __syncwarp();
       }
     }
+    if ((dbg & 8) && lane == 0) atomicAdd(&g_t5dbg[24], tdbg[0]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+  if (warp == 4 * kEpi + 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }
 
 }  // namespace
@@ -545,7 +648,7 @@ int tc5_build(nfftcu_ctx *c, const MmaParams &P) {
   for (int t = 0; t < 3; t++) { Wp.b[t] = c->b[t]; Wp.ws[t] = c->wscale[t]; }
   Wp.m2 = (double) c->m * (double) c->m;
   Wp.window = c->window;
-  t5_images_kernel<<<(unsigned) nchunks, 128, 0, c->stream>>>((const float *) c->tile_x, (const uint4 *) c->tc5_chunks,
+  t5_images_kernel<<<(unsigned) nchunks, 128, 0, c->stream>>>((const float *) c->tile_x, c->tile_perm, (const uint4 *) c->tc5_chunks,
                                                               (const uint2 *) c->tc5_batches, (unsigned char *) c->tc5_images, P, Wp);
   c->launches += 2;
   NFFTCU_CUDA(cudaGetLastError());
@@ -558,13 +661,15 @@ int tc5_interp(nfftcu_ctx *c, void *f_dev) {
   const MmaParams P = mma3d_params(c);
   unsigned grid = (unsigned) c->sm_count;
   if ((long long) grid > c->tc5_nchunks) grid = (unsigned) c->tc5_nchunks;
-  // the CTA owns all 512 TMEM columns of its SM: the (unused) dynamic shared memory keeps a second CTA off the SM, which
-  // would otherwise sit in tcgen05.alloc until the first one exits
+  // the CTA owns all 512 TMEM columns of its SM: at least 120 KB of dynamic shared memory keep a second CTA off the SM,
+  // which would otherwise sit in tcgen05.alloc until the first one exits
+  const int kOneCtaSmem = sizeof(SmemI) > 120 * 1024 ? (int) sizeof(SmemI) : 120 * 1024;
   NFFTCU_CUDA(cudaFuncSetAttribute(tc5_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOneCtaSmem));
+  static const int dbg = getenv("NFFT_B200_TC5_DBG") ? atoi(getenv("NFFT_B200_TC5_DBG")) : 0;
   if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
-  tc5_interp_kernel<<<grid, 320, kOneCtaSmem, c->stream>>>((const float2 *) c->grid, c->tile_perm, (float *) f_dev,
-                                                 (const uint4 *) c->tc5_chunks, (int) c->tc5_nchunks,
-                                                 (const uint2 *) c->tc5_batches, (const unsigned char *) c->tc5_images, P);
+  tc5_interp_kernel<<<grid, kThreadsI, kOneCtaSmem, c->stream>>>((const float2 *) c->grid, (float *) f_dev,
+                                                               (const uint4 *) c->tc5_chunks, (int) c->tc5_nchunks,
+                                                               (const uint2 *) c->tc5_batches, (const unsigned char *) c->tc5_images, P, dbg);
   if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
   c->launches++;
   NFFTCU_CUDA(cudaGetLastError());
@@ -572,3 +677,12 @@ int tc5_interp(nfftcu_ctx *c, void *f_dev) {
 }
 
 }  // namespace nfftcu
+
+// debugging aid (tools/tc5_check.py): the probe totals of the last launches, cleared on read
+extern "C" int nfftcu_tc5_debug(unsigned long long *out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, nfftcu::g_t5dbg, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(nfftcu::g_t5dbg, z, sizeof(z));
+  return 0;
+}

@@ -356,3 +356,49 @@ def test_slab_mode_fft_vs_oracle(case, precision):
     tol = 1e-14 if precision == "double" else 2e-6
     assert rel_l2(outs[0][0], outs[1][0]) <= tol
     assert rel_l2(outs[0][1], outs[1][1]) <= tol
+
+
+# ---- fp32 plans on the tcgen05 / TMEM kernels (tc5.cu) ---------------------------------------------------------------
+TC5_CASES = {
+    "n32_m6": dict(N=[16, 16, 16], n=[32, 32, 32], m=6, M=2000),
+    "n64_m6": dict(N=[32, 32, 32], n=[64, 64, 64], m=6, M=40000),
+    "nonpow2_m4": dict(N=[24, 20, 18], n=[48, 40, 36], m=4, M=6000),
+    "n2_70_m2": dict(N=[16, 16, 32], n=[32, 32, 70], m=2, M=5000),
+    "m5_sparse": dict(N=[32, 32, 64], n=[64, 64, 128], m=5, M=700),       # long gaps between window bases
+    "n128_m6": dict(N=[64, 64, 64], n=[128, 128, 128], m=6, M=300000),
+    "clustered_m6": dict(N=[32, 32, 32], n=[64, 64, 64], m=6, M=60000, cluster=True),   # hundreds of batches on one base
+}
+
+
+@pytest.mark.parametrize("case", sorted(TC5_CASES))
+def test_tc5_fp32_kernels_vs_oracle_and_mma_sync(case):
+    """fp32 3-D plans, m <= 6: interpolation on tcgen05.mma kind::tf32 with the grid window and the accumulators in tensor
+    memory (tc5.cu) -- against the oracle, against the mma.sync TF32 kernels (NFFTCU_OPT_TC5 = 1) on the same plan
+    geometry, twice in a row (the persistent CTAs keep no state between launches), and as a batched transform."""
+    spec = TC5_CASES[case]
+    rng = np.random.default_rng(23)
+    M, NN = spec["M"], int(np.prod(spec["N"]))
+    x = rng.random((M, 3)) - 0.5
+    if spec.get("cluster"):
+        x[: M // 2] = 0.02 * rng.standard_normal((M // 2, 3))        # half of the nodes in a few tiles
+        x = np.clip(x, -0.5, 0.4999)
+    x = np.minimum(x.astype(np.float32), np.nextafter(np.float32(0.5), np.float32(0)))
+    fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(np.complex64)
+    f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(np.complex64)
+    o = common.oracle("float")
+    want_f = o.trafo(spec["N"], spec["n"], spec["m"], x, fh)
+    want_fh = o.adjoint(spec["N"], spec["n"], spec["m"], x, f, True)
+    got = {}
+    for tc5 in (1, 2):
+        eng = cabi.Engine(spec["N"], spec["n"], spec["m"], M, precision="float")
+        eng.set_option(cabi.OPT_TC5, tc5)
+        eng.set_nodes(x)
+        a = eng.trafo(fh)
+        b = eng.trafo(fh)
+        fb = eng.trafo_batch(np.stack([fh, -2 * fh]))
+        got[tc5] = (a, eng.adjoint(f))
+        eng.close()
+        assert np.array_equal(a, b)
+        assert rel_l2(a, want_f) <= TOL["float"] and rel_l2(got[tc5][1], want_fh) <= TOL["float"]
+        assert rel_l2(fb[1], -2 * want_f) <= TOL["float"]
+    assert rel_l2(got[2][0], got[1][0]) <= 2e-6 and rel_l2(got[2][1], got[1][1]) <= 2e-6

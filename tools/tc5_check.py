@@ -1,6 +1,6 @@
 """Quick GPU check of the tcgen05 fp32 kernels (tc5.cu) against the mma.sync kernels and the oracle.
 Usage: timeout 300 python tools/tc5_check.py [--big]"""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from nfft_b200 import cabi
@@ -35,6 +35,18 @@ for spec in CASES:
         t0 = time.time()
         got_f = eng.trafo(fh)
         tb = eng.b_kernel_time()
+        if tc5 == 2 and os.environ.get("NFFT_B200_TC5_DBG") and int(os.environ["NFFT_B200_TC5_DBG"]) & 8:
+            import ctypes
+            buf = (ctypes.c_ulonglong * 32)()
+            cabi.lib().nfftcu_tc5_debug(buf)
+            d = list(buf)
+            nbm = max(d[20], 1)   # own batches of MMA warp 0
+            nb = nbm
+            print("  per batch (cycles): MMA warp 0 (per own batch): wait op_full %.0f, acc_empty %.0f, a_ready %.0f, issue %.0f | epilogue warp 0 (per own batch): "
+                  "wait acc_full %.0f, ld %.0f, math+butterfly %.0f, cross-warp %.0f, loop total/batch %.0f | refill PER SLIDE: hazard wait %.0f, cvt+st issue %.0f, "
+                  "prefetch+wait::st %.0f, slides %.2f/batch | feeder wait op_empty %.0f" % (
+                      d[16] / nbm, d[17] / nbm, d[18] / nbm, d[19] / nbm, d[0] / max(d[3], 1), d[1] / max(d[3], 1), d[2] / max(d[3], 1),
+                      d[4] / max(d[3], 1), d[5] / nb, d[8] / max(d[11], 1), d[9] / max(d[11], 1), d[10] / max(d[11], 1), d[11] / nb, d[24] / nb))
         got_fh = eng.adjoint(f)
         tbt = eng.b_kernel_time()
         res[tc5] = (got_f, got_fh, tb, tbt)
