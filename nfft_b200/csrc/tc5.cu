@@ -53,8 +53,12 @@ constexpr int kSpan = 24;        // slots one batch contracts: 3 k-steps of 8
 constexpr int kOpStages = 16;    // operand-image ring: 80 KB in flight per SM (the images stream from HBM, ~2 us away)
 constexpr int kAcc = 3;          // accumulator stages (4 row blocks x 16 columns each)
 constexpr int kEpi = 2;          // epilogue warpgroups; group g takes the batches with index = g (mod kEpi)
-constexpr int kMmaWarps = 1;     // MMA-issuing warps (warp m would take the batches with index = m mod kMmaWarps; two warps
-                                 // measured no faster: the tensor pipe, the epilogue and the refill share tensor memory)
+#ifndef TC5_MMA_WARPS
+#define TC5_MMA_WARPS 1
+#endif
+constexpr int kMmaWarps = TC5_MMA_WARPS;   // MMA-issuing warps; warp m takes the batches with index = m (mod kMmaWarps).  Two warps
+                                 // (one's hand-shakes under the other's MMAs) measured no faster and are NOT validated at size.
+static_assert(kMmaWarps == 1 || kMmaWarps == kEpi, "epilogue group g reports the completion of MMA warp g's batches");
 constexpr int kThreadsI = 32 * (4 * kEpi + 4 + kMmaWarps + 1);
 constexpr int kImgBytes = 5248;  // psi2 hi 1536 | psi2 lo 1536 | psi0 1024 | psi1 1024 | output index of the 16 nodes 64 | batch entry 8 | pad
 constexpr int kOffLo = 1536, kOffP0 = 3072, kOffP1 = 4096, kOffPerm = 5120, kOffEntry = 5184;
@@ -506,16 +510,19 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
       const uint4 chunk = chunks[ch];
       const int nbat = (int) (chunk.z - chunk.y);
       int whi = 0;
+      // window bases from the batch table, 32 per coalesced load (the image of another warp's batch may be gone already)
+      int nj0 = 0, nbase = lane < nbat ? t5_base(table[chunk.y + lane]) : 0x3fffffff;
       for (int j = 0; j < nbat; j++, jg++) {
         const int st = (int) (jg % kOpStages), s = (int) (jg % kAcc);
-        const long long c0 = CLK();
-        mbar_wait(&S.op_full[st], (int) ((jg / kOpStages) & 1));
-        const long long c1 = CLK();
-        const int base = t5_base(*reinterpret_cast<const uint2 *>(S.ops[st] + kOffEntry));
+        if (j >= nj0 + 32) { nj0 += 32; nbase = nj0 + lane < nbat ? t5_base(table[chunk.y + nj0 + lane]) : 0x3fffffff; }
+        const int base = __shfl_sync(kFull, nbase, j - nj0);
         // the slides the batches need, in the order the refill warps produce them (same rule as theirs)
         if (j == 0 || whi < base) whi = base;
         for (; whi < base + kSpan; whi += 8) sg++;
         if ((int) (jg % kMmaWarps) != mw) continue;   // the other warp's batch
+        const long long c0 = CLK();
+        mbar_wait(&S.op_full[st], (int) ((jg / kOpStages) & 1));
+        const long long c1 = CLK();
         mbar_wait(&S.acc_empty[s], (int) (((jg / kAcc) & 1) ^ 1));
         const long long c2 = CLK();
         for (; sw < sg; sw++) mbar_wait(&S.a_ready[sw % kSlides], (int) ((sw / kSlides) & 1));
