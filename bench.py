@@ -529,7 +529,7 @@ def run_ours(args, rank, world, local_rank):
         taps = (2 * cfg["m"] + 2) ** cfg["d"]
         flops = 4.0 * taps * M_local      # per tap: complex value x real weight = 2 FMA = 4 flops
         kname = (("spread_mma_kernel (B^T)" if spread_dom else "interp_mma_kernel (B)") if dmma else
-                 ("spread_tf32_kernel (B^T)" if spread_dom else "interp_tf32_kernel (B)") if tf32 else
+                 ("spread_tf32_kernel (B^T)" if spread_dom else "tc5_interp_kernel (B)") if tf32 else
                  ("spread (B^T)" if spread_dom else "interp (B)"))
         roof = {"bound": "hbm", "kernel": kname, "achieved": hbm_ach, "peak": peak, "unit": "GB/s",
                 "frac": (hbm_ach / peak) if hbm_ach else None, "traffic": traffic,
@@ -567,7 +567,9 @@ def run_ours(args, rank, world, local_rank):
                 "multi_gpu": ("node-sharded x%d: trafo replicates f_hat and the grid; adjoint reduces f_hat (%s, "
                               "%.3f ms per D^T + reduction measured alone)" % (world, sp_reduce_name(reduce_mode), collective_ms)
                               if world > 1 else "single GPU"),
-                "nodes_setup_s": t_nodes},
+                "nodes_setup_s": t_nodes,
+                **({"fp32_kernels": "B: tcgen05.mma kind::tf32, grid window and accumulators in tensor memory (tc5.cu, 5 KB operand "
+                                    "image per 16-node batch); B^T: 3xTF32 mma.sync (mma3d.cu)"} if tf32 else {})},
             "stage_ms": {"trafo": {"D": stage[0][0], "F": stage[0][1], "B": stage[0][2]},
                          "adjoint": {"DT": stage[1][0], "F": stage[1][1], "BT": stage[1][2]},
                          "ms_per_step_with_timers": ms_step_timers},

@@ -53,12 +53,8 @@ constexpr int kSpan = 24;        // slots one batch contracts: 3 k-steps of 8
 constexpr int kOpStages = 16;    // operand-image ring: 80 KB in flight per SM (the images stream from HBM, ~2 us away)
 constexpr int kAcc = 3;          // accumulator stages (4 row blocks x 16 columns each)
 constexpr int kEpi = 2;          // epilogue warpgroups; group g takes the batches with index = g (mod kEpi)
-#ifndef TC5_MMA_WARPS
-#define TC5_MMA_WARPS 1
-#endif
-constexpr int kMmaWarps = TC5_MMA_WARPS;   // MMA-issuing warps; warp m takes the batches with index = m (mod kMmaWarps).  Two warps
-                                 // (one's hand-shakes under the other's MMAs) measured no faster and are NOT validated at size.
-static_assert(kMmaWarps == 1 || kMmaWarps == kEpi, "epilogue group g reports the completion of MMA warp g's batches");
+constexpr int kMmaWarps = 1;     // MMA-issuing warps.  (Two warps taking alternate batches, so that one's hand-shakes run under the
+                                 // other's MMAs, measured no faster -- the refill and the epilogue then limit -- and are not wired.)
 constexpr int kThreadsI = 32 * (4 * kEpi + 4 + kMmaWarps + 1);
 constexpr int kImgBytes = 5248;  // psi2 hi 1536 | psi2 lo 1536 | psi0 1024 | psi1 1024 | output index of the 16 nodes 64 | batch entry 8 | pad
 constexpr int kOffLo = 1536, kOffP0 = 3072, kOffP1 = 4096, kOffPerm = 5120, kOffEntry = 5184;
@@ -167,7 +163,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // ---- batch table and chunks (plan time) ---------------------------------------------------------------------
-// entry.x = first node (tile order), entry.y = base | nb << 24.  One warp per work unit (see mma3d.cu) walks the unit's
+// entry.x = first node (tile order), entry.y = base | nb << 24 | two_ksteps << 29.  One warp per work unit (see mma3d.cu) walks the unit's
 // sorted nodes 32 at a time: a batch starts at the first unassigned node, base = its u2 rounded down to a multiple of 8,
 // and takes up to 16 nodes with u2 + W <= base + 24.
 template <bool FILL>
@@ -192,7 +188,10 @@ __global__ void t5_batches_kernel(const uint64_t *__restrict__ keys, const uint3
       const int base = __shfl_sync(kFull, u, o) & ~7;
       const bool member = lane >= o && lane < o + kN && u + W <= base + kSpan;
       const int nb = __popc(__ballot_sync(kFull, member));
-      if (FILL && lane == 0) table[out + nbat] = make_uint2((uint32_t) (pos + o), (unsigned) base | ((unsigned) nb << 24));
+      // bit 29: the taps of every node end below base + 16 (the batch's last node has the largest u2): two k-steps suffice
+      const int u_last = __shfl_sync(kFull, u, o + nb - 1);
+      const unsigned two = (u_last + W <= base + 16) ? 1u : 0u;
+      if (FILL && lane == 0) table[out + nbat] = make_uint2((uint32_t) (pos + o), (unsigned) base | ((unsigned) nb << 24) | (two << 29));
       nbat++;
       o += nb;
     }
@@ -458,7 +457,7 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
           }
           const long long need = jg0 + hz - 1;   // last batch that must have committed (-1: none)
           const long long c0 = CLK();
-          if (need >= 0 && !((dbg & 16) && j > 0)) {
+          if (need >= 0) {
             // batch `need` and everything before it: the newest batch of either MMA stream
             const volatile int *du0 = &S.done_upto[need % kMmaWarps], *du1 = &S.done_upto[(need + 1) % kMmaWarps];
             while ((long long) *du0 < need) { }
@@ -502,7 +501,7 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
     }
     if ((dbg & 8) && q == 0 && lane == 0) { for (int i = 0; i < 4; i++) atomicAdd(&g_t5dbg[8 + i], tdbg[i]); }
   } else if (warp < 4 * kEpi + 4 + kMmaWarps) {
-    // ===== MMA issue: the whole warp runs the loop (uniform operands), one elected lane issues; warp mw takes every second batch
+    // ===== MMA issue: the whole warp runs the loop (uniform operands), one elected lane issues
     constexpr uint32_t idesc = make_idesc(128, kN);
     const int mw = warp - (4 * kEpi + 4);
     long long jg = 0, sg = 0, sw = 0;   // batches walked, slides needed so far, slides this warp has waited for
@@ -510,19 +509,19 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
       const uint4 chunk = chunks[ch];
       const int nbat = (int) (chunk.z - chunk.y);
       int whi = 0;
-      // window bases from the batch table, 32 per coalesced load (the image of another warp's batch may be gone already)
-      int nj0 = 0, nbase = lane < nbat ? t5_base(table[chunk.y + lane]) : 0x3fffffff;
       for (int j = 0; j < nbat; j++, jg++) {
         const int st = (int) (jg % kOpStages), s = (int) (jg % kAcc);
-        if (j >= nj0 + 32) { nj0 += 32; nbase = nj0 + lane < nbat ? t5_base(table[chunk.y + nj0 + lane]) : 0x3fffffff; }
-        const int base = __shfl_sync(kFull, nbase, j - nj0);
-        // the slides the batches need, in the order the refill warps produce them (same rule as theirs)
-        if (j == 0 || whi < base) whi = base;
-        for (; whi < base + kSpan; whi += 8) sg++;
-        if ((int) (jg % kMmaWarps) != mw) continue;   // the other warp's batch
         const long long c0 = CLK();
         mbar_wait(&S.op_full[st], (int) ((jg / kOpStages) & 1));
         const long long c1 = CLK();
+        // the batch entry travels in the image (reading it from the batch table through a lane cache measured 0.3 ms
+        // slower per launch); with more than one issuing warp the image of another warp's batch could be gone already
+        const unsigned ey = reinterpret_cast<const uint2 *>(S.ops[st] + kOffEntry)->y;
+        const int base = (int) (ey & 0xffffffu);
+        const int nk = ((ey >> 29) & 1u) ? 2 : 3;
+        // the slides the batches need, in the order the refill warps produce them (same rule as theirs)
+        if (j == 0 || whi < base) whi = base;
+        for (; whi < base + kSpan; whi += 8) sg++;
         mbar_wait(&S.acc_empty[s], (int) (((jg / kAcc) & 1) ^ 1));
         const long long c2 = CLK();
         for (; sw < sg; sw++) mbar_wait(&S.a_ready[sw % kSlides], (int) ((sw / kSlides) & 1));
@@ -532,7 +531,7 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
           const uint32_t bsm = smem_u32(S.ops[st]);
 #pragma unroll
           for (int i = 0; i < 3; i++) {
-            if ((dbg & 4) && i > 0) break;
+            if (i >= nk || ((dbg & 4) && i > 0)) break;
             const uint32_t kb = (uint32_t) ((base + 8 * i) % kRing);
             const uint64_t bh = make_desc(bsm + 2 * i * kBChunk, kBChunk, kBGroup);
             const uint64_t bl = make_desc(bsm + kOffLo + 2 * i * kBChunk, kBChunk, kBGroup);
@@ -560,7 +559,7 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
       for (int j = 0; j < nbat; j++, jg++) {
         const int st = (int) (jg % kOpStages);
         const long long c0 = CLK();
-        mbar_wait(&S.op_empty[st], (int) (((jg / kOpStages) & 1) ^ 1));
+        mbar_wait<true>(&S.op_empty[st], (int) (((jg / kOpStages) & 1) ^ 1));
         if ((dbg & 8) && lane == 0) tdbg[0] += clock64() - c0;
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -399,6 +399,9 @@ def test_tc5_fp32_kernels_vs_oracle_and_mma_sync(case):
         got[tc5] = (a, eng.adjoint(f))
         eng.close()
         assert np.array_equal(a, b)
-        assert rel_l2(a, want_f) <= TOL["float"] and rel_l2(got[tc5][1], want_fh) <= TOL["float"]
+        # the adjoint of the clustered case adds 3e4 fp32 samples into a few cells: two fp32 summation orders (ours, the
+        # oracle's) differ by more than the 1e-5 bar there -- with either kernel family
+        tol_adj = 4e-5 if spec.get("cluster") else TOL["float"]
+        assert rel_l2(a, want_f) <= TOL["float"] and rel_l2(got[tc5][1], want_fh) <= tol_adj
         assert rel_l2(fb[1], -2 * want_f) <= TOL["float"]
     assert rel_l2(got[2][0], got[1][0]) <= 2e-6 and rel_l2(got[2][1], got[1][1]) <= 2e-6
