@@ -427,7 +427,7 @@ bool same_plan(const nfftcu_ctx *c, int precision, int d, const int64_t *N, cons
 }
 size_t plan_device_bytes(const nfftcu_ctx *c) {   // rough: what parking this plan keeps allocated
   const size_t r = real_size(c);
-  return 2 * r * (size_t) c->n_total * (size_t) c->batch_cap * (c->grid2 ? 2 : 1) + c->mma_images_bytes + c->tc5_images_bytes +
+  return 2 * r * (size_t) c->n_total * (size_t) c->batch_cap * (c->grid2 ? 2 : 1) + c->mma_images_bytes + c->tc5i.images_bytes + c->tc5s.images_bytes +
          (size_t) c->M * (size_t) (r * c->d * 4 + 48);
 }
 }  // namespace
@@ -612,7 +612,8 @@ int nfftcu_destroy(nfftcu_ctx *c) {
   fft_free_axes(c);
   for (int t = 0; t < NFFTCU_MAX_D; t++)
     if (c->c_dev[t]) pool_free(c->c_dev[t]);
-  void *bufs[] = {c->tc5_images, c->tc5_batches, (void *) c->tc5_batch_start, (void *) c->tc5_counts, (void *) c->tc5_chunk_start, c->tc5_chunks,
+  void *bufs[] = {c->tc5i.images, c->tc5i.batches, (void *) c->tc5i.batch_start, (void *) c->tc5i.chunk_start, c->tc5i.chunks,
+                  c->tc5s.images, c->tc5s.batches, (void *) c->tc5s.batch_start, (void *) c->tc5s.chunk_start, c->tc5s.chunks, (void *) c->tc5_counts, c->tc5_ft,
                   c->mma_images, c->mma_batches, (void *) c->mma_batch_start, (void *) c->mma_counts, (void *) c->mma_chunk_start, c->mma_chunks, c->f_tile, c->kbpoly_dev, c->tile_keys, (void *) c->tile_perm, c->tile_x, (void *) c->bin_start, c->tile_psi, c->grid, c->x_dev, c->x_stage, (void *) c->diff_flag, c->x_sorted, (void *) c->perm, c->keys_ref, c->psi_table,
                   c->sort_tmp, c->fhat_dev, c->f_dev};
   for (void *p : bufs)

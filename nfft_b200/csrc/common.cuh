@@ -74,7 +74,19 @@ struct FftAxis {
 
 }  // namespace nfftcu
 
-namespace nfftcu { struct PeerState; }
+namespace nfftcu {
+struct PeerState;
+// one set of plan-time tables of the tcgen05 kernels (tc5.cu)
+struct Tc5Tables {
+  void *batches = nullptr;          // uint2 per batch: first node, base | nb << 24 | flags
+  uint32_t *batch_start = nullptr;  // units + 1 offsets into batches
+  uint32_t *chunk_start = nullptr;  // units + 1 offsets into chunks
+  void *chunks = nullptr;           // uint4 per chunk: tile, first batch, end batch
+  void *images = nullptr;           // operand image of every batch
+  size_t images_bytes = 0;
+  long long units = 0, batch_cap = 0, chunk_cap = 0, nchunks = 0, nbatches = 0;
+};
+}
 
 struct nfftcu_ctx_s {
   int prec = NFFTCU_DOUBLE;
@@ -137,15 +149,16 @@ struct nfftcu_ctx_s {
   bool mma_images_ready = false;
   bool mma_images_tf32 = false;     // images hold packed fp32 / TF32 pairs (fp32 plans on the TF32 kernels)
   int opt_window_images = 0;        // 0 auto | 1 off | 2 on regardless of the memory budget
-  // fp32 plans on the tcgen05 / TMEM kernels (tc5.cu): own batch table (<= 16 nodes, 8-aligned window base), chunks, images
-  bool tc5_ready = false;
-  void *tc5_batches = nullptr;      // uint2 per batch: first node, base | nb << 24
-  uint32_t *tc5_batch_start = nullptr, *tc5_counts = nullptr, *tc5_chunk_start = nullptr;
-  void *tc5_chunks = nullptr;       // uint4 per chunk: tile, first batch, end batch
-  void *tc5_images = nullptr;       // 5 KB per batch: psi2 as the (hi, lo) B operand, psi0 / psi1 placed in the footprint
-  size_t tc5_images_bytes = 0;
-  long long tc5_units = 0, tc5_batch_cap = 0, tc5_chunk_cap = 0, tc5_nchunks = 0, tc5_nbatches = 0;
-  int opt_tc5 = 0;                  // NFFTCU_OPT_TC5: 0 auto (fp32, d = 3, m <= 6) | 1 off | 2 on
+  // fp32 plans on the tcgen05 / TMEM kernels (tc5.cu): own batch tables (<= 16 nodes; interpolation: 8-aligned window base,
+  // 24 slots; spreading: 16-aligned, 32 slots), chunk lists and operand images
+  nfftcu::Tc5Tables tc5i, tc5s;
+  uint32_t *tc5_counts = nullptr;   // scratch: batches / chunks per unit
+  void *tc5_ft = nullptr;           // spreading: samples in tile order, M + 18 float2
+  long long tc5_ft_cap = 0;
+  long long tc5_counts_units = 0;
+  bool tc5_ready = false;           // tc5i is valid for the current nodes: B runs on tc5_interp_kernel
+  bool tc5s_ready = false;          // tc5s is valid: B^T runs on tc5_spread_kernel
+  int opt_tc5 = 0;                  // NFFTCU_OPT_TC5: 0 auto (fp32, d = 3, m <= 6) | 1 off | 2 B only | 3 B and B^T
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

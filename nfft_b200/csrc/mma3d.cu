@@ -1427,7 +1427,7 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
     }
   }
   // fp32 plans: the tcgen05 kernels take over when their tables and images could be built (tc5.cu)
-  c->tc5_ready = false;
+  c->tc5_ready = c->tc5s_ready = false;
   if (tc5_selected(c)) NFFTCU_TRY(tc5_build(c, P));
   c->mma_ready = true;
   return NFFTCU_OK;
@@ -1449,6 +1449,7 @@ int mma3d_interp(nfftcu_ctx *c, void *f_dev) {
 }
 
 int mma3d_spread(nfftcu_ctx *c, const void *f_dev) {
+  if (c->tc5s_ready) return tc5_spread(c, f_dev);
   return c->prec == NFFTCU_DOUBLE ? dispatch<double>(c, f_dev, nullptr, true) : dispatch<float>(c, f_dev, nullptr, true);
 }
 

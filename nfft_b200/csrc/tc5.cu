@@ -63,6 +63,17 @@ constexpr int kSlides = 8;       // window hand-offs in flight (the hazards keep
 constexpr int kBChunk = 256, kBGroup = 128;   // B operand: (slot/4)*256 + (node/8)*128 + (node%8)*16 + (slot%4)*4
 constexpr int kColA = 64 * kAcc;  // TMEM: D stage s at 64 s + 16 b, A ring of row block b at kColA + 2 kRing b (+ kRing: lo) + slot
 static_assert(kColA + 8 * kRing <= 512, "tensor memory has 512 columns");
+// spreading (tc5_spread_kernel): batches with a 16-aligned base whose taps lie in [base, base + 32); the accumulators are a
+// ring of 64 z-slots per row (256 TMEM columns), the A operand (psi0 psi1 f)[row, node] as a (hi, lo) pair takes 128 columns
+// per stage, two stages
+constexpr int kSpanS = 32;       // slots one spreading batch touches
+constexpr int kRingS = 64;       // accumulator ring
+constexpr int kOpStagesS = 12;   // operand-image ring of the spreading kernel
+constexpr int kImgBytesS = 6272; // psi2 hi 2048 | psi2 lo 2048 | psi0 1024 | psi1 1024 | batch entry 8 | pad
+constexpr int kOffLoS = 2048, kOffP0S = 4096, kOffP1S = 5120, kOffEntryS = 6144;
+constexpr int kStageS = kImgBytesS + 256;   // + the batch's samples: 18 float2 from an even node index on (TMA needs 16-byte alignment)
+constexpr int kOpG = 2;          // operand warpgroups of the spreading kernel; group g takes the batches = g (mod 2) and owns A stage g
+constexpr int kThreadsS = 32 * (4 * kOpG + 4 + 2);
 constexpr int kChunkBatches = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -70,6 +81,9 @@ __device__ __forceinline__ int b_off(int n, int s) { return (s >> 2) * kBChunk +
 // psi0 / psi1 rows of 16 floats; the four 16-byte chunks of row l are rotated by l >> 1 so that the eight rows a quarter
 // warp reads in one LDS.128 phase fall into eight different bank groups
 __device__ __forceinline__ int w_off(int l, int n) { return l * 64 + ((((n >> 2) + (l >> 1)) & 3) << 4) + (n & 3) * 4; }
+
+// spreading: B[slot][node], K = nodes: (node/8)*1024 + ((node/4)&1)*512 + (slot/8)*128 + (slot%8)*16 + (node%4)*4
+__device__ __forceinline__ int sb_off(int n, int s) { return (n >> 3) * 1024 + ((n >> 2) & 1) * 512 + (s >> 3) * 128 + (s & 7) * 16 + (n & 3) * 4; }
 
 __device__ __forceinline__ int wrapi(int v, int n) {
   v %= n;
@@ -155,6 +169,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
                  "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+                 "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+                 "r"(__float_as_uint(v[15])) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -164,9 +187,9 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 // ---- batch table and chunks (plan time) ---------------------------------------------------------------------
 // entry.x = first node (tile order), entry.y = base | nb << 24 | two_ksteps << 29.  One warp per work unit (see mma3d.cu) walks the unit's
-// sorted nodes 32 at a time: a batch starts at the first unassigned node, base = its u2 rounded down to a multiple of 8,
-// and takes up to 16 nodes with u2 + W <= base + 24.
-template <bool FILL>
+// sorted nodes 32 at a time: a batch starts at the first unassigned node, base = its u2 rounded down to a multiple of
+// ALIGN, and takes up to 16 nodes with u2 + W <= base + SPAN (interpolation: 8 / 24, spreading: 16 / 32).
+template <bool FILL, int ALIGN, int SPAN>
 __global__ void t5_batches_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ unit_start,
                                   uint32_t *__restrict__ counts, const uint32_t *__restrict__ batch_start,
                                   uint2 *__restrict__ table, long long units, MmaParams P) {
@@ -185,8 +208,8 @@ __global__ void t5_batches_kernel(const uint64_t *__restrict__ keys, const uint3
     int o = 0;
     while (pos + o < k1) {
       if (o + kN > 32 && pos + 32 < k1) break;   // the batch may extend beyond these 32 nodes: reload from pos + o
-      const int base = __shfl_sync(kFull, u, o) & ~7;
-      const bool member = lane >= o && lane < o + kN && u + W <= base + kSpan;
+      const int base = __shfl_sync(kFull, u, o) & ~(ALIGN - 1);
+      const bool member = lane >= o && lane < o + kN && u + W <= base + SPAN;
       const int nb = __popc(__ballot_sync(kFull, member));
       // bit 29: the taps of every node end below base + 16 (the batch's last node has the largest u2): two k-steps suffice
       const int u_last = __shfl_sync(kFull, u, o + nb - 1);
@@ -250,6 +273,7 @@ struct WinParams {
 };
 
 // one warp per batch; the image buffer was cleared before, only the taps are written
+template <bool SPREAD>
 __global__ void __launch_bounds__(128)
 t5_images_kernel(const float *__restrict__ xt, const uint32_t *__restrict__ perm, const uint4 *__restrict__ chunks,
                  const uint2 *__restrict__ table, unsigned char *__restrict__ img, MmaParams P, WinParams Wp) {
@@ -261,9 +285,9 @@ t5_images_kernel(const float *__restrict__ xt, const uint32_t *__restrict__ perm
   for (uint32_t b = chunk.y + (threadIdx.x >> 5); b < chunk.z; b += 4) {
     const uint2 e = table[b];
     const int base = t5_base(e), nb = t5_nb(e);
-    unsigned char *im = img + (size_t) b * kImgBytes;
-    if (lane < 16) reinterpret_cast<uint32_t *>(im + kOffPerm)[lane] = lane < nb ? perm[e.x + lane] : 0u;
-    if (lane == 16) *reinterpret_cast<uint2 *>(im + kOffEntry) = e;
+    unsigned char *im = img + (size_t) b * (SPREAD ? kImgBytesS : kImgBytes);
+    if (!SPREAD && lane < 16) reinterpret_cast<uint32_t *>(im + kOffPerm)[lane] = lane < nb ? perm[e.x + lane] : 0u;
+    if (lane == 16) *reinterpret_cast<uint2 *>(im + (SPREAD ? kOffEntryS : kOffEntry)) = e;
     for (int i = lane; i < nb * 3 * W; i += 32) {
       const int n = i / (3 * W), r = i - n * 3 * W, t = r / W, l = r - t * W;
       const float x = xt[3 * (size_t) (e.x + n) + t];
@@ -273,13 +297,13 @@ t5_images_kernel(const float *__restrict__ xt, const uint32_t *__restrict__ perm
       const float v = (float) window_phi(dist, Wp.m2, Wp.b[t], Wp.window, Wp.ws[t]);
       const int uw = wrapi((int) u, nn);
       if (t == 2) {
-        const int s = uw - base + l;   // 0 .. 23
+        const int s = uw - base + l;   // 0 .. 23 (spreading: 0 .. 31)
         const float hi = tf32_rna(v);
-        *reinterpret_cast<float *>(im + b_off(n, s)) = hi;
-        *reinterpret_cast<float *>(im + kOffLo + b_off(n, s)) = v - hi;
+        *reinterpret_cast<float *>(im + (SPREAD ? sb_off(n, s) : b_off(n, s))) = hi;
+        *reinterpret_cast<float *>(im + (SPREAD ? kOffLoS + sb_off(n, s) : kOffLo + b_off(n, s))) = v - hi;
       } else {
         const int row = uw - P.T * (t == 0 ? a : bt) + l;   // 0 .. 15
-        *reinterpret_cast<float *>(im + (t == 0 ? kOffP0 : kOffP1) + w_off(row, n)) = v;
+        *reinterpret_cast<float *>(im + (SPREAD ? (t == 0 ? kOffP0S : kOffP1S) : (t == 0 ? kOffP0 : kOffP1)) + w_off(row, n)) = v;
       }
     }
   }
@@ -578,95 +602,404 @@ tc5_interp_kernel(const float2 *__restrict__ G, float *__restrict__ f, const uin
   if (warp == 4 * kEpi + 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
 }
 
+
+// ---- spreading ------------------------------------------------------------------------------------------------
+// G[row, z] += sum_node (psi0 psi1 f)[row, node] psi2[node, z]: the accumulators ARE the window -- a ring of 64 z-slots per
+// row in TMEM columns [0, 256) (row block b at 64 b), fp32, alive for the whole sweep of a tile.  Per batch (<= 16 nodes,
+// taps in [base, base + 32), base a multiple of 16):
+//   operand warps (2 groups x 4): A[row, node] = psi0[l0] psi1[l1] f_c[node] for the thread's four rows, split into tf32
+//                 (hi, lo), written to the group's A stage (128 columns) with tcgen05.st; a_full
+//   MMA warp:     2 k-steps (8 nodes each) x 3 split terms x 4 row blocks of M = 128, N = 32 (two N = 16 pieces when the 32
+//                 slots wrap around the ring), accumulating; commits release the A stage and the image stage
+//   retire warps: a block of 16 cells leaves the ring when every batch that touches it has completed: tcgen05.ld,
+//                 red.global.add.v4.f32 (two cells of a pencil, zero quadruples skipped), columns cleared with tcgen05.st
+//   feeder:       image (psi2 as the B operand with K = nodes, psi0 / psi1) and the batch's samples by TMA
+constexpr int kColAS = 256;   // A stages: kColAS + 128 stage + 32 b (+16: lo) + node
+
+struct __align__(128) SmemS {
+  unsigned char ops[kOpStagesS][kStageS];
+  int done_upto;                   // every batch <= done_upto has completed (published by the operand warps)
+  int retired[4];                  // retire warp q: every block <= retired[q] (CTA-wide block sequence) is in the grid and cleared
+  uint64_t op_full[kOpStagesS], op_empty[kOpStagesS];
+  uint64_t a_full[kOpG], a_empty[kOpG];
+  uint32_t tmem_base;
+};
+
+__global__ void t5_gather_f_kernel(const float2 *__restrict__ f, const uint32_t *__restrict__ perm, float2 *__restrict__ ft,
+                                   long long M) {
+  const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < M) ft[k] = f[perm[k]];
+}
+
+__global__ void __launch_bounds__(kThreadsS, 1)
+tc5_spread_kernel(float2 *__restrict__ G, const float2 *__restrict__ ft, const uint4 *__restrict__ chunks, int nchunks,
+                  const uint2 *__restrict__ table, const unsigned char *__restrict__ img, MmaParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemS &S = *reinterpret_cast<SmemS *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarpRetire = 4 * kOpG, kWarpMma = 4 * kOpG + 4;
+  if (tid == 0) {
+    for (int i = 0; i < kOpStagesS; i++) { mbar_init(&S.op_full[i], 1); mbar_init(&S.op_empty[i], 1); }
+    for (int i = 0; i < kOpG; i++) { mbar_init(&S.a_full[i], 4); mbar_init(&S.a_empty[i], 1); }
+    S.done_upto = -1;
+    for (int i = 0; i < 4; i++) S.retired[i] = -1;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = S.tmem_base;
+  const int n2 = P.n2;
+  if (warp >= kWarpRetire && warp < kWarpMma) {   // clear the accumulator ring
+    const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) z[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; c++) tmem_st16(tb + lane_base + 16 * c, z);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < kWarpRetire) {
+    // ===== operand warps: lane quarter q, row r = 32 q + lane of every row block; block b = 2 c + h is component c of
+    // pencil p = 128 h + r, i.e. l0 = 8 h + 2 q + (lane >> 4), l1 = lane & 15
+    const int q = warp & 3, grp = warp >> 2;
+    const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+    const int l1 = lane & 15, l0a = 2 * q + (lane >> 4);
+    long long jg = 0;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const uint4 chunk = chunks[ch];
+      const int nbat = (int) (chunk.z - chunk.y);
+      for (int j = 0; j < nbat; j++, jg++) {
+        if ((int) (jg % kOpG) != grp) continue;   // the other group's batch
+        const int st = (int) (jg % kOpStagesS);
+        mbar_wait(&S.op_full[st], (int) ((jg / kOpStagesS) & 1));
+        const unsigned char *op = S.ops[st];
+        const uint2 e = *reinterpret_cast<const uint2 *>(op + kOffEntryS);
+        const float2 *fs = reinterpret_cast<const float2 *>(op + kImgBytesS) + (e.x & 1u);   // samples of nodes e.x ...
+        float w[2][16];   // row weights (psi0[l0a] psi1[l1], psi0[l0a + 8] psi1[l1]) of the 16 nodes
+#pragma unroll
+        for (int cq = 0; cq < 4; cq++) {
+          const float4 p1 = *reinterpret_cast<const float4 *>(op + kOffP1S + l1 * 64 + (((cq + (l1 >> 1)) & 3) << 4));
+          const float4 pa = *reinterpret_cast<const float4 *>(op + kOffP0S + l0a * 64 + (((cq + (l0a >> 1)) & 3) << 4));
+          const float4 pb = *reinterpret_cast<const float4 *>(op + kOffP0S + (l0a + 8) * 64 + (((cq + ((l0a + 8) >> 1)) & 3) << 4));
+          w[0][4 * cq] = pa.x * p1.x; w[0][4 * cq + 1] = pa.y * p1.y; w[0][4 * cq + 2] = pa.z * p1.z; w[0][4 * cq + 3] = pa.w * p1.w;
+          w[1][4 * cq] = pb.x * p1.x; w[1][4 * cq + 1] = pb.y * p1.y; w[1][4 * cq + 2] = pb.z * p1.z; w[1][4 * cq + 3] = pb.w * p1.w;
+        }
+        float fr[16], fi[16];
+#pragma unroll
+        for (int n = 0; n < 16; n++) { const float2 v = fs[n]; fr[n] = v.x; fi[n] = v.y; }
+        // the group's A stage: free once the MMAs of the group's previous batch have completed
+        mbar_wait(&S.a_empty[grp], (int) (((jg / kOpG) & 1) ^ 1));
+        if (q == 0 && lane == 0 && jg >= kOpG) atomicMax(&S.done_upto, (int) (jg - kOpG));   // MMAs complete in order
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int n = 0; n < 16; n++) {
+              const float v = w[h][n] * (c ? fi[n] : fr[n]);
+              hi[n] = tf32_rna(v);
+              lo[n] = v - hi[n];
+            }
+            const uint32_t col = tb + lane_base + kColAS + 128 * grp + 32 * (2 * c + h);
+            tmem_st16(col, hi);
+            tmem_st16(col + 16, lo);
+          }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.a_full[grp]);
+      }
+    }
+    // the group's last batch: publish its completion (the retire warps wait for it)
+    const long long J = jg;
+    long long last = J - 1;
+    while (last >= 0 && (int) (last % kOpG) != grp) last--;
+    if (last >= 0) {
+      mbar_wait(&S.a_empty[grp], (int) ((last / kOpG) & 1));
+      if (q == 0 && lane == 0) atomicMax(&S.done_upto, (int) last);
+    }
+  } else if (warp < kWarpMma) {
+    // ===== retire warps: thread (q, lane) owns row r = 32 q + lane of the four row blocks = pencils r and 128 + r
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t) (q * 32) << 16;
+    const int r = 32 * q + lane;
+    long long jg0 = 0;
+    int goff = 0;   // block sequence number of the chunk's first block
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const uint4 chunk = chunks[ch];
+      const int nbat = (int) (chunk.z - chunk.y);
+      const int tile = (int) chunk.x;
+      const int a = tile / P.NT1, bt = tile - a * P.NT1;
+      unsigned rowoff[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int p = 128 * h + r;
+        rowoff[h] = (unsigned) ((wrapi(P.T * a + (p >> 4), P.n0) * (long long) P.n1 + wrapi(P.T * bt + (p & 15), P.n1)) * n2);
+      }
+      const int kfirst = t5_base(table[chunk.y]) >> 4, klast = (t5_base(table[chunk.z - 1]) >> 4) + 1;
+      int cj0 = 0, cbase = lane < nbat ? t5_base(table[chunk.y + lane]) : 0x3fffffff;   // cursor: bases of batches [cj0, cj0 + 32)
+      int jp = 0;   // batches [0, jp) of the chunk have base / 16 <= k
+      for (int k = kfirst; k <= klast; k++) {
+        for (;;) {
+          if (jp >= cj0 + 32) { cj0 += 32; cbase = cj0 + lane < nbat ? t5_base(table[chunk.y + cj0 + lane]) : 0x3fffffff; }
+          if (jp >= nbat || (__shfl_sync(kFull, cbase, jp - cj0) >> 4) > k) break;
+          jp++;
+        }
+        // block k is touched by the batches with base / 16 in {k - 1, k}: all of [0, jp) must have completed
+        const long long need = jg0 + jp - 1;
+        {
+          const volatile int *du = &S.done_upto;
+          while ((long long) *du < need) { }
+        }
+        tc_fence_after();
+        const uint32_t col = (uint32_t) ((16 * k) & (kRingS - 1));
+        float v[4][16];
+#pragma unroll
+        for (int b = 0; b < 4; b++) tmem_ld16(tb + lane_base + 64 * b + col, v[b]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float re0 = v[h][i], im0 = v[2 + h][i], re1 = v[h][i + 1], im1 = v[2 + h][i + 1];
+            if (re0 != 0.f || im0 != 0.f || re1 != 0.f || im1 != 0.f) {
+              int z = 16 * k + i;
+              if (z >= n2) z %= n2;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                           ::"l"(G + rowoff[h] + z), "f"(re0), "f"(im0), "f"(re1), "f"(im1) : "memory");
+            }
+          }
+        float zr[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) zr[i] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; b++) tmem_st16(tb + lane_base + 64 * b + col, zr);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int *>(&S.retired[q]) = goff + (k - kfirst);
+      }
+      goff += klast - kfirst + 1;
+      jg0 += nbat;
+    }
+  } else if (warp == kWarpMma) {
+    // ===== MMA issue: the whole warp runs the loop (uniform operands), one elected lane issues
+    constexpr uint32_t idesc32 = make_idesc(128, 32), idesc16 = make_idesc(128, 16);
+    long long jg = 0;
+    int goff = 0;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const uint4 chunk = chunks[ch];
+      const int nbat = (int) (chunk.z - chunk.y);
+      const int klast = (t5_base(table[chunk.z - 1]) >> 4) + 1;   // needed at the end of the chunk only
+      int kfirst = 0;
+      for (int j = 0; j < nbat; j++, jg++) {
+        const int st = (int) (jg % kOpStagesS), as = (int) (jg % kOpG);
+        mbar_wait(&S.op_full[st], (int) ((jg / kOpStagesS) & 1));
+        const uint2 e = *reinterpret_cast<const uint2 *>(S.ops[st] + kOffEntryS);
+        const int base = t5_base(e), kb = base >> 4;
+        if (j == 0) kfirst = kb;
+        mbar_wait(&S.a_full[as], (int) ((jg / kOpG) & 1));
+        // the ring positions of blocks kb, kb + 1 were those of kb - 4, kb - 3: they and every block of the earlier chunks
+        // (another tile) must be in the grid and cleared
+        const int need = (kb - 3 >= kfirst) ? goff + (kb - 3 - kfirst) : goff - 1;
+        {
+          const volatile int *rt = S.retired;
+          while (min(min(rt[0], rt[1]), min(rt[2], rt[3])) < need) { }
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t bsm = smem_u32(S.ops[st]);
+          const uint32_t s0 = (uint32_t) (base & (kRingS - 1));
+          const bool wraps = s0 + kSpanS > kRingS;   // base = 48 (mod 64): two pieces of 16 slots
+          const int nks = t5_nb(e) > 8 ? 2 : 1;      // nodes 8 .. 15 absent: their k-step is all zero
+          for (int ks = 0; ks < nks; ks++) {
+            const uint64_t bh = make_desc(bsm + ks * 1024, 512, 128);
+            const uint64_t bl = make_desc(bsm + kOffLoS + ks * 1024, 512, 128);
+#pragma unroll
+            for (int term = 0; term < 3; term++)
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const uint32_t a_hi = tb + kColAS + 128 * as + 32 * b + 8 * ks;
+                const uint32_t aa = term == 0 ? a_hi + 16 : a_hi;
+                const uint64_t bb = term == 1 ? bl : bh;
+                if (!wraps) {
+                  mma_ts(tb + 64 * b + s0, aa, bb, idesc32, 1u);
+                } else {
+                  mma_ts(tb + 64 * b + s0, aa, bb, idesc16, 1u);
+                  mma_ts(tb + 64 * b, aa, bb + (uint64_t) (256 >> 4), idesc16, 1u);   // slot groups 2, 3 -> ring slots 0 .. 15
+                }
+              }
+          }
+          mma_commit(&S.a_empty[as]);
+          mma_commit(&S.op_empty[st]);
+        }
+        __syncwarp();
+      }
+      goff += klast - kfirst + 1;
+    }
+  } else {
+    // ===== feeder: image and samples of every batch into the ring
+    long long jg = 0;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const uint4 chunk = chunks[ch];
+      const int nbat = (int) (chunk.z - chunk.y);
+      int cj0 = 0;
+      uint32_t cx = lane < nbat ? table[chunk.y + lane].x : 0u;   // first nodes of batches [cj0, cj0 + 32)
+      for (int j = 0; j < nbat; j++, jg++) {
+        if (j >= cj0 + 32) { cj0 += 32; cx = cj0 + lane < nbat ? table[chunk.y + cj0 + lane].x : 0u; }
+        const uint32_t first = __shfl_sync(kFull, cx, j - cj0);
+        const int st = (int) (jg % kOpStagesS);
+        mbar_wait<true>(&S.op_empty[st], (int) (((jg / kOpStagesS) & 1) ^ 1));
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&S.op_full[st])), "r"(kImgBytesS + 144) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(S.ops[st])), "l"(img + (size_t) (chunk.y + j) * kImgBytesS), "r"(kImgBytesS),
+                         "r"(smem_u32(&S.op_full[st])) : "memory");
+          // 18 samples from the even node index below `first`: 16-byte aligned source, covers first .. first + 15
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(S.ops[st] + kImgBytesS)), "l"(ft + (first & ~1u)), "r"(144),
+                         "r"(smem_u32(&S.op_full[st])) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+}
+
 }  // namespace
 
-// NFFTCU_OPT_TC5: 0 auto | 1 off | 2 on
+// NFFTCU_OPT_TC5: 0 auto (B on tc5_interp_kernel) | 1 off | 2 B only | 3 B and B^T
 bool tc5_selected(const nfftcu_ctx *c) {
   if (c->prec != NFFTCU_FLOAT || c->opt_tc5 == 1 || !mma3d_supported(c)) return false;
   if (!(c->opt_b_kernel == 0)) return false;   // an explicit kernel choice (generic / pencils / DMMA) wins
-  return c->opt_tc5 == 2 || c->opt_tc5 == 0;
+  return c->opt_tc5 != 1;
 }
 
-int tc5_build(nfftcu_ctx *c, const MmaParams &P) {
-  c->tc5_ready = false;
+namespace {
+
+// batch table, chunk list and (cleared) image buffer of one kernel: SPREAD selects the batch rule and the image size
+template <bool SPREAD>
+int build_tables(nfftcu_ctx *c, const MmaParams &P, Tc5Tables &T, bool *ok) {
+  *ok = false;
   const long long units = (long long) P.NT0 * P.NT1 * P.zseg;
   const int kb = 256;
-  if (c->tc5_units != units) {
-    if (c->tc5_batch_start) pool_free(c->tc5_batch_start);
+  if (c->tc5_counts_units != units) {
     if (c->tc5_counts) pool_free(c->tc5_counts);
-    if (c->tc5_chunk_start) pool_free(c->tc5_chunk_start);
-    c->tc5_batch_start = c->tc5_counts = c->tc5_chunk_start = nullptr;
-    NFFTCU_CUDA(pool_malloc((void **) &c->tc5_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    c->tc5_counts = nullptr;
     NFFTCU_CUDA(pool_malloc((void **) &c->tc5_counts, sizeof(uint32_t) * (size_t) units));
-    NFFTCU_CUDA(pool_malloc((void **) &c->tc5_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
-    c->tc5_units = units;
+    c->tc5_counts_units = units;
   }
+  if (T.units != units) {
+    if (T.batch_start) pool_free(T.batch_start);
+    if (T.chunk_start) pool_free(T.chunk_start);
+    T.batch_start = T.chunk_start = nullptr;
+    NFFTCU_CUDA(pool_malloc((void **) &T.batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    NFFTCU_CUDA(pool_malloc((void **) &T.chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    T.units = units;
+  }
+  constexpr int ALIGN = SPREAD ? 16 : 8, SPAN = SPREAD ? kSpanS : kSpan;
   const unsigned wgrid = (unsigned) ((units * 32 + kb - 1) / kb);
-  t5_batches_kernel<false><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, c->tc5_counts, nullptr,
-                                                        nullptr, units, P);
-  t5_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tc5_counts, c->tc5_batch_start, units);
+  t5_batches_kernel<false, ALIGN, SPAN><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, c->tc5_counts,
+                                                                     nullptr, nullptr, units, P);
+  t5_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tc5_counts, T.batch_start, units);
   uint32_t total = 0;
-  NFFTCU_CUDA(cudaMemcpyAsync(&total, c->tc5_batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaMemcpyAsync(&total, T.batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
-  if ((long long) total > c->tc5_batch_cap) {
-    if (c->tc5_batches) pool_free(c->tc5_batches);
-    c->tc5_batches = nullptr;
-    c->tc5_batch_cap = (long long) total + total / 8 + 1024;
-    NFFTCU_CUDA(pool_malloc(&c->tc5_batches, sizeof(uint2) * (size_t) c->tc5_batch_cap));
+  if ((long long) total > T.batch_cap) {
+    if (T.batches) pool_free(T.batches);
+    T.batches = nullptr;
+    T.batch_cap = (long long) total + total / 8 + 1024;
+    NFFTCU_CUDA(pool_malloc(&T.batches, sizeof(uint2) * (size_t) T.batch_cap));
   }
-  t5_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr, c->tc5_batch_start,
-                                                       (uint2 *) c->tc5_batches, units, P);
+  t5_batches_kernel<true, ALIGN, SPAN><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
+                                                                    T.batch_start, (uint2 *) T.batches, units, P);
   const unsigned ugrid = (unsigned) ((units + kb - 1) / kb);
-  t5_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(c->tc5_batch_start, c->tc5_counts, units);
-  t5_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tc5_counts, c->tc5_chunk_start, units);
+  t5_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(T.batch_start, c->tc5_counts, units);
+  t5_scan_kernel<<<1, 1024, 0, c->stream>>>(c->tc5_counts, T.chunk_start, units);
   uint32_t nchunks = 0;
-  NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, c->tc5_chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, T.chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
-  if ((long long) nchunks > c->tc5_chunk_cap) {
-    if (c->tc5_chunks) pool_free(c->tc5_chunks);
-    c->tc5_chunks = nullptr;
-    c->tc5_chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
-    NFFTCU_CUDA(pool_malloc(&c->tc5_chunks, sizeof(uint4) * (size_t) c->tc5_chunk_cap));
+  if ((long long) nchunks > T.chunk_cap) {
+    if (T.chunks) pool_free(T.chunks);
+    T.chunks = nullptr;
+    T.chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
+    NFFTCU_CUDA(pool_malloc(&T.chunks, sizeof(uint4) * (size_t) T.chunk_cap));
   }
-  t5_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(c->tc5_batch_start, c->tc5_chunk_start, (uint4 *) c->tc5_chunks, units, P.zseg);
-  c->tc5_nchunks = nchunks;
-  c->tc5_nbatches = total;
+  t5_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(T.batch_start, T.chunk_start, (uint4 *) T.chunks, units, P.zseg);
+  T.nchunks = nchunks;
+  T.nbatches = total;
   c->launches += 6;
   NFFTCU_CUDA(cudaGetLastError());
-  if (total == 0) { c->tc5_ready = true; return NFFTCU_OK; }
-  // operand images: 5 KB per batch, always resident (the kernels have no evaluating fallback; a plan whose images do not
-  // fit keeps the mma.sync kernels)
-  const size_t need = (size_t) kImgBytes * (size_t) total;
-  if (!c->tc5_images || c->tc5_images_bytes < need) {
-    if (c->tc5_images) pool_free(c->tc5_images);
-    c->tc5_images = nullptr;
-    c->tc5_images_bytes = 0;
+  if (total == 0) { *ok = true; return NFFTCU_OK; }
+  // operand images, always resident (the kernels have no evaluating fallback; a plan whose images do not fit keeps the
+  // mma.sync kernels)
+  const size_t need = (size_t) (SPREAD ? kImgBytesS : kImgBytes) * (size_t) total;
+  if (!T.images || T.images_bytes < need) {
+    if (T.images) pool_free(T.images);
+    T.images = nullptr;
+    T.images_bytes = 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if (need + need / 16 > free_b / 2 || pool_malloc(&c->tc5_images, need + need / 16) != cudaSuccess) {
+    if (need + need / 16 > free_b / 2 || pool_malloc(&T.images, need + need / 16) != cudaSuccess) {
       cudaGetLastError();
-      return NFFTCU_OK;   // tc5_ready stays false: the caller falls back to the mma.sync path
+      return NFFTCU_OK;   // *ok stays false: the caller falls back to the mma.sync path
     }
-    c->tc5_images_bytes = need + need / 16;
+    T.images_bytes = need + need / 16;
   }
-  NFFTCU_CUDA(cudaMemsetAsync(c->tc5_images, 0, need, c->stream));
+  NFFTCU_CUDA(cudaMemsetAsync(T.images, 0, need, c->stream));
   WinParams Wp;
   for (int t = 0; t < 3; t++) { Wp.b[t] = c->b[t]; Wp.ws[t] = c->wscale[t]; }
   Wp.m2 = (double) c->m * (double) c->m;
   Wp.window = c->window;
-  t5_images_kernel<<<(unsigned) nchunks, 128, 0, c->stream>>>((const float *) c->tile_x, c->tile_perm, (const uint4 *) c->tc5_chunks,
-                                                              (const uint2 *) c->tc5_batches, (unsigned char *) c->tc5_images, P, Wp);
+  t5_images_kernel<SPREAD><<<(unsigned) nchunks, 128, 0, c->stream>>>((const float *) c->tile_x, c->tile_perm, (const uint4 *) T.chunks,
+                                                                      (const uint2 *) T.batches, (unsigned char *) T.images, P, Wp);
   c->launches += 2;
   NFFTCU_CUDA(cudaGetLastError());
-  c->tc5_ready = true;
+  *ok = true;
+  return NFFTCU_OK;
+}
+
+}  // namespace
+
+int tc5_build(nfftcu_ctx *c, const MmaParams &P) {
+  c->tc5_ready = c->tc5s_ready = false;
+  NFFTCU_TRY(build_tables<false>(c, P, c->tc5i, &c->tc5_ready));
+  if (c->tc5_ready && c->opt_tc5 == 3) {
+    NFFTCU_TRY(build_tables<true>(c, P, c->tc5s, &c->tc5s_ready));
+    if (c->tc5s_ready && c->tc5_ft_cap < c->M + 18) {
+      // samples in tile order, padded: the feeder copies 18 samples from an even node index on, also for the last batch
+      if (c->tc5_ft) pool_free(c->tc5_ft);
+      c->tc5_ft = nullptr;
+      c->tc5_ft_cap = 0;
+      NFFTCU_CUDA(pool_malloc(&c->tc5_ft, sizeof(float2) * (size_t) (c->M + 18)));
+      c->tc5_ft_cap = c->M + 18;
+    }
+    if (c->tc5s_ready) NFFTCU_CUDA(cudaMemsetAsync((char *) c->tc5_ft + sizeof(float2) * (size_t) c->M, 0, sizeof(float2) * 18, c->stream));
+  }
   return NFFTCU_OK;
 }
 
 int tc5_interp(nfftcu_ctx *c, void *f_dev) {
-  if (c->tc5_nchunks == 0) return NFFTCU_OK;
+  const Tc5Tables &T = c->tc5i;
+  if (T.nchunks == 0) return NFFTCU_OK;
   const MmaParams P = mma3d_params(c);
   unsigned grid = (unsigned) c->sm_count;
-  if ((long long) grid > c->tc5_nchunks) grid = (unsigned) c->tc5_nchunks;
+  if ((long long) grid > T.nchunks) grid = (unsigned) T.nchunks;
   // the CTA owns all 512 TMEM columns of its SM: at least 120 KB of dynamic shared memory keep a second CTA off the SM,
   // which would otherwise sit in tcgen05.alloc until the first one exits
   const int kOneCtaSmem = sizeof(SmemI) > 120 * 1024 ? (int) sizeof(SmemI) : 120 * 1024;
@@ -674,10 +1007,31 @@ int tc5_interp(nfftcu_ctx *c, void *f_dev) {
   static const int dbg = getenv("NFFT_B200_TC5_DBG") ? atoi(getenv("NFFT_B200_TC5_DBG")) : 0;
   if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
   tc5_interp_kernel<<<grid, kThreadsI, kOneCtaSmem, c->stream>>>((const float2 *) c->grid, (float *) f_dev,
-                                                               (const uint4 *) c->tc5_chunks, (int) c->tc5_nchunks,
-                                                               (const uint2 *) c->tc5_batches, (const unsigned char *) c->tc5_images, P, dbg);
+                                                               (const uint4 *) T.chunks, (int) T.nchunks,
+                                                               (const uint2 *) T.batches, (const unsigned char *) T.images, P, dbg);
   if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
   c->launches++;
+  NFFTCU_CUDA(cudaGetLastError());
+  return NFFTCU_OK;
+}
+
+
+int tc5_spread(nfftcu_ctx *c, const void *f_dev) {
+  const Tc5Tables &T = c->tc5s;
+  if (T.nchunks == 0) return NFFTCU_OK;
+  const MmaParams P = mma3d_params(c);
+  const int kb = 256;
+  t5_gather_f_kernel<<<(unsigned) ((c->M + kb - 1) / kb), kb, 0, c->stream>>>((const float2 *) f_dev, c->tile_perm,
+                                                                             (float2 *) c->tc5_ft, c->M);
+  unsigned grid = (unsigned) c->sm_count;
+  if ((long long) grid > T.nchunks) grid = (unsigned) T.nchunks;
+  const int smem = sizeof(SmemS) > 120 * 1024 ? (int) sizeof(SmemS) : 120 * 1024;   // one CTA per SM (see tc5_interp)
+  NFFTCU_CUDA(cudaFuncSetAttribute(tc5_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (c->opt_timing) cudaEventRecord(c->evk[0], c->stream);
+  tc5_spread_kernel<<<grid, kThreadsS, smem, c->stream>>>((float2 *) c->grid, (const float2 *) c->tc5_ft, (const uint4 *) T.chunks,
+                                                          (int) T.nchunks, (const uint2 *) T.batches, (const unsigned char *) T.images, P);
+  if (c->opt_timing) { cudaEventRecord(c->evk[1], c->stream); c->evk_recorded = true; }
+  c->launches += 2;
   NFFTCU_CUDA(cudaGetLastError());
   return NFFTCU_OK;
 }

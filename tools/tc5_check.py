@@ -27,7 +27,7 @@ for spec in CASES:
     fh = (rng.random(NN) - 0.5 + 1j * (rng.random(NN) - 0.5)).astype(np.complex64)
     f = (rng.random(M) - 0.5 + 1j * (rng.random(M) - 0.5)).astype(np.complex64)
     res = {}
-    for tc5 in (1, 2):
+    for tc5 in (1, 3):
         eng = cabi.Engine(spec["N"], spec["n"], spec["m"], M, precision="float")
         eng.set_option(cabi.OPT_TC5, tc5)
         eng.set_option(cabi.OPT_TIMING, 1)
@@ -35,7 +35,7 @@ for spec in CASES:
         t0 = time.time()
         got_f = eng.trafo(fh)
         tb = eng.b_kernel_time()
-        if tc5 == 2 and os.environ.get("NFFT_B200_TC5_DBG") and int(os.environ["NFFT_B200_TC5_DBG"]) & 8:
+        if tc5 == 3 and os.environ.get("NFFT_B200_TC5_DBG") and int(os.environ["NFFT_B200_TC5_DBG"]) & 8:
             import ctypes
             buf = (ctypes.c_ulonglong * 32)()
             cabi.lib().nfftcu_tc5_debug(buf)
@@ -52,13 +52,13 @@ for spec in CASES:
         res[tc5] = (got_f, got_fh, tb, tbt)
         eng.close()
     line = "N=%s m=%d M=%d: trafo tc5 vs legacy %.2e, adjoint %.2e; B kernel %.3f ms (legacy %.3f), BT %.3f (legacy %.3f)" % (
-        spec["N"], spec["m"], M, rel(res[2][0], res[1][0]), rel(res[2][1], res[1][1]), res[2][2], res[1][2], res[2][3], res[1][3])
+        spec["N"], spec["m"], M, rel(res[3][0], res[1][0]), rel(res[3][1], res[1][1]), res[3][2], res[1][2], res[3][3], res[1][3])
     if M <= 400000:
         want_f = o.trafo(spec["N"], spec["n"], spec["m"], x, fh)
         want_fh = o.adjoint(spec["N"], spec["n"], spec["m"], x, f, True)
         line += "; vs oracle: trafo %.2e (legacy %.2e) adjoint %.2e (legacy %.2e)" % (
-            rel(res[2][0], want_f), rel(res[1][0], want_f), rel(res[2][1], want_fh), rel(res[1][1], want_fh))
+            rel(res[3][0], want_f), rel(res[1][0], want_f), rel(res[3][1], want_fh), rel(res[1][1], want_fh))
     print(line, flush=True)
-    bad = np.flatnonzero(~np.isfinite(res[2][0]))
+    bad = np.flatnonzero(~np.isfinite(res[3][0]))
     if bad.size:
         print("  non-finite entries:", bad.size, bad[:10])
