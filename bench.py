@@ -529,7 +529,7 @@ def run_ours(args, rank, world, local_rank):
         taps = (2 * cfg["m"] + 2) ** cfg["d"]
         flops = 4.0 * taps * M_local      # per tap: complex value x real weight = 2 FMA = 4 flops
         kname = (("spread_mma_kernel (B^T)" if spread_dom else "interp_mma_kernel (B)") if dmma else
-                 ("spread_tf32_kernel (B^T)" if spread_dom else "tc5_interp_kernel (B)") if tf32 else
+                 ("tc5_spread_kernel (B^T)" if spread_dom else "tc5_interp_kernel (B)") if tf32 else
                  ("spread (B^T)" if spread_dom else "interp (B)"))
         roof = {"bound": "hbm", "kernel": kname, "achieved": hbm_ach, "peak": peak, "unit": "GB/s",
                 "frac": (hbm_ach / peak) if hbm_ach else None, "traffic": traffic,
@@ -551,8 +551,12 @@ def run_ours(args, rank, world, local_rank):
             else:
                 roof["tf32_pipe"] = {
                     "achieved": 3 * tf, "peak": tf32_now, "unit": "TFLOP/s", "frac": 3 * tf / tf32_now,
-                    "peak_source": "mma.sync m16n8k8 TF32 rate measured in this process (nfftcu_measure_peaks)",
-                    "note": "3xTF32 split: three tensor flops per useful flop counted (useful %.2f TFLOP/s)" % tf}
+                    "peak_source": "mma.sync m16n8k8 TF32 rate measured in this process (nfftcu_measure_peaks); the kernels "
+                                   "themselves issue tcgen05.mma kind::tf32 (M=128, N=16/32, K=8: 17 / 23 cycles each with A in "
+                                   "tensor memory, profiles/r2l_microbench_tcgen05.txt)",
+                    "note": "3xTF32 split: three tensor flops per useful flop counted (useful %.2f TFLOP/s); the tensor pipe is "
+                            "~20 %% active (profiles/r2r_full_tc5_fp32.md): the kernels are bound by the hand-offs between their "
+                            "warp roles, see DESIGN 4.1d" % tf}
         pipe_ach = bm["pair"] / (ms_step * 1e-3) / 1e9
         line = {
             "metric": metric_name(cfg, prec), "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
@@ -561,15 +565,18 @@ def run_ours(args, rank, world, local_rank):
             "config": workload_config(cfg, world, scaling),
             "rel_l2": rel,
             "implementation": {
-                "window": ("plan-time window images (3 KB per 8-node batch, %.2f GB, built in set_nodes like "
-                           "precompute_psi, streamed by TMA every launch)" % (eng_images_gb(M_local))
-                           if (dmma or tf32) else ("psi table" if args.psi_table else "psi on the fly")),
+                "window": (("plan-time operand images (5.2 KB per 16-node batch for B, 6.2 KB for B^T, %.2f GB together, built in "
+                            "set_nodes like precompute_psi, streamed by TMA every launch)" % (M_local / 15.1 * (5248 + 6272) / 1e9))
+                           if tf32 else
+                           ("plan-time window images (3 KB per 8-node batch, %.2f GB, built in set_nodes like "
+                            "precompute_psi, streamed by TMA every launch)" % (eng_images_gb(M_local)))
+                           if dmma else ("psi table" if args.psi_table else "psi on the fly")),
                 "multi_gpu": ("node-sharded x%d: trafo replicates f_hat and the grid; adjoint reduces f_hat (%s, "
                               "%.3f ms per D^T + reduction measured alone)" % (world, sp_reduce_name(reduce_mode), collective_ms)
                               if world > 1 else "single GPU"),
                 "nodes_setup_s": t_nodes,
-                **({"fp32_kernels": "B: tcgen05.mma kind::tf32, grid window and accumulators in tensor memory (tc5.cu, 5 KB operand "
-                                    "image per 16-node batch); B^T: 3xTF32 mma.sync (mma3d.cu)"} if tf32 else {})},
+                **({"fp32_kernels": "B and B^T: tcgen05.mma kind::tf32 (3xTF32 split), grid window / accumulators in tensor memory, "
+                                    "operand images by TMA (tc5.cu)"} if tf32 else {})},
             "stage_ms": {"trafo": {"D": stage[0][0], "F": stage[0][1], "B": stage[0][2]},
                          "adjoint": {"DT": stage[1][0], "F": stage[1][1], "BT": stage[1][2]},
                          "ms_per_step_with_timers": ms_step_timers},

@@ -61,7 +61,7 @@ typedef struct nfftcu_ctx_s nfftcu_ctx;
 #define NFFTCU_OPT_FFT_KERNEL 7    /* 0 auto (register-resident Stockham for 2^k lengths 64..2048) | 1 shared-memory Stockham only */
 #define NFFTCU_OPT_WINDOW_IMAGES 8 /* 3-D tensor kernels: per-batch window images built with the node set and fed by TMA: 0 auto (when they fit) | 1 off | 2 on */
 #define NFFTCU_OPT_SLAB_FFT 9      /* 0 auto: when the nodes occupy a slab of the first axis (a rank of a node-sharded run), the pruned FFT passes and the B^T memset touch only the slab's planes | 1 off */
-#define NFFTCU_OPT_TC5 10          /* fp32 plans, d = 3, m <= 6: B / B^T on tcgen05.mma kind::tf32 with the grid window and the accumulators in tensor memory (tc5.cu): 0 auto | 1 off (mma.sync TF32 kernels) | 2 on */
+#define NFFTCU_OPT_TC5 10          /* fp32 plans, d = 3, m <= 6: B / B^T on tcgen05.mma kind::tf32 with the grid window and the accumulators in tensor memory (tc5.cu): 0 auto (both) | 1 off (mma.sync TF32 kernels) | 2 B only | 3 B and B^T */
 #define NFFTCU_OPT_NODE_ORDER 4    /* 0 auto | 1 reference row-major key | 2 tile-binned */
 
 const char *nfftcu_last_error(void);

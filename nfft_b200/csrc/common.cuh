@@ -158,7 +158,7 @@ struct nfftcu_ctx_s {
   long long tc5_counts_units = 0;
   bool tc5_ready = false;           // tc5i is valid for the current nodes: B runs on tc5_interp_kernel
   bool tc5s_ready = false;          // tc5s is valid: B^T runs on tc5_spread_kernel
-  int opt_tc5 = 0;                  // NFFTCU_OPT_TC5: 0 auto (fp32, d = 3, m <= 6) | 1 off | 2 B only | 3 B and B^T
+  int opt_tc5 = 0;                  // NFFTCU_OPT_TC5: 0 auto (fp32, d = 3, m <= 6: B and B^T) | 1 off | 2 B only | 3 B and B^T
   bool ref_sorted = false;          // keys_ref / perm / x_sorted are valid for the current nodes
   void *tile_keys = nullptr;        // uint64 bin ids, sorted
   uint32_t *tile_perm = nullptr;    // tile order -> original node index

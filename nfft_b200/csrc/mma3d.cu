@@ -1357,78 +1357,82 @@ int mma3d_bin_nodes(nfftcu_ctx *c) {
   mma_unit_bounds_kernel<<<(unsigned) ((units + 1 + kb - 1) / kb), kb, 0, c->stream>>>(
       (const uint64_t *) c->tile_keys, c->bin_start, units, M, P);
   c->launches++;
-  // batch table: count per unit, scan, fill
-  if (c->mma_units != units) {
-    if (c->mma_batch_start) pool_free(c->mma_batch_start);
-    if (c->mma_counts) pool_free(c->mma_counts);
-    if (c->mma_chunk_start) pool_free(c->mma_chunk_start);
-    c->mma_batch_start = c->mma_counts = c->mma_chunk_start = nullptr;
-    NFFTCU_CUDA(pool_malloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
-    NFFTCU_CUDA(pool_malloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
-    c->mma_units = units;
-  }
-  const unsigned wgrid = (unsigned) ((units * 32 + kb - 1) / kb);
-  mma_batches_kernel<false><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, c->mma_counts,
-                                                         nullptr, nullptr, units, P);
-  mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_batch_start, units);
-  uint32_t total = 0;
-  NFFTCU_CUDA(cudaMemcpyAsync(&total, c->mma_batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
-  if ((long long) total > c->mma_batch_cap) {
-    if (c->mma_batches) pool_free(c->mma_batches);
-    c->mma_batches = nullptr;
-    c->mma_batch_cap = (long long) total + total / 8 + 1024;
-    NFFTCU_CUDA(pool_malloc(&c->mma_batches, sizeof(uint2) * (size_t) c->mma_batch_cap));
-  }
-  mma_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
-                                                        c->mma_batch_start, (uint2 *) c->mma_batches, units, P);
-  // chunks: count per unit (reusing the counts scratch), scan, fill
-  if (!c->mma_chunk_start) NFFTCU_CUDA(pool_malloc((void **) &c->mma_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
-  const unsigned ugrid = (unsigned) ((units + kb - 1) / kb);
-  mma_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_counts, units);
-  mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_chunk_start, units);
-  uint32_t nchunks = 0;
-  NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, c->mma_chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
-  if ((long long) nchunks > c->mma_chunk_cap) {
-    if (c->mma_chunks) pool_free(c->mma_chunks);
-    c->mma_chunks = nullptr;
-    c->mma_chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
-    NFFTCU_CUDA(pool_malloc(&c->mma_chunks, sizeof(uint4) * (size_t) c->mma_chunk_cap));
-  }
-  mma_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_chunk_start, (uint4 *) c->mma_chunks, units,
-                                                    P.zseg);
-  c->mma_nchunks = nchunks;
-  c->launches += 6;
-  NFFTCU_CUDA(cudaGetLastError());
-  // window images: on when they fit (NFFTCU_OPT_WINDOW_IMAGES: 0 auto | 1 off | 2 on regardless of the budget)
+  // fp32 plans: the tcgen05 kernels take over when their tables and images could be built (tc5.cu); the tables and
+  // window images of this file are then only built for the direction that stays here
+  c->tc5_ready = c->tc5s_ready = false;
+  if (tc5_selected(c)) NFFTCU_TRY(tc5_build(c, P));
   c->mma_images_ready = false;
-  if (c->opt_window_images != 1 && total > 0) {
-    const size_t need = sizeof(double) * kImgDoubles * (size_t) total;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    const bool have = c->mma_images && c->mma_images_bytes >= need;
-    const bool fits = have || c->opt_window_images == 2 || (need <= free_b / 2 && need <= ((size_t) 48 << 30));
-    if (fits) {
-      if (!have) {
-        if (c->mma_images) pool_free(c->mma_images);
-        c->mma_images = nullptr;
-        c->mma_images_bytes = 0;
-        if (pool_malloc(&c->mma_images, need + need / 16) == cudaSuccess) c->mma_images_bytes = need + need / 16;
-        else cudaGetLastError();   // no room after all: keep the evaluating producers
-      }
-      if (c->mma_images) {
-        MmaParams Pi = P;
-        Pi.img = nullptr;
-        NFFTCU_TRY(c->prec == NFFTCU_DOUBLE ? build_images<double>(c, Pi, total) : build_images<float>(c, Pi, total));
-        c->mma_images_tf32 = c->prec == NFFTCU_FLOAT && c->opt_b_kernel != 3;
-        c->mma_images_ready = true;
+  if (!(c->tc5_ready && c->tc5s_ready)) {
+    // batch table: count per unit, scan, fill
+    if (c->mma_units != units) {
+      if (c->mma_batch_start) pool_free(c->mma_batch_start);
+      if (c->mma_counts) pool_free(c->mma_counts);
+      if (c->mma_chunk_start) pool_free(c->mma_chunk_start);
+      c->mma_batch_start = c->mma_counts = c->mma_chunk_start = nullptr;
+      NFFTCU_CUDA(pool_malloc((void **) &c->mma_batch_start, sizeof(uint32_t) * (size_t) (units + 1)));
+      NFFTCU_CUDA(pool_malloc((void **) &c->mma_counts, sizeof(uint32_t) * (size_t) units));
+      c->mma_units = units;
+    }
+    const unsigned wgrid = (unsigned) ((units * 32 + kb - 1) / kb);
+    mma_batches_kernel<false><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, c->mma_counts,
+                                                           nullptr, nullptr, units, P);
+    mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_batch_start, units);
+    uint32_t total = 0;
+    NFFTCU_CUDA(cudaMemcpyAsync(&total, c->mma_batch_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+    if ((long long) total > c->mma_batch_cap) {
+      if (c->mma_batches) pool_free(c->mma_batches);
+      c->mma_batches = nullptr;
+      c->mma_batch_cap = (long long) total + total / 8 + 1024;
+      NFFTCU_CUDA(pool_malloc(&c->mma_batches, sizeof(uint2) * (size_t) c->mma_batch_cap));
+    }
+    mma_batches_kernel<true><<<wgrid, kb, 0, c->stream>>>((const uint64_t *) c->tile_keys, c->bin_start, nullptr,
+                                                          c->mma_batch_start, (uint2 *) c->mma_batches, units, P);
+    // chunks: count per unit (reusing the counts scratch), scan, fill
+    if (!c->mma_chunk_start) NFFTCU_CUDA(pool_malloc((void **) &c->mma_chunk_start, sizeof(uint32_t) * (size_t) (units + 1)));
+    const unsigned ugrid = (unsigned) ((units + kb - 1) / kb);
+    mma_chunk_count_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_counts, units);
+    mma_scan_kernel<<<1, 1024, 0, c->stream>>>(c->mma_counts, c->mma_chunk_start, units);
+    uint32_t nchunks = 0;
+    NFFTCU_CUDA(cudaMemcpyAsync(&nchunks, c->mma_chunk_start + units, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    NFFTCU_CUDA(cudaStreamSynchronize(c->stream));
+    if ((long long) nchunks > c->mma_chunk_cap) {
+      if (c->mma_chunks) pool_free(c->mma_chunks);
+      c->mma_chunks = nullptr;
+      c->mma_chunk_cap = (long long) nchunks + nchunks / 8 + 1024;
+      NFFTCU_CUDA(pool_malloc(&c->mma_chunks, sizeof(uint4) * (size_t) c->mma_chunk_cap));
+    }
+    mma_chunk_fill_kernel<<<ugrid, kb, 0, c->stream>>>(c->mma_batch_start, c->mma_chunk_start, (uint4 *) c->mma_chunks, units,
+                                                      P.zseg);
+    c->mma_nchunks = nchunks;
+    c->launches += 6;
+    NFFTCU_CUDA(cudaGetLastError());
+    // window images: on when they fit (NFFTCU_OPT_WINDOW_IMAGES: 0 auto | 1 off | 2 on regardless of the budget)
+    c->mma_images_ready = false;
+    if (c->opt_window_images != 1 && total > 0) {
+      const size_t need = sizeof(double) * kImgDoubles * (size_t) total;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const bool have = c->mma_images && c->mma_images_bytes >= need;
+      const bool fits = have || c->opt_window_images == 2 || (need <= free_b / 2 && need <= ((size_t) 48 << 30));
+      if (fits) {
+        if (!have) {
+          if (c->mma_images) pool_free(c->mma_images);
+          c->mma_images = nullptr;
+          c->mma_images_bytes = 0;
+          if (pool_malloc(&c->mma_images, need + need / 16) == cudaSuccess) c->mma_images_bytes = need + need / 16;
+          else cudaGetLastError();   // no room after all: keep the evaluating producers
+        }
+        if (c->mma_images) {
+          MmaParams Pi = P;
+          Pi.img = nullptr;
+          NFFTCU_TRY(c->prec == NFFTCU_DOUBLE ? build_images<double>(c, Pi, total) : build_images<float>(c, Pi, total));
+          c->mma_images_tf32 = c->prec == NFFTCU_FLOAT && c->opt_b_kernel != 3;
+          c->mma_images_ready = true;
+        }
       }
     }
   }
-  // fp32 plans: the tcgen05 kernels take over when their tables and images could be built (tc5.cu)
-  c->tc5_ready = c->tc5s_ready = false;
-  if (tc5_selected(c)) NFFTCU_TRY(tc5_build(c, P));
   c->mma_ready = true;
   return NFFTCU_OK;
 }

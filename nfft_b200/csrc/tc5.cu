@@ -883,7 +883,7 @@ tc5_spread_kernel(float2 *__restrict__ G, const float2 *__restrict__ ft, const u
 
 }  // namespace
 
-// NFFTCU_OPT_TC5: 0 auto (B on tc5_interp_kernel) | 1 off | 2 B only | 3 B and B^T
+// NFFTCU_OPT_TC5: 0 auto (B and B^T on the tcgen05 kernels) | 1 off | 2 B only | 3 B and B^T
 bool tc5_selected(const nfftcu_ctx *c) {
   if (c->prec != NFFTCU_FLOAT || c->opt_tc5 == 1 || !mma3d_supported(c)) return false;
   if (!(c->opt_b_kernel == 0)) return false;   // an explicit kernel choice (generic / pencils / DMMA) wins
@@ -979,7 +979,7 @@ int build_tables(nfftcu_ctx *c, const MmaParams &P, Tc5Tables &T, bool *ok) {
 int tc5_build(nfftcu_ctx *c, const MmaParams &P) {
   c->tc5_ready = c->tc5s_ready = false;
   NFFTCU_TRY(build_tables<false>(c, P, c->tc5i, &c->tc5_ready));
-  if (c->tc5_ready && c->opt_tc5 == 3) {
+  if (c->tc5_ready && c->opt_tc5 != 2) {
     NFFTCU_TRY(build_tables<true>(c, P, c->tc5s, &c->tc5s_ready));
     if (c->tc5s_ready && c->tc5_ft_cap < c->M + 18) {
       // samples in tile order, padded: the feeder copies 18 samples from an even node index on, also for the last batch

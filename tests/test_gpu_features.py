@@ -372,9 +372,9 @@ TC5_CASES = {
 
 @pytest.mark.parametrize("case", sorted(TC5_CASES))
 def test_tc5_fp32_kernels_vs_oracle_and_mma_sync(case):
-    """fp32 3-D plans, m <= 6: interpolation on tcgen05.mma kind::tf32 with the grid window and the accumulators in tensor
-    memory (tc5.cu) -- against the oracle, against the mma.sync TF32 kernels (NFFTCU_OPT_TC5 = 1) on the same plan
-    geometry, twice in a row (the persistent CTAs keep no state between launches), and as a batched transform."""
+    """fp32 3-D plans, m <= 6: interpolation and spreading on tcgen05.mma kind::tf32 with the grid window / the accumulators
+    in tensor memory (tc5.cu) -- against the oracle, against the mma.sync TF32 kernels (NFFTCU_OPT_TC5 = 1) on the same
+    plan geometry, twice in a row (the persistent CTAs keep no state between launches), and as batched transforms."""
     spec = TC5_CASES[case]
     rng = np.random.default_rng(23)
     M, NN = spec["M"], int(np.prod(spec["N"]))
@@ -389,7 +389,7 @@ def test_tc5_fp32_kernels_vs_oracle_and_mma_sync(case):
     want_f = o.trafo(spec["N"], spec["n"], spec["m"], x, fh)
     want_fh = o.adjoint(spec["N"], spec["n"], spec["m"], x, f, True)
     got = {}
-    for tc5 in (1, 2):
+    for tc5 in (1, 2, 3):   # mma.sync kernels | B on tcgen05 | B and B^T on tcgen05 (the default)
         eng = cabi.Engine(spec["N"], spec["n"], spec["m"], M, precision="float")
         eng.set_option(cabi.OPT_TC5, tc5)
         eng.set_nodes(x)
@@ -397,11 +397,13 @@ def test_tc5_fp32_kernels_vs_oracle_and_mma_sync(case):
         b = eng.trafo(fh)
         fb = eng.trafo_batch(np.stack([fh, -2 * fh]))
         got[tc5] = (a, eng.adjoint(f))
+        fhb = eng.adjoint_batch(np.stack([f, 3 * f]))
         eng.close()
         assert np.array_equal(a, b)
         # the adjoint of the clustered case adds 3e4 fp32 samples into a few cells: two fp32 summation orders (ours, the
         # oracle's) differ by more than the 1e-5 bar there -- with either kernel family
         tol_adj = 4e-5 if spec.get("cluster") else TOL["float"]
         assert rel_l2(a, want_f) <= TOL["float"] and rel_l2(got[tc5][1], want_fh) <= tol_adj
-        assert rel_l2(fb[1], -2 * want_f) <= TOL["float"]
-    assert rel_l2(got[2][0], got[1][0]) <= 2e-6 and rel_l2(got[2][1], got[1][1]) <= 2e-6
+        assert rel_l2(fb[1], -2 * want_f) <= TOL["float"] and rel_l2(fhb[1], 3 * want_fh) <= tol_adj
+    for tc5 in (2, 3):   # the two kernel families against each other (clustered adjoint: fp32 summation order, see above)
+        assert rel_l2(got[tc5][0], got[1][0]) <= 2e-6 and rel_l2(got[tc5][1], got[1][1]) <= (tol_adj if spec.get("cluster") else 2e-6)
