@@ -9,7 +9,7 @@
 // Why not the register-window mma.sync kernels of mma3d.cu.  Those keep the sliding grid window in registers because
 // mma.sync takes its operands from registers; on the fp32 path they are issue-bound (2550 warp instructions per 8-node
 // batch).  tcgen05.mma takes A from TMEM: the window of a tile -- 512 rows (256 pencils x re / im) by a ring
-// of 32 z-slots, as a (hi, lo) pair -- lives in 256 TMEM columns for the whole sweep, is refilled 8 cells at a time with
+// of 40 z-slots, as a (hi, lo) pair -- lives in 320 TMEM columns for the whole sweep, is refilled 8 cells at a time with
 // tcgen05.st, and ONE thread issues the contraction.  Measured on B200 (profiles/r2l_microbench_tcgen05.txt): an
 // M = 128, N = 16, K = 8 kind::tf32 MMA with A in TMEM retires every 17 cycles (A in shared memory: 78).
 //
@@ -17,24 +17,27 @@
 //                   f_node       = sum_row (psi0[l0] psi1[l1])[node] T[row, node]           (epilogue, FFMA + shuffles)
 //   spreading       G[row, z]   += sum_node (psi0 psi1 f)[row, node] psi2[node, z]            (accumulators = the window)
 //
-// Batches.  Nodes are in the (tile, u2) order of mma3d.cu.  A batch = up to 16 consecutive nodes of a tile whose taps
-// lie in the 24 cells [base, base + 24), base = 8 floor(u2_first / 8): three k-steps of 8 slots, each starting at an
-// 8-slot boundary of the ring (slot = z mod 32), so the k-steps never wrap and the A operand address is just a column
-// offset.  psi2 is zero outside a node's taps, so whatever else the 24 slots hold only has to be finite.
+// Batches.  Nodes are in the (tile, u2) order of mma3d.cu.  An interpolation batch = up to 16 consecutive nodes of a tile
+// whose taps lie in the 24 cells [base, base + 24), base = 8 floor(u2_first / 8): three k-steps of 8 slots, each starting
+// at an 8-slot boundary of the ring (slot = z mod 40), so the k-steps never wrap and the A operand address is just a
+// column offset.  psi2 is zero outside a node's taps, so whatever else the 24 slots hold only has to be finite.  (The
+// spreading batches are cut with a 16-aligned base and 32 slots: see tc5_spread_kernel.)
 //
-// Per batch the plan-time IMAGE (5 KB, like the reference's PRE_PSI table) holds psi2 as the (hi, lo) B operand in the
-// canonical K-major no-swizzle layout and psi0 / psi1 placed in the footprint; a feeder lane streams it into a
-// shared-memory ring by TMA (cp.async.bulk + mbarrier expect_tx).
+// Per batch the plan-time IMAGE (5.2 KB, like the reference's PRE_PSI table) holds psi2 as the (hi, lo) B operand in the
+// canonical K-major no-swizzle layout, psi0 / psi1 placed in the footprint, the batch entry and the output indices of
+// its nodes; a feeder lane streams it into a shared-memory ring by TMA (cp.async.bulk + mbarrier expect_tx).
 //
-// CTA = 10 warps, persistent over the chunk list, one CTA per SM (it owns all 512 TMEM columns):
-//   warps 0-3  epilogue: tcgen05.ld of the batch's T (lane quarter q = warp), row weights, 32-value butterfly reduction,
-//              f[perm[node]] stored by one warp per batch
-//   warps 4-7  window refill: 8 cells x 2 pencils per thread from L2, split into tf32 (hi, lo), tcgen05.st
-//   warp  8    MMA issue (one elected lane): 3 k-steps x 3 split terms x 4 row blocks = 36 tcgen05.mma + 1 commit
-//   warp  9    TMA feeder of the operand images
-// Hand-offs are mbarriers only: op_full / op_empty (image ring), a_ready (window covers the batch), acc_full (commit:
-// T is complete) / acc_empty (T was read).  The refill warps run up to three batches ahead; a slot is only overwritten
-// once every batch that still reads its old cell has committed (bases at least 16 cells behind).
+// tc5_interp_kernel: CTA = 14 warps, persistent over the chunk list, one CTA per SM (it owns all 512 TMEM columns):
+//   warps 0-7   two epilogue groups (a group takes every second batch): tcgen05.ld of the batch's T (lane quarter
+//               q = warp mod 4), row weights, 32-value butterfly reduction, f[perm[node]] stored by one warp per batch
+//   warps 8-11  window refill: 8 cells x 2 pencils per thread from L2 (loaded one slide ahead), split into tf32
+//               (hi, lo), tcgen05.st
+//   warp  12    MMA issue (one elected lane): 3 k-steps x 3 split terms x 4 row blocks = 36 tcgen05.mma + 1 commit
+//   warp  13    TMA feeder of the operand images
+// Hand-offs: op_full / op_empty (image ring), a_ready (one phase per slide of 8 cells), acc_full (commit: T is complete)
+// / acc_empty (T was read) are mbarriers; done_upto (shared-memory counter, written by the epilogue) tells the refill
+// warps which batches have committed: a slot is only overwritten once every batch that still reads its old cell has
+// (with 40 slots for a 24-slot span: bases at least 24 cells behind).
 #include <stdlib.h>
 
 #include "common.cuh"

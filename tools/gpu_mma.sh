@@ -8,5 +8,5 @@ for ln in sys.stdin:
     if ln.startswith('{'):
         d=json.loads(ln); s=d['stage_ms']; print('$1 value %.3e ms %.2f B %.2f BT %.2f e2e %.1f ms'%(d['value'],d['ms_per_step'],s['trafo']['B'],s['adjoint']['BT'],d['e2e']['ms_per_step']))
     else: print(ln.rstrip()[:300])"; }
-timeout 90 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | tee $OUT/bench.log | summ mma
-timeout 90 python bench.py --steps 10 --warmup 3 --no-cpu --b-flush 2 2>&1 | tee $OUT/bench_tma.log | summ mma-tma
+timeout 90 python bench.py --steps 10 --warmup 3 --no-check 2>&1 | tee $OUT/bench.log | summ mma
+timeout 90 python bench.py --steps 10 --warmup 3 --no-check --b-flush 2 2>&1 | tee $OUT/bench_tma.log | summ mma-tma

@@ -10,11 +10,11 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tee $OUT/pytest_gpu.log | tail -15
 echo "== microbench"; timeout 120 ./tools/microbench 2>&1 | tee $OUT/microbench.log
 echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tee $OUT/bench.log | tail -3
-echo "== bench fp32"; timeout 600 python bench.py --steps 5 --warmup 3 --precision float --no-cpu 2>&1 | tee $OUT/bench_f32.log | tail -2
+echo "== bench fp32"; timeout 600 python bench.py --steps 5 --warmup 3 --precision float --no-check 2>&1 | tee $OUT/bench_f32.log | tail -2
 echo "== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-check > $OUT/ncu_launches.log 2>&1
 echo "== ncu full (spread+interp, M=1e6)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"spread_generic|interp_generic" -c 2 \
-    -o $OUT/prof_B python bench.py --steps 1 --warmup 3 --no-cpu --nodes 1000000 > $OUT/ncu_full.log 2>&1
+    -o $OUT/prof_B python bench.py --steps 1 --warmup 3 --no-check --nodes 1000000 > $OUT/ncu_full.log 2>&1
 ls -la $OUT

@@ -4,7 +4,7 @@ TAG=$1; shift; OUT=gpurun_out/$TAG; mkdir -p $OUT
 cp nfft_b200/lib/libnfftcu.so /tmp/libnfftcu_base.so
 for v in base "$@"; do
   if [ $v = base ]; then cp /tmp/libnfftcu_base.so nfft_b200/lib/libnfftcu.so; else cp nfft_b200/lib_var/$v/libnfftcu.so nfft_b200/lib/libnfftcu.so; fi
-  timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu $BENCH_ARGS 2>&1 | tee $OUT/bench_$v.log | python -c "
+  timeout 120 python bench.py --steps 10 --warmup 3 --no-check $BENCH_ARGS 2>&1 | tee $OUT/bench_$v.log | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):
