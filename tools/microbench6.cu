@@ -225,6 +225,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// kind::i8 (signed 8-bit operands, s32 accumulate, K = 32 per MMA = the same 32 bytes per row and k-step as kind::tf32):
+// rate only -- the gate for an Ozaki-style fp64 emulation on the integer tensor path
+__device__ __forceinline__ uint32_t make_idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)) : "memory");
 }
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(128) k_correct_ts(const float *A, const float 
 
 // rate, A from TMEM: groups of 36 MMAs (4 row blocks x 3 k-steps x 3 terms) like one batch of tc5.cu; TMEM columns
 // [0, 4 NN) D, [256, 512) A (4 row blocks x (hi, lo) x 32 slots)
-template <int NN, int ORDER>
+template <int NN, int ORDER, int KIND = 0>
 __global__ void __launch_bounds__(128) k_rate_ts(int reps, long long *cyc, int *status) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ uint64_t bar[4];
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(128) k_rate_ts(int reps, long long *cyc, int *
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   bool ok = true;
   if (warp == 0) {   // the whole warp runs the loop (uniform operands); one elected lane issues
-    const uint32_t idesc = make_idesc(128, NN);
+    const uint32_t idesc = KIND ? make_idesc_i8(128, NN) : make_idesc(128, NN);
     const uint64_t b0 = make_desc(smem_u32(sm), kBChunk * (NN / 16), kBGroup);
     const long long t0 = clock64();
     for (int r = 0; r < reps; r++) {
@@ -354,7 +364,8 @@ __global__ void __launch_bounds__(128) k_rate_ts(int reps, long long *cyc, int *
 #pragma unroll
             for (int mb = 0; mb < 4; mb++) {
               const uint32_t a_hi = tb + 256 + mb * 64 + kb, a_lo = a_hi + 32, d = tb + mb * NN;
-              mma_tf32_ts(d, term == 0 ? a_lo : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
+              if (KIND) mma_i8_ts(d, term == 0 ? a_lo : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
+              else mma_tf32_ts(d, term == 0 ? a_lo : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
             }
         }
       }
@@ -471,6 +482,11 @@ int main() {
     printf("rate A-from-TMEM M=128 N=%d order=%d: %.1f cycles per MMA executed, %.1f issued (36 per batch), status %d\n", NN, ORD, \
            (double) cyc[0] / (36.0 * 2000), (double) cyc[1] / (36.0 * 2000), *status); } while (0)
   RATE_TS(16, 0); RATE_TS(16, 1); RATE_TS(32, 0); RATE_TS(32, 1); RATE_TS(64, 0); RATE_TS(64, 1);
+#define RATE_I8(NN) do { \
+    CK(cudaFuncSetAttribute(k_rate_ts<NN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384)); \
+    for (int pass = 0; pass < 2; pass++) { k_rate_ts<NN, 1, 1><<<1, 128, 16384>>>(2000, cyc, status); CK(cudaDeviceSynchronize()); } \
+    printf("rate kind::i8 A-from-TMEM M=128 N=%d K=32: %.1f cycles per MMA, status %d\n", NN, (double) cyc[0] / (36.0 * 2000), *status); } while (0)
+  RATE_I8(16); RATE_I8(32); RATE_I8(64);
   const size_t smem_rate = 65536 + 8192;
   CK(cudaFuncSetAttribute(k_rate<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_rate));
   CK(cudaFuncSetAttribute(k_rate<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_rate));
