@@ -65,6 +65,9 @@ typedef struct nfftcu_ctx_s nfftcu_ctx;
 #define NFFTCU_OPT_NODE_ORDER 4    /* 0 auto | 1 reference row-major key | 2 tile-binned */
 
 const char *nfftcu_last_error(void);
+
+/* debugging aid of the tcgen05 kernels (tc5.cu): 32 cycle totals of the timing probes (env NFFT_B200_TC5_DBG & 8), cleared on read */
+int nfftcu_tc5_debug(unsigned long long *out32);
 int nfftcu_device_count(void);
 
 /* ---- plan life cycle --------------------------------------------------------------------
