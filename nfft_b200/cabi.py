@@ -35,7 +35,7 @@ SYMBOLS = (
     "nfftcu_free_pinned", "nfftcu_memcpy_h2d", "nfftcu_memcpy_d2h",
     "nfftcu_solver_create", "nfftcu_solver_create_batch", "nfftcu_solver_destroy", "nfftcu_solver_upload", "nfftcu_solver_download",
     "nfftcu_solver_vector", "nfftcu_solver_before_loop", "nfftcu_solver_step",
-    "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim", "nfftcu_fingerprint",
+    "nfftcu_tc5_debug", "nfftcu_measure_peaks", "nfftcu_host_alloc", "nfftcu_host_free", "nfftcu_pool_trim", "nfftcu_fingerprint",
     "nfftcu_trafo_batch", "nfftcu_adjoint_batch", "nfftcu_trafo_batch_dev", "nfftcu_adjoint_batch_dev",
     "nfftcu_mri_inh_2d1d", "nfftcu_mri_inh_3d", "nfftcu_adjoint_mul_trafo",
     "nfftcu_get_sorted_slab", "nfftcu_peer_export", "nfftcu_peer_attach", "nfftcu_peer_detach",
