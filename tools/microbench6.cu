@@ -383,6 +383,69 @@ __global__ void __launch_bounds__(128) k_rate_ts(int reps, long long *cyc, int *
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tb), "r"(512));
 }
 
+
+// issue rate with NW issuing warps (each its own accumulators and commit barriers, the same A ring): does a second issuing
+// thread raise the ~16-cycle cadence of one thread's tcgen05.mma stream?
+template <int NN, int NW>
+__global__ void __launch_bounds__(128) k_rate_multi(int reps, long long *cyc, int *status) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ uint64_t bar[4][4];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384 / 4; i += 128) reinterpret_cast<float *>(sm)[i] = 1.0f + 1e-3f * (i & 63);
+  if (tid == 0) { for (int w = 0; w < 4; w++) for (int i = 0; i < 4; i++) mbar_init(&bar[w][i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base;
+  const uint32_t lane_base = (uint32_t) (warp * 32) << 16;
+  for (int c = 0; c < 256; c += 2) tmem_st2(tb + lane_base + 256 + c, 1.0f + 1e-3f * c, 0.5f);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  bool ok = true;
+  const long long t0 = clock64();
+  if (warp < NW) {
+    const uint32_t idesc = make_idesc(128, NN);
+    const uint64_t b0 = make_desc(smem_u32(sm), kBChunk * (NN / 16), kBGroup);
+    constexpr uint32_t kLo = (6 * kBChunk * (NN / 16)) >> 4;
+    for (int r = 0; r < reps; r++) {
+      if (r >= 4) ok = ok && mbar_wait_bounded(&bar[warp][r & 3], ((r >> 2) - 1) & 1);
+      const uint32_t kb0 = (uint32_t) (8 * r) & 31;
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const uint32_t kb = (kb0 + 8 * i) & 31;
+          const uint64_t bh = b0 + (uint64_t) ((2 * i * kBChunk * (NN / 16)) >> 4);
+          const uint64_t bl = bh + kLo;
+#pragma unroll
+          for (int term = 0; term < 3; term++)
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) {
+              const uint32_t a_hi = tb + 256 + mb * 64 + kb, a_lo = a_hi + 32, d = tb + warp * 4 * NN + mb * NN;
+              mma_tf32_ts(d, term == 0 ? a_lo : a_hi, term == 1 ? bl : bh, idesc, (i | term) ? 1u : 0u);
+            }
+        }
+        mma_commit(&bar[warp][r & 3]);
+      }
+      __syncwarp();
+    }
+    for (int r = reps - 4; r < reps; r++) ok = ok && mbar_wait_bounded(&bar[warp][r & 3], (r >> 2) & 1);
+  }
+  __syncthreads();
+  if (tid == 0) { cyc[0] = clock64() - t0; }
+  if (!ok) *status = 3;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tb), "r"(512));
+}
+
 static float tf32_trunc_host(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; memcpy(&x, &u, 4); return x; }
 
 int main() {
@@ -487,6 +550,12 @@ int main() {
     for (int pass = 0; pass < 2; pass++) { k_rate_ts<NN, 1, 1><<<1, 128, 16384>>>(2000, cyc, status); CK(cudaDeviceSynchronize()); } \
     printf("rate kind::i8 A-from-TMEM M=128 N=%d K=32: %.1f cycles per MMA, status %d\n", NN, (double) cyc[0] / (36.0 * 2000), *status); } while (0)
   RATE_I8(16); RATE_I8(32); RATE_I8(64);
+#define RATE_MULTI(NN, NW) do { \
+    CK(cudaFuncSetAttribute(k_rate_multi<NN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384)); \
+    for (int pass = 0; pass < 2; pass++) { k_rate_multi<NN, NW><<<1, 128, 16384>>>(2000, cyc, status); CK(cudaDeviceSynchronize()); } \
+    printf("rate %d issuing warps, M=128 N=%d: %.1f cycles per MMA aggregate (%d MMAs), status %d\n", NW, NN, \
+           (double) cyc[0] / (36.0 * 2000 * NW), 36 * 2000 * NW, *status); } while (0)
+  RATE_MULTI(16, 1); RATE_MULTI(16, 2); RATE_MULTI(16, 4); RATE_MULTI(32, 2);
   const size_t smem_rate = 65536 + 8192;
   CK(cudaFuncSetAttribute(k_rate<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_rate));
   CK(cudaFuncSetAttribute(k_rate<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_rate));
