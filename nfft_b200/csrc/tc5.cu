@@ -888,6 +888,9 @@ tc5_spread_kernel(float2 *__restrict__ G, const float2 *__restrict__ ft, const u
 
 // NFFTCU_OPT_TC5: 0 auto (B and B^T on the tcgen05 kernels) | 1 off | 2 B only | 3 B and B^T
 bool tc5_selected(const nfftcu_ctx *c) {
+  // env NFFT_B200_TC5=0: the switch for callers of the plan API, who cannot reach nfftcu_set_option
+  static const bool env_off = getenv("NFFT_B200_TC5") && atoi(getenv("NFFT_B200_TC5")) == 0;
+  if (env_off && c->opt_tc5 == 0) return false;
   if (c->prec != NFFTCU_FLOAT || c->opt_tc5 == 1 || !mma3d_supported(c)) return false;
   if (!(c->opt_b_kernel == 0)) return false;   // an explicit kernel choice (generic / pencils / DMMA) wins
   return c->opt_tc5 != 1;
